@@ -1,0 +1,427 @@
+// K2/K3/K4/K11: reweighting, ESS sums, device-driven beta bisection, resampling
+// weights + evidence bookkeeping, importance weights.  All HBM-bound streaming
+// reductions: coalesced fp64 loads, 4 independent loads in flight per thread,
+// warp-shuffle + shared-memory block reduce, deterministic last-block grid reduce.
+//
+// Reference arithmetic replaced (paths under /root/reference):
+//   src/aspire/samples.py:1221-1249  unnormalized_log_weights / log_weights
+//   src/aspire/utils.py:248-255,510-512  logsumexp / effective_sample_size
+//   src/aspire/samplers/smc/base.py:166-186  determine_beta bisection
+//   src/aspire/samples.py:1226-1242  log_evidence_ratio[_variance]
+//   src/aspire/samples.py:457-475    Samples.compute_weights
+#include <math.h>
+
+#include "common.cuh"
+
+namespace asp {
+
+constexpr int kUnroll = 4;
+
+// ---------------------------------------------------------------------------
+// K2: d = (logL + logP) - logq, with min / max / NaN / +inf statistics
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) reweight_kernel(const double* __restrict__ ll, const double* __restrict__ lp,
+                                                          const double* __restrict__ lq, int64_t n,
+                                                          double* __restrict__ d, double* __restrict__ stats,
+                                                          ReduceWs* ws) {
+    __shared__ double smem[4 * 32];
+    double v[4] = {identity(OP_MIN), identity(OP_MAX), 0.0, 0.0};
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + (kUnroll - 1) * stride < n; i += kUnroll * stride) {
+        double a[kUnroll], b[kUnroll], c[kUnroll];
+#pragma unroll
+        for (int k = 0; k < kUnroll; ++k) {
+            a[k] = ld_stream(ll + i + k * stride);
+            b[k] = ld_stream(lp + i + k * stride);
+            c[k] = ld_stream(lq + i + k * stride);
+        }
+#pragma unroll
+        for (int k = 0; k < kUnroll; ++k) {
+            double t = (a[k] + b[k]) - c[k];
+            d[i + k * stride] = t;
+            v[0] = fmin(v[0], t);
+            v[1] = fmax(v[1], t);
+            v[2] += (t != t) ? 1.0 : 0.0;
+            v[3] += (t == identity(OP_MIN)) ? 1.0 : 0.0;
+        }
+    }
+    for (; i < n; i += stride) {
+        double t = (ll[i] + lp[i]) - lq[i];
+        d[i] = t;
+        v[0] = fmin(v[0], t);
+        v[1] = fmax(v[1], t);
+        v[2] += (t != t) ? 1.0 : 0.0;
+        v[3] += (t == identity(OP_MIN)) ? 1.0 : 0.0;
+    }
+    const int ops[4] = {OP_MIN, OP_MAX, OP_SUM, OP_SUM};
+    grid_reduce<4>(v, ops, ws, smem, [&](double(&r)[4]) {
+        stats[0] = r[0];
+        stats[1] = r[1];
+        stats[2] = r[2];
+        stats[3] = r[3];
+    });
+}
+
+// ---------------------------------------------------------------------------
+// K3: sums for ESS at NB candidate betas in one pass
+// ---------------------------------------------------------------------------
+template <int NB>
+__global__ void __launch_bounds__(kBlock) ess_sums_kernel(const double* __restrict__ d, int64_t n,
+                                                          const double* __restrict__ dbeta,
+                                                          const double* __restrict__ stats, double* __restrict__ sums,
+                                                          ReduceWs* ws) {
+    __shared__ double smem[2 * NB * 32];
+    double db[NB], c[NB], v[2 * NB];
+    int ops[2 * NB];
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+        db[k] = dbeta[k];
+        c[k] = db[k] * (db[k] >= 0.0 ? stats[1] : stats[0]);
+        v[2 * k] = v[2 * k + 1] = 0.0;
+        ops[2 * k] = ops[2 * k + 1] = OP_SUM;
+    }
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + (kUnroll - 1) * stride < n; i += kUnroll * stride) {
+        double x[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) x[u] = ld_stream(d + i + u * stride);
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+#pragma unroll
+            for (int k = 0; k < NB; ++k) {
+                double e = exp(db[k] * x[u] - c[k]);
+                v[2 * k] += e;
+                v[2 * k + 1] += e * e;
+            }
+        }
+    }
+    for (; i < n; i += stride) {
+        double x = d[i];
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+            double e = exp(db[k] * x - c[k]);
+            v[2 * k] += e;
+            v[2 * k + 1] += e * e;
+        }
+    }
+    grid_reduce<2 * NB>(v, ops, ws, smem, [&](double(&r)[2 * NB]) {
+#pragma unroll
+        for (int k = 0; k < 2 * NB; ++k) sums[k] = r[k];
+    });
+}
+
+// ---------------------------------------------------------------------------
+// device-driven bisection
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void beta_decide(asp_beta_state_t* st) {
+    if (st->phase == 2) return;
+    const double eff = (st->s1 * st->s1 / st->s2) / st->n_total;
+    if (st->phase == 0) {
+        st->eff_beta_max = eff;
+        if (eff >= st->target_eff) {  // smc/base.py:174-175
+            st->beta_min = 1.0;
+            st->s1_min = st->s1;
+            st->s2_min = st->s2;
+            st->min_valid = 1;
+        }
+        st->phase = 1;
+    } else {
+        if (eff >= st->target_eff) {  // smc/base.py:182-185
+            st->beta_min = st->beta_try;
+            st->s1_min = st->s1;
+            st->s2_min = st->s2;
+            st->min_valid = 1;
+        } else {
+            st->beta_max = st->beta_try;
+        }
+    }
+    st->n_evals += 1;
+    if (st->beta_max - st->beta_min > st->tol) {  // smc/base.py:177-178
+        st->beta_try = 0.5 * (st->beta_max + st->beta_min);
+    } else {
+        st->phase = 2;
+    }
+}
+
+__global__ void beta_init_kernel(asp_beta_state_t* st, double beta_prev, double target_eff, double tol, double n_total,
+                                 const double* stats) {
+    st->beta_prev = beta_prev;
+    st->beta_min = beta_prev;
+    st->beta_max = 1.0;
+    st->target_eff = target_eff;
+    st->tol = tol;
+    st->n_total = n_total;
+    st->beta_try = 1.0;
+    st->s1 = st->s2 = 0.0;
+    st->eff_beta_max = 0.0;
+    st->s1_min = st->s2_min = 0.0;
+    st->d_min = stats[0];
+    st->d_max = stats[1];
+    st->phase = 0;
+    st->n_evals = 0;
+    st->min_valid = 0;
+    st->reserved = 0;
+}
+
+__global__ void beta_decide_kernel(asp_beta_state_t* st) { beta_decide(st); }
+
+__global__ void __launch_bounds__(kBlock) beta_pass_kernel(const double* __restrict__ d, int64_t n,
+                                                           asp_beta_state_t* st, int fused_decide, ReduceWs* ws) {
+    __shared__ double smem[2 * 32];
+    if (st->phase == 2) return;  // uniform across the grid: phase only changes in the last block's epilogue
+    const double db = st->beta_try - st->beta_prev;
+    const double c = db * (db >= 0.0 ? st->d_max : st->d_min);
+    double v[2] = {0.0, 0.0};
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + (kUnroll - 1) * stride < n; i += kUnroll * stride) {
+        double x[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) x[u] = ld_stream(d + i + u * stride);
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            double e = exp(db * x[u] - c);
+            v[0] += e;
+            v[1] += e * e;
+        }
+    }
+    for (; i < n; i += stride) {
+        double e = exp(db * d[i] - c);
+        v[0] += e;
+        v[1] += e * e;
+    }
+    const int ops[2] = {OP_SUM, OP_SUM};
+    grid_reduce<2>(v, ops, ws, smem, [&](double(&r)[2]) {
+        st->s1 = r[0];
+        st->s2 = r[1];
+        if (fused_decide) beta_decide(st);
+    });
+}
+
+// ---------------------------------------------------------------------------
+// resampling weights, evidence-variance sum, exact-scan tile statistics
+// one block handles one ASP_CDF_TILE (=2048) tile per iteration
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) smc_weights_kernel(const double* __restrict__ d, int64_t n, double dbeta,
+                                                             double c, double s1, double n_total,
+                                                             double* __restrict__ p, double* __restrict__ result,
+                                                             double* __restrict__ tile_stats, ReduceWs* ws) {
+    __shared__ double smem[2 * 32];
+    constexpr int kItems = ASP_CDF_TILE / kBlock;  // 8
+    const double mean = s1 / n_total;
+    const int64_t n_tiles = (n + ASP_CDF_TILE - 1) / ASP_CDF_TILE;
+    double v[2] = {0.0, 0.0};
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t base = tile * ASP_CDF_TILE;
+        double x[kItems];
+#pragma unroll
+        for (int k = 0; k < kItems; ++k) {
+            int64_t i = base + k * kBlock + threadIdx.x;
+            x[k] = i < n ? ld_stream(d + i) : identity(OP_MAX);  // -inf -> weight 0
+        }
+        double t[2] = {0.0, 0.0};  // tile sum, tile max
+#pragma unroll
+        for (int k = 0; k < kItems; ++k) {
+            int64_t i = base + k * kBlock + threadIdx.x;
+            double u = exp(dbeta * x[k] - c);
+            double w = u / s1;
+            if (i < n) {
+                if (p) p[i] = w;
+                double dv = u - mean;
+                v[0] += dv * dv;
+                v[1] += w;
+                t[0] += w;
+                t[1] = fmax(t[1], w);
+            }
+        }
+        if (tile_stats) {
+            const int tops[2] = {OP_SUM, OP_MAX};
+            block_reduce<2>(t, tops, smem);
+            if (threadIdx.x == 0) {
+                tile_stats[2 * tile] = t[0];
+                tile_stats[2 * tile + 1] = t[1];
+            }
+        }
+    }
+    const int ops[2] = {OP_SUM, OP_SUM};
+    grid_reduce<2>(v, ops, ws, smem, [&](double(&r)[2]) {
+        result[0] = r[0];
+        result[1] = r[1];
+        result[2] = 0.0;
+        result[3] = 0.0;
+    });
+}
+
+// ---------------------------------------------------------------------------
+// K11: importance weights (three stream-ordered passes)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) imp_logw_kernel(const double* __restrict__ ll, const double* __restrict__ lp,
+                                                          const double* __restrict__ lq, int64_t n,
+                                                          double* __restrict__ log_w, double* __restrict__ result,
+                                                          ReduceWs* ws) {
+    __shared__ double smem[2 * 32];
+    double v[2] = {identity(OP_MAX), 0.0};
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double t = ll[i] + lp[i] - lq[i];  // samples.py:459
+        log_w[i] = t;
+        v[0] = fmax(v[0], t);
+        v[1] += (t != t) ? 1.0 : 0.0;
+    }
+    const int ops[2] = {OP_MAX, OP_SUM};
+    grid_reduce<2>(v, ops, ws, smem, [&](double(&r)[2]) {
+        result[5] = r[0];
+        result[6] = r[1];
+        result[7] = 0.0;
+    });
+}
+
+__global__ void __launch_bounds__(kBlock) imp_sums_kernel(const double* __restrict__ log_w, int64_t n,
+                                                          double* __restrict__ weights, double* __restrict__ result,
+                                                          ReduceWs* ws) {
+    __shared__ double smem[2 * 32];
+    const double m = result[5];
+    double v[2] = {0.0, 0.0};
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double lw = log_w[i];
+        double e = exp(lw - m);
+        weights[i] = exp(lw);  // samples.py:463 (unshifted)
+        v[0] += e;
+        v[1] += e * e;
+    }
+    const int ops[2] = {OP_SUM, OP_SUM};
+    grid_reduce<2>(v, ops, ws, smem, [&](double(&r)[2]) {
+        double log_z = (m + log(r[0])) - log((double)n);  // samples.py:460-462
+        result[0] = log_z;
+        result[1] = exp(log_z);
+        result[4] = r[0] * r[0] / r[1];  // samples.py:472-475
+    });
+}
+
+__global__ void __launch_bounds__(kBlock) imp_err_kernel(const double* __restrict__ weights, int64_t n,
+                                                         double* __restrict__ result, ReduceWs* ws) {
+    __shared__ double smem[32];
+    const double z = result[1];
+    double v[1] = {0.0};
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double t = weights[i] - z;
+        v[0] += t * t;
+    }
+    const int ops[1] = {OP_SUM};
+    grid_reduce<1>(v, ops, ws, smem, [&](double(&r)[1]) {
+        double nn = (double)n;
+        double err = sqrt(r[0] / (nn * (nn - 1.0)));  // samples.py:465-467
+        result[2] = err;
+        result[3] = fabs(err / z);  // samples.py:468-470
+    });
+}
+
+}  // namespace asp
+
+using namespace asp;
+
+extern "C" {
+
+int asp_reweight(const double* d_log_l, const double* d_log_p, const double* d_log_q, int64_t n, double* d_d,
+                 double* d_stats, void* ws, void* stream) {
+    ASP_DEVICE_OR_RETURN();
+    ASP_REQUIRE(d_log_l && d_log_p && d_log_q && d_d && d_stats && ws, "null pointer");
+    ASP_REQUIRE(n > 0, "n must be positive");
+    reweight_kernel<<<grid_for(n, kUnroll), kBlock, 0, (cudaStream_t)stream>>>(d_log_l, d_log_p, d_log_q, n, d_d,
+                                                                               d_stats, (ReduceWs*)ws);
+    return check_launch("asp_reweight");
+}
+
+int asp_ess_sums(const double* d_d, int64_t n, const double* d_dbeta, int n_beta, const double* d_stats,
+                 double* d_sums, void* ws, void* stream) {
+    ASP_DEVICE_OR_RETURN();
+    ASP_REQUIRE(d_d && d_dbeta && d_stats && d_sums && ws, "null pointer");
+    ASP_REQUIRE(n > 0, "n must be positive");
+    ASP_REQUIRE(n_beta >= 1 && n_beta <= 8, "n_beta must be in [1, 8]");
+    const int g = grid_for(n, kUnroll);
+    cudaStream_t s = (cudaStream_t)stream;
+    ReduceWs* w = (ReduceWs*)ws;
+    switch (n_beta) {
+        case 1: ess_sums_kernel<1><<<g, kBlock, 0, s>>>(d_d, n, d_dbeta, d_stats, d_sums, w); break;
+        case 2: ess_sums_kernel<2><<<g, kBlock, 0, s>>>(d_d, n, d_dbeta, d_stats, d_sums, w); break;
+        case 3: ess_sums_kernel<3><<<g, kBlock, 0, s>>>(d_d, n, d_dbeta, d_stats, d_sums, w); break;
+        case 4: ess_sums_kernel<4><<<g, kBlock, 0, s>>>(d_d, n, d_dbeta, d_stats, d_sums, w); break;
+        case 5: ess_sums_kernel<5><<<g, kBlock, 0, s>>>(d_d, n, d_dbeta, d_stats, d_sums, w); break;
+        case 6: ess_sums_kernel<6><<<g, kBlock, 0, s>>>(d_d, n, d_dbeta, d_stats, d_sums, w); break;
+        case 7: ess_sums_kernel<7><<<g, kBlock, 0, s>>>(d_d, n, d_dbeta, d_stats, d_sums, w); break;
+        default: ess_sums_kernel<8><<<g, kBlock, 0, s>>>(d_d, n, d_dbeta, d_stats, d_sums, w); break;
+    }
+    return check_launch("asp_ess_sums");
+}
+
+int asp_beta_search_max_passes(double beta_prev, double tol) {
+    double width = 1.0 - beta_prev;
+    int k = 1;  // the beta = 1 evaluation
+    if (!(tol > 0.0)) return 1 + 1100;
+    while (width > tol && k < 1100) {
+        width *= 0.5;
+        ++k;
+    }
+    return k + 2;
+}
+
+int asp_beta_search_init(asp_beta_state_t* d_state, double beta_prev, double target_eff, double tol, double n_total,
+                         const double* d_stats, void* stream) {
+    ASP_DEVICE_OR_RETURN();
+    ASP_REQUIRE(d_state && d_stats, "null pointer");
+    beta_init_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(d_state, beta_prev, target_eff, tol, n_total, d_stats);
+    return check_launch("asp_beta_search_init");
+}
+
+int asp_beta_search_pass(const double* d_d, int64_t n, asp_beta_state_t* d_state, int fused_decide, void* ws,
+                         void* stream) {
+    ASP_DEVICE_OR_RETURN();
+    ASP_REQUIRE(d_d && d_state && ws, "null pointer");
+    ASP_REQUIRE(n > 0, "n must be positive");
+    beta_pass_kernel<<<grid_for(n, kUnroll), kBlock, 0, (cudaStream_t)stream>>>(d_d, n, d_state, fused_decide,
+                                                                                (ReduceWs*)ws);
+    return check_launch("asp_beta_search_pass");
+}
+
+int asp_beta_search_decide(asp_beta_state_t* d_state, void* stream) {
+    ASP_DEVICE_OR_RETURN();
+    ASP_REQUIRE(d_state, "null pointer");
+    beta_decide_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(d_state);
+    return check_launch("asp_beta_search_decide");
+}
+
+int asp_smc_weights(const double* d_d, int64_t n, double dbeta, double c, double s1, double n_total, double* d_p,
+                    double* d_result, double* d_tile_stats, void* ws, void* stream) {
+    ASP_DEVICE_OR_RETURN();
+    ASP_REQUIRE(d_d && d_result && ws, "null pointer");
+    ASP_REQUIRE(n > 0, "n must be positive");
+    const int64_t n_tiles = (n + ASP_CDF_TILE - 1) / ASP_CDF_TILE;
+    int g = (int)(n_tiles < (int64_t)kNumSMs * 8 ? n_tiles : (int64_t)kNumSMs * 8);
+    smc_weights_kernel<<<g, kBlock, 0, (cudaStream_t)stream>>>(d_d, n, dbeta, c, s1, n_total, d_p, d_result,
+                                                               d_tile_stats, (ReduceWs*)ws);
+    return check_launch("asp_smc_weights");
+}
+
+size_t asp_importance_workspace_bytes(int64_t n) {
+    (void)n;
+    return sizeof(ReduceWs);
+}
+
+int asp_importance_weights(const double* d_log_l, const double* d_log_p, const double* d_log_q, int64_t n,
+                           double* d_log_w, double* d_weights, double* d_result, void* ws, void* stream) {
+    ASP_DEVICE_OR_RETURN();
+    ASP_REQUIRE(d_log_l && d_log_p && d_log_q && d_log_w && d_weights && d_result && ws, "null pointer");
+    ASP_REQUIRE(n > 1, "n must be at least 2");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int g = grid_for(n, kUnroll);
+    imp_logw_kernel<<<g, kBlock, 0, s>>>(d_log_l, d_log_p, d_log_q, n, d_log_w, d_result, (ReduceWs*)ws);
+    imp_sums_kernel<<<g, kBlock, 0, s>>>(d_log_w, n, d_weights, d_result, (ReduceWs*)ws);
+    imp_err_kernel<<<g, kBlock, 0, s>>>(d_weights, n, d_result, (ReduceWs*)ws);
+    return check_launch("asp_importance_weights");
+}
+
+}  // extern "C"

@@ -1,0 +1,130 @@
+// K6 ancestor search and K7 row gather.
+//
+// numpy Generator.choice (called at /root/reference/src/aspire/samples.py:1278):
+//   idx = cdf.searchsorted(u, side='right')     -> asp_search_multinomial
+// and the fancy-index copies of samples.py:1279-1287 -> asp_gather_rows.
+// Both are HBM/L2 bound: the search is a branch-free binary search whose upper
+// levels stay L2-resident; the gather moves whole rows with 128-bit accesses,
+// one sub-warp group per row so every row is a single contiguous burst.
+#include "common.cuh"
+
+namespace asp {
+
+// count of cdf[k] <= u  (upper bound), branch-free
+__device__ __forceinline__ int64_t upper_bound(const double* __restrict__ cdf, int64_t n, double u) {
+    int64_t lo = 0, len = n;
+    while (len > 0) {
+        int64_t half = len >> 1;
+        double v = __ldg(cdf + lo + half);
+        bool right = v <= u;
+        lo = right ? lo + half + 1 : lo;
+        len = right ? len - half - 1 : half;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(kBlock) search_multinomial_kernel(const double* __restrict__ cdf, int64_t n,
+                                                                    const double* __restrict__ u, int64_t m,
+                                                                    int64_t* __restrict__ idx) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += stride)
+        idx[j] = upper_bound(cdf, n, ld_stream(u + j));
+}
+
+__global__ void __launch_bounds__(kBlock) search_systematic_kernel(const double* __restrict__ cdf, int64_t n,
+                                                                   double u0, int64_t j0, int64_t m, double m_total,
+                                                                   int64_t* __restrict__ idx) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += stride) {
+        // (j + u0) / m_total: one fp64 add, one IEEE division, no contraction
+        double uj = __ddiv_rn(__dadd_rn(__ll2double_rn(j0 + j), u0), m_total);
+        int64_t k = upper_bound(cdf, n, uj);
+        idx[j] = k < n - 1 ? k : n - 1;
+    }
+}
+
+// One group of G lanes moves one row of `dims` doubles (G * 2 doubles per step).
+template <int G>
+__global__ void __launch_bounds__(kBlock) gather_rows_kernel(const double* __restrict__ x, int dims,
+                                                             const int64_t* __restrict__ idx, int64_t m,
+                                                             double* __restrict__ xo, const double* __restrict__ l,
+                                                             const double* __restrict__ p, const double* __restrict__ q,
+                                                             double* __restrict__ lo, double* __restrict__ po,
+                                                             double* __restrict__ qo) {
+    const int lane = threadIdx.x % G;
+    const int64_t groups = ((int64_t)gridDim.x * blockDim.x) / G;
+    const bool vec = (dims % 2 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(xo) & 15) == 0);
+    for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G; r < m; r += groups) {
+        const int64_t a = idx[r];
+        const double* src = x + a * dims;
+        double* dst = xo + r * dims;
+        if (vec) {
+            for (int c = 2 * lane; c < dims; c += 2 * G) {
+                double2 v = *reinterpret_cast<const double2*>(src + c);
+                st_stream2(dst + c, v.x, v.y);
+            }
+        } else {
+            for (int c = lane; c < dims; c += G) dst[c] = src[c];
+        }
+        if (lane == 0) {
+            if (l) lo[r] = l[a];
+            if (p) po[r] = p[a];
+            if (q) qo[r] = q[a];
+        }
+    }
+}
+
+}  // namespace asp
+
+using namespace asp;
+
+extern "C" {
+
+int asp_search_multinomial(const double* d_cdf, int64_t n_cdf, const double* d_u, int64_t m, int64_t* d_idx,
+                           void* stream) {
+    ASP_DEVICE_OR_RETURN();
+    ASP_REQUIRE(d_cdf && d_u && d_idx, "null pointer");
+    ASP_REQUIRE(n_cdf > 0 && m > 0, "sizes must be positive");
+    search_multinomial_kernel<<<grid_for(m, 1), kBlock, 0, (cudaStream_t)stream>>>(d_cdf, n_cdf, d_u, m, d_idx);
+    return check_launch("asp_search_multinomial");
+}
+
+int asp_search_systematic(const double* d_cdf, int64_t n_cdf, double u0, int64_t j0, int64_t m, int64_t m_total,
+                          int64_t* d_idx, void* stream) {
+    ASP_DEVICE_OR_RETURN();
+    ASP_REQUIRE(d_cdf && d_idx, "null pointer");
+    ASP_REQUIRE(n_cdf > 0 && m > 0 && m_total > 0, "sizes must be positive");
+    ASP_REQUIRE(u0 >= 0.0 && u0 < 1.0, "u0 must be in [0, 1)");
+    search_systematic_kernel<<<grid_for(m, 1), kBlock, 0, (cudaStream_t)stream>>>(d_cdf, n_cdf, u0, j0, m,
+                                                                                  (double)m_total, d_idx);
+    return check_launch("asp_search_systematic");
+}
+
+int asp_gather_rows(const double* d_x, int32_t dims, const int64_t* d_idx, int64_t m, double* d_x_out,
+                    const double* d_l, const double* d_p, const double* d_q, double* d_l_out, double* d_p_out,
+                    double* d_q_out, void* stream) {
+    ASP_DEVICE_OR_RETURN();
+    ASP_REQUIRE(d_x && d_idx && d_x_out, "null pointer");
+    ASP_REQUIRE(dims > 0 && m > 0, "sizes must be positive");
+    ASP_REQUIRE((!d_l || d_l_out) && (!d_p || d_p_out) && (!d_q || d_q_out), "log output missing");
+    cudaStream_t s = (cudaStream_t)stream;
+    // lanes per row: each lane moves 16 B per step
+    int g = 1;
+    while (g < 32 && g * 2 < dims) g <<= 1;
+    const int grid = grid_for(m * g, 1);
+#define ASP_GATHER(G) \
+    gather_rows_kernel<G><<<grid, kBlock, 0, s>>>(d_x, dims, d_idx, m, d_x_out, d_l, d_p, d_q, d_l_out, d_p_out, d_q_out)
+    switch (g) {
+        case 1: ASP_GATHER(1); break;
+        case 2: ASP_GATHER(2); break;
+        case 4: ASP_GATHER(4); break;
+        case 8: ASP_GATHER(8); break;
+        case 16: ASP_GATHER(16); break;
+        default: ASP_GATHER(32); break;
+    }
+#undef ASP_GATHER
+    return check_launch("asp_gather_rows");
+}
+
+}  // extern "C"

@@ -1,0 +1,261 @@
+/*
+ * aspire_b200 - C-ABI of the B200-native SMC particle engine.
+ *
+ * This is the drop-in boundary for the ONE hot path of mj-will/aspire this
+ * repository rebuilds: importance reweighting, log-sum-exp /
+ * ESS, adaptive-beta bisection, exact multinomial / systematic resampling, the
+ * pCN mutation sweep and the built-in benchmark log-densities.  The reference
+ * is pure Python and has no FFI of its own; each entry point below names the
+ * reference code (path:line under /root/reference) whose arithmetic it
+ * replaces, and INTEGRATION.md shows the ctypes binding a maintainer of the
+ * reference would add.
+ *
+ * Conventions
+ *  - plain C types only; every pointer named d_* is a DEVICE pointer (fp64 /
+ *    int64, contiguous, row-major, 16-byte aligned), every h_* a host pointer;
+ *  - the caller owns all memory; scratch comes from the caller through
+ *    `ws` (size from the matching *_workspace_bytes, 256-byte aligned);
+ *  - `stream` is a cudaStream_t passed as void*; all launches are
+ *    asynchronous on it, nothing synchronises unless stated;
+ *  - every function returns 0 on success, a negative asp_status otherwise,
+ *    and never throws; asp_last_error() is thread-local;
+ *  - there is NO CPU fallback: without an sm_100 device every compute entry
+ *    point fails with ASP_ERR_DEVICE.
+ */
+#ifndef ASPIRE_B200_H
+#define ASPIRE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* the library is built with -fvisibility=hidden: only these entry points are exported */
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define ASP_VERSION 100 /* 0.1.0 */
+
+enum asp_status {
+    ASP_OK = 0,
+    ASP_ERR_ARG = -1,     /* bad argument (null pointer, size, alignment)      */
+    ASP_ERR_DEVICE = -2,  /* no sm_100 device / wrong architecture             */
+    ASP_ERR_CUDA = -3,    /* CUDA runtime error, see asp_last_error()          */
+    ASP_ERR_NUMERIC = -4  /* reserved: numeric guards are reported in-band     */
+};
+
+int asp_version(void);
+const char* asp_last_error(void);
+/* 0 when the current device is compute capability 10.x, else ASP_ERR_DEVICE. */
+int asp_device_check(void);
+
+/* ---- built-in log-densities (K1) ---------------------------------------
+ * The reference takes user callables (src/aspire/samplers/base.py:81-91); these
+ * are the synthetic benchmark targets of SURVEY 8d, following the reference's
+ * fixtures README.md:47-52, tests/integration_tests/conftest.py:84-108,
+ * examples/smc_example.py:40-58.
+ *   GAUSSIAN   s0 - 1/2 sum_j ((x_j - p0_j) * p1_j)^2        p0=mean[D] p1=1/sigma[D]
+ *   ROSENBROCK -sum_{j<D-1}[s0 (x_{j+1}-x_j^2)^2 + (s1-x_j)^2] / s2
+ *   GMM        logsumexp_k[p2_k - 1/2 p1_k^2 |x-p0_k|^2]     p0=means[K,D] p1=1/sigma[K] p2=logc[K]
+ *   UNIFORM    s0 inside the open box (p0=lo[D], p1=hi[D]), -inf outside
+ */
+enum asp_density_kind {
+    ASP_DENSITY_GAUSSIAN = 0,
+    ASP_DENSITY_ROSENBROCK = 1,
+    ASP_DENSITY_GMM = 2,
+    ASP_DENSITY_UNIFORM = 3
+};
+
+typedef struct asp_density {
+    int32_t kind;
+    int32_t dims;
+    int32_t n_comp; /* GMM only (<= 32) */
+    int32_t reserved;
+    const double* p0; /* device */
+    const double* p1; /* device */
+    const double* p2; /* device */
+    double s0, s1, s2;
+} asp_density_t;
+
+/* out[i] = log density(x[i, :]);  x is [n, dims] row-major. */
+int asp_logdensity(const asp_density_t* dens, const double* d_x, int64_t n, double* d_out, void* stream);
+
+/* ---- importance weights (K11) -------------------------------------------
+ * Samples.compute_weights, src/aspire/samples.py:457-475.
+ * d_log_w = logL + logP - logq;  d_weights = exp(log_w) (unshifted, as the
+ * reference);  d_result[8] = {log_evidence, evidence, evidence_error,
+ * log_evidence_error, effective_sample_size, max log_w, n_nan, reserved}. */
+size_t asp_importance_workspace_bytes(int64_t n);
+int asp_importance_weights(const double* d_log_l, const double* d_log_p, const double* d_log_q, int64_t n,
+                           double* d_log_w, double* d_weights, double* d_result, void* ws, void* stream);
+
+/* ---- SMC reweighting (K2) -----------------------------------------------
+ * d[i] = (logL + logP) - logq, the per-particle slope of
+ * SMCSamples.unnormalized_log_weights, src/aspire/samples.py:1221-1224
+ * ((beta-beta0)*d == (beta0-beta)*logq + (beta-beta0)*(logL+logP)).
+ * d_stats[4] = {min d, max d, number of NaN, number of +inf}, over the LOCAL
+ * slice; multi-GPU callers all-reduce it (min, max, sum, sum). */
+size_t asp_reduce_workspace_bytes(void);
+int asp_reweight(const double* d_log_l, const double* d_log_p, const double* d_log_q, int64_t n, double* d_d,
+                 double* d_stats, void* ws, void* stream);
+
+/* ---- ESS(beta) sums (K3) ------------------------------------------------
+ * effective_sample_size(log_weights(beta)), src/aspire/utils.py:248-255,510-512:
+ * for each k < n_beta:  c_k = dbeta_k * (dbeta_k >= 0 ? d_max : d_min),
+ * d_sums[2k] = sum_i exp(dbeta_k d_i - c_k), d_sums[2k+1] = sum_i exp(2(dbeta_k d_i - c_k)).
+ * ESS = sums[2k]^2 / sums[2k+1].  d_dbeta / d_stats are device arrays so the
+ * call can sit in a stream / CUDA graph with no host round trip. n_beta <= 8. */
+int asp_ess_sums(const double* d_d, int64_t n, const double* d_dbeta, int n_beta, const double* d_stats,
+                 double* d_sums, void* ws, void* stream);
+
+/* ---- adaptive-beta bisection, device-driven (a5) ------------------------
+ * SMCSampler.determine_beta, src/aspire/samplers/smc/base.py:166-186.  The state
+ * lives on the device; asp_beta_search_init seeds it, each asp_beta_search_pass
+ * evaluates ESS at state.beta_try over the LOCAL slice (sums land in
+ * state.s1/s2), asp_beta_search_decide applies the reference's `>=` decision
+ * and picks the next midpoint.  Single GPU: pass(fused_decide=1) does both.
+ * Multi GPU: pass(0) -> all-reduce(state.s1,s2; sum) -> decide.  Passes after
+ * convergence are no-ops, so the host launches a fixed count
+ * (asp_beta_search_max_passes) without synchronising. */
+typedef struct asp_beta_state {
+    double beta_prev, beta_min, beta_max; /* bisection bracket                     */
+    double target_eff, tol, n_total;      /* target efficiency, tolerance, global N */
+    double beta_try;                      /* beta the next pass evaluates           */
+    double s1, s2;                        /* sums of the last pass (all-reduce these) */
+    double eff_beta_max;                  /* ESS(1)/N (history.ess_target / N)      */
+    double s1_min, s2_min;                /* sums at beta_min (ESS(beta*) for free)  */
+    double d_min, d_max;                  /* global min / max of d                  */
+    int32_t phase;                        /* 0: evaluating beta=1, 1: bisecting, 2: done */
+    int32_t n_evals;
+    int32_t min_valid;                    /* 1 when s1_min/s2_min belong to beta_min */
+    int32_t reserved;
+} asp_beta_state_t;
+
+int asp_beta_search_max_passes(double beta_prev, double tol);
+int asp_beta_search_init(asp_beta_state_t* d_state, double beta_prev, double target_eff, double tol,
+                         double n_total, const double* d_stats, void* stream);
+int asp_beta_search_pass(const double* d_d, int64_t n, asp_beta_state_t* d_state, int fused_decide, void* ws,
+                         void* stream);
+int asp_beta_search_decide(asp_beta_state_t* d_state, void* stream);
+
+/* ---- resampling weights + evidence bookkeeping (K4/K5 front end) --------
+ * p_i = exp(dbeta d_i - c - log S1) (== exp(lw - lse(lw)), src/aspire/samples.py:1277),
+ * log_evidence_ratio[_variance] (src/aspire/samples.py:1226-1242).
+ * h_s1/h_s2/h_c are the GLOBAL sums and shift for this dbeta; n_total the
+ * global particle count.  d_p may be NULL (bookkeeping only).
+ * d_result[4] = {sum_i (u_i - mean u)^2 over the local slice, sum p, 0, 0}
+ * (variance = result[0] / n_total / (n_total * mean^2)); also fills the exact
+ * scan's per-tile sums / maxima (d_tile_stats, may be NULL). */
+int asp_smc_weights(const double* d_d, int64_t n, double dbeta, double c, double s1, double n_total,
+                    double* d_p, double* d_result, double* d_tile_stats, void* ws, void* stream);
+
+/* ---- exact CDF (K5) -----------------------------------------------------
+ * numpy Generator.choice(p=...) as called at src/aspire/samples.py:1278:
+ * cdf = cumsum(p) with SEQUENTIAL fp64 rounding, then cdf /= cdf[-1].
+ * Bit-identical to numpy for any non-negative finite p.
+ * Stages (so that ranks can interleave their collectives):
+ *   asp_cdf_tile_stats   per-tile sum/max of p          (skipped if asp_smc_weights filled them)
+ *   asp_cdf_plan         approximate prefixes -> per-tile binade / dirty flag
+ *   asp_cdf_aggregate    integer increment pairs of the clean tiles
+ *   asp_cdf_resolve      exact running sum at every tile start; dirty tiles done here
+ *   asp_cdf_write        cdf (normalised by d_total[0] when normalise != 0)
+ * d_carry[4]: in  {approx offset, running max, exact incoming sum, n_total}
+ *             out (after resolve) d_carry_out[2] = {exact outgoing sum, running max}.
+ * asp_cdf_exact runs all five on one GPU. */
+#define ASP_CDF_TILE 2048
+size_t asp_cdf_workspace_bytes(int64_t n);
+int asp_cdf_tile_stats(const double* d_p, int64_t n, void* ws, void* stream);
+int asp_cdf_set_tile_stats(const double* d_tile_stats, int64_t n, void* ws, void* stream);
+int asp_cdf_plan(int64_t n, const double* d_carry, void* ws, void* stream);
+int asp_cdf_aggregate(const double* d_p, int64_t n, void* ws, void* stream);
+int asp_cdf_resolve(const double* d_p, int64_t n, const double* d_carry, double* d_cdf, double* d_carry_out,
+                    void* ws, void* stream);
+int asp_cdf_write(const double* d_p, int64_t n, const double* d_total, int normalise, double* d_cdf, void* ws,
+                  void* stream);
+int asp_cdf_exact(const double* d_p, int64_t n, int normalise, double* d_cdf, void* ws, void* stream);
+/* d_info[4] (int64) = {n_tiles, n_dirty, n_phases, error_flags} of the last resolve. */
+int asp_cdf_info(void* ws, int64_t* h_info, void* stream);
+
+/* ---- ancestor search (K6) -----------------------------------------------
+ * idx[j] = #{k : cdf[k] <= u[j]}  == cdf.searchsorted(u, side='right'), int64
+ * (numpy Generator.choice; src/aspire/samples.py:1278).  Systematic variant
+ * (extension): u_j = (j0 + j + u0) / m_total in fp64 (one add, one
+ * IEEE division), result clamped to n_cdf - 1.  A global offset is added to every
+ * index by the caller when the CDF is a shard of a larger one. */
+int asp_search_multinomial(const double* d_cdf, int64_t n_cdf, const double* d_u, int64_t m, int64_t* d_idx,
+                           void* stream);
+int asp_search_systematic(const double* d_cdf, int64_t n_cdf, double u0, int64_t j0, int64_t m,
+                          int64_t m_total, int64_t* d_idx, void* stream);
+
+/* ---- row gather (K7) ----------------------------------------------------
+ * x[idx], logL[idx], logP[idx], logq[idx] - src/aspire/samples.py:1279-1287.
+ * Any of the three log pointers (and its output) may be NULL. */
+int asp_gather_rows(const double* d_x, int32_t dims, const int64_t* d_idx, int64_t m, double* d_x_out,
+                    const double* d_l, const double* d_p, const double* d_q, double* d_l_out, double* d_p_out,
+                    double* d_q_out, void* stream);
+
+/* ---- pCN mutation (K8) --------------------------------------------------
+ * Replaces minipcn.Sampler.sample as driven by MiniPCNSMC.mutate
+ * (src/aspire/samplers/smc/minipcn.py:69-135) against the tempered target of
+ * src/aspire/samplers/smc/base.py:507-519.  Step spec: oracle/pcn.py (parity
+ * with minipcn itself is UNPINNED - the package is absent).
+ * Reference measure moments: d_moments[1 + 2*dims] = {sum w, sum w x_j, sum w x_j^2}
+ * over the local slice with w = exp(dbeta d - c). */
+size_t asp_moments_workspace_bytes(int32_t dims);
+int asp_weighted_moments(const double* d_x, int32_t dims, const double* d_d, int64_t n, double dbeta, double c,
+                         double* d_moments, void* ws, void* stream);
+
+typedef struct asp_pcn_params {
+    double beta;          /* inverse temperature of the target                  */
+    double rho;           /* pCN step, (0, 1]                                   */
+    const double* d_mu;   /* reference measure mean [dims]                      */
+    const double* d_sigma;/* reference measure std  [dims]                      */
+    int32_t n_moves;
+    int32_t noise_mode;   /* 0: Philox in-kernel, 1: supplied d_xi / d_log_u    */
+    uint64_t seed;        /* Philox key                                         */
+    uint32_t stream0;     /* Philox stream of move 0 (move t uses stream0 + t)  */
+    uint32_t reserved;
+    int64_t index0;       /* global index of local particle 0 (Philox counter)  */
+    const double* d_xi;   /* [n_moves, n, dims] normals (noise_mode 1)          */
+    const double* d_log_u;/* [n_moves, n] log-uniforms   (noise_mode 1)         */
+} asp_pcn_params_t;
+
+/* Fused sweep: particle i starts from row d_idx[i] of the inputs (d_idx NULL
+ * = identity, i.e. no resampling gather), runs n_moves accept/reject moves
+ * with built-in densities and writes the final state.  d_accepts[n_moves]
+ * (uint64) is incremented by the per-move accept counts (caller zeroes it). */
+int asp_pcn_sweep(const double* d_x, const double* d_log_l, const double* d_log_p, const double* d_log_q,
+                  const int64_t* d_idx, int64_t n, int32_t dims, const asp_density_t* like,
+                  const asp_density_t* prior, const asp_density_t* q, const asp_pcn_params_t* params,
+                  double* d_x_out, double* d_log_l_out, double* d_log_p_out, double* d_log_q_out,
+                  unsigned long long* d_accepts, void* stream);
+
+/* Unfused halves for user-supplied Python callables: propose x' for move
+ * `move`, then (after the caller evaluated the three logs at x') accept/reject
+ * in place. */
+int asp_pcn_propose(const double* d_x, int64_t n, int32_t dims, const asp_pcn_params_t* params, int32_t move,
+                    double* d_x_prop, void* stream);
+int asp_pcn_accept(double* d_x, double* d_log_l, double* d_log_p, double* d_log_q, const double* d_x_prop,
+                   const double* d_log_l_prop, const double* d_log_p_prop, const double* d_log_q_prop, int64_t n,
+                   int32_t dims, const asp_pcn_params_t* params, int32_t move, unsigned long long* d_accepts,
+                   void* stream);
+
+/* ---- counter-based RNG (K13) --------------------------------------------
+ * Philox4x32-10; layouts in oracle/philox.py.  uniform: fp64 in [0,1) with
+ * numpy's 53-bit conversion; normal: fp64 Box-Muller, out[n, dims] =
+ * mean_j + sigma_j * z (d_mean / d_sigma may be NULL for standard normals). */
+int asp_philox_uniform(uint64_t seed, uint32_t stream_id, int64_t index0, int64_t n, double* d_out, void* stream);
+int asp_philox_normal(uint64_t seed, uint32_t stream_id, int64_t index0, int64_t n, int32_t dims,
+                      const double* d_mean, const double* d_sigma, double* d_out, void* stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ASPIRE_B200_H */

@@ -1,0 +1,165 @@
+"""Generate ``tests/golden/*.npz`` by running the UNMODIFIED reference.
+
+Run in the dev container only (needs ``/root/reference``)::
+
+    python -m oracle.make_golden
+
+The reference's own tests hold closed-form known answers for this path
+(``tests/test_samples.py:162-185, 637-670, 673-759``; restated in
+``tests/test_reference_kats.py``) but no golden index / beta-schedule / logZ
+vectors, so these fixtures are produced from the reference itself:
+its ``SMCSamples`` methods, ``Samples.compute_weights``,
+``SMCSampler.determine_beta`` and the full ``SMCSampler.sample`` loop with an
+injected ``mutate`` (our restated pCN, because ``minipcn`` is absent).
+"""
+
+from __future__ import annotations
+
+import logging
+import os
+
+import numpy as np
+
+from . import pcn, problems, ref_shim
+from . import densities as dn
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+class _Flow:
+    """Duck-typed proposal for the reference sampler: diagonal Gaussian."""
+
+    def __init__(self, q, rng, xp):
+        self.q, self.rng, self.xp = q, rng, xp
+
+    def sample_and_log_prob(self, n):
+        x = self.q["mean"] + self.q["sigma"] * self.rng.standard_normal((n, len(self.q["mean"])))
+        return x, dn.evaluate(self.q, x)
+
+    def log_prob(self, x):
+        return dn.evaluate(self.q, np.asarray(x))
+
+
+def _reference_objects():
+    ref_shim.import_reference()
+    import array_api_compat.numpy as xp
+    from aspire.samplers.smc.base import SMCSampler
+    from aspire.samples import Samples, SMCSamples
+    from aspire.utils import effective_sample_size
+
+    return xp, SMCSampler, Samples, SMCSamples, effective_sample_size
+
+
+def reweight_case(name, problem, n, seed, beta0, target_eff=0.5, tol=1e-6, min_step=0.0, max_step=1.0):
+    xp, SMCSampler, Samples, SMCSamples, ess_fn = _reference_objects()
+    x, ll, lp, lq = problems.draw(problem, n, seed)
+    smc = SMCSamples(x=x, log_likelihood=ll, log_prior=lp, log_q=lq, beta=beta0, xp=xp, dtype="float64")
+
+    class _S(SMCSampler):
+        def mutate(self, particles, beta, n_steps=None):  # pragma: no cover
+            return particles
+
+    s = _S(lambda s_: dn.evaluate(problem["like"], s_.x), lambda s_: dn.evaluate(problem["prior"], s_.x),
+           problem["dims"], _Flow(problem["q"], np.random.default_rng(0), xp), xp, dtype="float64",
+           rng=np.random.default_rng(0))
+    s.adaptive = True
+    s.adaptive_min_beta_step = False
+    s.target_efficiency = target_eff
+    s.target_efficiency_rate = 1.0
+    beta, _ = s.determine_beta(smc, beta0, np.nan, min_step, max_step, tol)
+    lw = smc.log_weights(beta)
+    from aspire.utils import logsumexp
+
+    w = np.exp(lw - logsumexp(lw))
+    rng_seed = seed + 1000
+    out = smc.resample(beta, rng=np.random.default_rng(rng_seed))
+    idx = np.random.default_rng(rng_seed).choice(n, size=n, replace=True, p=w)
+    assert np.array_equal(out.x, x[idx])
+    u = np.random.default_rng(rng_seed).random(n)
+    np.savez_compressed(
+        os.path.join(OUT, f"reweight_{name}.npz"),
+        x=x, log_l=ll, log_p=lp, log_q=lq, beta0=beta0, target_eff=target_eff, tol=tol,
+        min_step=min_step, max_step=max_step,
+        beta=beta,
+        ess=float(ess_fn(smc.log_weights(beta))),
+        ess_target=float(ess_fn(smc.log_weights(1.0))),
+        log_evidence_ratio=float(smc.log_evidence_ratio(beta)),
+        log_evidence_ratio_var=float(smc.log_evidence_ratio_variance(beta)),
+        uw=smc.unnormalized_log_weights(beta), w=w, u=u, idx=idx,
+    )
+    print(f"reweight_{name}: n={n} beta {beta0} -> {beta:.9f}")
+
+
+def importance_case(name, problem, n, seed):
+    xp, _, Samples, _, _ = _reference_objects()
+    x, ll, lp, lq = problems.draw(problem, n, seed)
+    s = Samples(x=x, log_likelihood=ll, log_prior=lp, log_q=lq, xp=xp, dtype="float64")
+    np.savez_compressed(
+        os.path.join(OUT, f"importance_{name}.npz"),
+        log_l=ll, log_p=lp, log_q=lq, log_w=s.log_w, weights=s.weights,
+        log_evidence=float(s.log_evidence), evidence=float(s.evidence),
+        evidence_error=float(s.evidence_error), log_evidence_error=float(s.log_evidence_error),
+        effective_sample_size=float(s.effective_sample_size),
+    )
+    print(f"importance_{name}: logZ={float(s.log_evidence):.6f} ess={float(s.effective_sample_size):.1f}")
+
+
+def loop_case(name, problem, n, seed, n_moves=4, rho=0.5):
+    """Full reference tempering loop (smc/base.py:215-488) with the restated
+    pCN as ``mutate``; noise from the sampler's numpy Generator."""
+    xp, SMCSampler, Samples, SMCSamples, _ = _reference_objects()
+    rng = np.random.default_rng(seed)
+    like, prior, q = problem["like"], problem["prior"], problem["q"]
+    record = dict(mu=[], sigma=[], acc=[])
+
+    class _S(SMCSampler):
+        def mutate(self, particles, beta, n_steps=None):
+            # reference measure: moments of the (resampled) ensemble
+            x = np.asarray(particles.x)
+            mu, sigma = x.mean(axis=0), x.std(axis=0)
+            m = n_moves
+            xi = self.rng.standard_normal((m, len(x), x.shape[1]))
+            log_u = np.log(1.0 - self.rng.random((m, len(x))))
+            xo, ll, lp, lq, acc = pcn.sweep(
+                x, particles.log_likelihood, particles.log_prior, particles.log_q,
+                like=like, prior=prior, q=q, beta=beta, mu=mu, sigma=sigma, rho=rho, n_moves=m,
+                xi=xi, log_u=log_u)
+            record["mu"].append(mu), record["sigma"].append(sigma), record["acc"].append(acc)
+            self.history.mcmc_acceptance.append(float(acc.sum()) / (m * len(x)))
+            return SMCSamples(x=xo, log_likelihood=ll, log_prior=lp, log_q=lq, beta=beta, xp=self.xp,
+                              dtype=self.dtype, parameters=self.parameters)
+
+    s = _S(lambda s_: dn.evaluate(like, np.asarray(s_.x)), lambda s_: dn.evaluate(prior, np.asarray(s_.x)),
+           problem["dims"], _Flow(q, rng, xp), xp, dtype="float64", rng=rng)
+    s.sampler_kwargs = {}
+    out = s.sample(n, adaptive=True, target_efficiency=0.5, beta_tolerance=1e-6, store_sample_history=False)
+    h = s.history
+    np.savez_compressed(
+        os.path.join(OUT, f"loop_{name}.npz"),
+        seed=seed, n=n, n_moves=n_moves, rho=rho,
+        beta=np.array(h.beta), ess=np.array(h.ess), ess_target=np.array(h.ess_target),
+        eff_target=np.array(h.eff_target), log_norm_ratio=np.array(h.log_norm_ratio),
+        log_norm_ratio_var=np.array(h.log_norm_ratio_var), mcmc_acceptance=np.array(h.mcmc_acceptance),
+        log_evidence=float(out.log_evidence), log_evidence_error=float(out.log_evidence_error),
+        x_mean=np.asarray(out.x).mean(axis=0), x_std=np.asarray(out.x).std(axis=0),
+        x=np.asarray(out.x), log_l=np.asarray(out.log_likelihood), log_p=np.asarray(out.log_prior),
+    )
+    print(f"loop_{name}: {len(h.beta)} steps, logZ={float(out.log_evidence):.4f} +/- {float(out.log_evidence_error):.4f}")
+
+
+def main():
+    logging.disable(logging.CRITICAL)
+    os.makedirs(OUT, exist_ok=True)
+    reweight_case("gauss16", problems.gaussian_problem(16), 4000, 11, 0.0)
+    reweight_case("rosen8", problems.rosenbrock_problem(8), 6000, 12, 0.0)
+    reweight_case("rosen8_mid", problems.rosenbrock_problem(8), 3000, 13, 0.35, target_eff=0.7)
+    reweight_case("gmm6", problems.gmm_problem(6, 4), 5000, 14, 0.1, tol=1e-8)
+    reweight_case("quick4_final", problems.quickstart_problem(4), 500, 15, 0.9)
+    importance_case("gauss16", problems.gaussian_problem(16), 20000, 21)
+    importance_case("quick4", problems.quickstart_problem(4), 2000, 22)
+    loop_case("quick4", problems.quickstart_problem(4), 500, 31)
+    loop_case("rosen4", problems.rosenbrock_problem(4), 1500, 32, n_moves=6)
+
+
+if __name__ == "__main__":
+    main()
