@@ -1,0 +1,326 @@
+"""Tensor-level wrappers over the C-ABI (``include/aspire_b200.h``).
+
+PyTorch is only the carrier: every op takes contiguous fp64 / int64 CUDA tensors,
+passes ``data_ptr()`` + the current CUDA stream to the native library and returns
+tensors.  Nothing here computes on the CPU and nothing falls back: without the
+library or without an sm_100 device the calls raise ``AspireB200Error``.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import AspireB200Error, check
+
+_ws_cache: dict = {}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f64(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise AspireB200Error(f"{name} must be a CUDA tensor (aspire_b200 has no CPU path)")
+    if t.dtype != torch.float64:
+        raise AspireB200Error(f"{name} must be float64, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _i64(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype != torch.int64:
+        raise AspireB200Error(f"{name} must be an int64 CUDA tensor")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def reduce_ws(device) -> torch.Tensor:
+    """Zero-initialised scratch of the grid reductions (ticket + partials),
+    one per (device, stream)."""
+    key = ("reduce", torch.device(device), _stream())
+    ws = _ws_cache.get(key)
+    if ws is None:
+        ws = torch.zeros(_lib.load().asp_reduce_workspace_bytes(), dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def _sized_ws(kind: str, nbytes: int, device) -> torch.Tensor:
+    key = (kind, torch.device(device), _stream())
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def device_check() -> None:
+    check(_lib.load().asp_device_check(), "asp_device_check")
+
+
+# ---- K1 -------------------------------------------------------------------
+def logdensity(density, x: torch.Tensor) -> torch.Tensor:
+    x = _f64(x, "x")
+    if x.ndim != 2 or x.shape[1] != density.dims:
+        raise AspireB200Error(f"x must be [n, {density.dims}]")
+    out = torch.empty(x.shape[0], dtype=torch.float64, device=x.device)
+    if x.shape[0] == 0:
+        return out
+    check(_lib.load().asp_logdensity(C.byref(density.struct()), x.data_ptr(), x.shape[0], out.data_ptr(), _stream()),
+          "asp_logdensity")
+    return out
+
+
+# ---- K11 ------------------------------------------------------------------
+def importance_weights(log_l, log_p, log_q):
+    """-> (log_w [n], weights [n], result [8] device tensor); see the header for
+    the layout of ``result``."""
+    log_l, log_p, log_q = _f64(log_l, "log_l"), _f64(log_p, "log_p"), _f64(log_q, "log_q")
+    n = log_l.numel()
+    log_w = torch.empty_like(log_l)
+    weights = torch.empty_like(log_l)
+    result = torch.zeros(8, dtype=torch.float64, device=log_l.device)
+    check(_lib.load().asp_importance_weights(log_l.data_ptr(), log_p.data_ptr(), log_q.data_ptr(), n,
+                                             log_w.data_ptr(), weights.data_ptr(), result.data_ptr(),
+                                             reduce_ws(log_l.device).data_ptr(), _stream()),
+          "asp_importance_weights")
+    return log_w, weights, result
+
+
+# ---- K2 / K3 --------------------------------------------------------------
+def reweight(log_l, log_p, log_q):
+    """-> (d [n], stats [4] = {min d, max d, #NaN, #+inf}) on the device."""
+    log_l, log_p, log_q = _f64(log_l, "log_l"), _f64(log_p, "log_p"), _f64(log_q, "log_q")
+    n = log_l.numel()
+    d = torch.empty_like(log_l)
+    stats = torch.empty(4, dtype=torch.float64, device=log_l.device)
+    check(_lib.load().asp_reweight(log_l.data_ptr(), log_p.data_ptr(), log_q.data_ptr(), n, d.data_ptr(),
+                                   stats.data_ptr(), reduce_ws(d.device).data_ptr(), _stream()), "asp_reweight")
+    return d, stats
+
+
+def ess_sums(d, dbetas, stats) -> torch.Tensor:
+    """-> [K, 2] device tensor of (S1, S2) per candidate ``beta - beta0``."""
+    d, stats = _f64(d, "d"), _f64(stats, "stats")
+    dbetas = torch.as_tensor(dbetas, dtype=torch.float64, device=d.device).reshape(-1).contiguous()
+    k = dbetas.numel()
+    sums = torch.empty(k, 2, dtype=torch.float64, device=d.device)
+    check(_lib.load().asp_ess_sums(d.data_ptr(), d.numel(), dbetas.data_ptr(), k, stats.data_ptr(), sums.data_ptr(),
+                                   reduce_ws(d.device).data_ptr(), _stream()), "asp_ess_sums")
+    return sums
+
+
+_STATE_WORDS = C.sizeof(_lib.BetaState) // 8
+
+
+def beta_search(d, stats, beta_prev: float, target_eff: float, tol: float, n_total: int | None = None,
+                allreduce=None) -> _lib.BetaState:
+    """Device-driven bisection of ``determine_beta`` (smc/base.py:166-186).
+
+    Launches a fixed number of passes with no host round trip; ``allreduce``
+    (multi-GPU) is called on the two-element sums tensor between a pass and its
+    decision.  Returns the final state (one device->host read)."""
+    lib = _lib.load()
+    d, stats = _f64(d, "d"), _f64(stats, "stats")
+    n = d.numel()
+    n_total = float(n if n_total is None else n_total)
+    state = torch.zeros(_STATE_WORDS, dtype=torch.float64, device=d.device)
+    ws = reduce_ws(d.device).data_ptr()
+    st = _stream()
+    check(lib.asp_beta_search_init(state.data_ptr(), beta_prev, target_eff, tol, n_total, stats.data_ptr(), st),
+          "asp_beta_search_init")
+    for _ in range(lib.asp_beta_search_max_passes(beta_prev, tol)):
+        if allreduce is None:
+            check(lib.asp_beta_search_pass(d.data_ptr(), n, state.data_ptr(), 1, ws, st), "asp_beta_search_pass")
+        else:
+            check(lib.asp_beta_search_pass(d.data_ptr(), n, state.data_ptr(), 0, ws, st), "asp_beta_search_pass")
+            allreduce(state[7:9])  # s1, s2
+            check(lib.asp_beta_search_decide(state.data_ptr(), st), "asp_beta_search_decide")
+    host = state.cpu().numpy().tobytes()
+    out = _lib.BetaState.from_buffer_copy(host)
+    if out.phase != 2:
+        raise AspireB200Error("beta bisection did not converge within the planned number of passes")
+    return out
+
+
+def smc_weights(d, dbeta: float, c: float, s1: float, n_total: int | None = None, want_p: bool = True,
+                want_tiles: bool = True):
+    """-> (p or None, result [4] device, tile_stats or None).  ``p`` is the
+    normalised resampling weight ``exp(dbeta d - c) / s1``."""
+    d = _f64(d, "d")
+    n = d.numel()
+    n_total = float(n if n_total is None else n_total)
+    p = torch.empty_like(d) if want_p else None
+    n_tiles = (n + _lib.CDF_TILE - 1) // _lib.CDF_TILE
+    tiles = torch.empty(2 * n_tiles, dtype=torch.float64, device=d.device) if want_tiles else None
+    result = torch.empty(4, dtype=torch.float64, device=d.device)
+    check(_lib.load().asp_smc_weights(d.data_ptr(), n, dbeta, c, s1, n_total, _ptr(p), result.data_ptr(), _ptr(tiles),
+                                      reduce_ws(d.device).data_ptr(), _stream()), "asp_smc_weights")
+    return p, result, tiles
+
+
+# ---- K5 -------------------------------------------------------------------
+def cdf_workspace(n: int, device) -> torch.Tensor:
+    return _sized_ws("cdf", _lib.load().asp_cdf_workspace_bytes(n), device)
+
+
+def cdf_exact(p, normalise: bool = True, tile_stats=None, return_info: bool = False):
+    """Sequential-order-exact ``cumsum(p)`` (then ``/= cdf[-1]``): bit-identical
+    to what ``numpy.random.Generator.choice`` builds from ``p``."""
+    lib = _lib.load()
+    p = _f64(p, "p")
+    n = p.numel()
+    cdf = torch.empty_like(p)
+    ws = cdf_workspace(n, p.device)
+    st = _stream()
+    if tile_stats is None:
+        check(lib.asp_cdf_exact(p.data_ptr(), n, int(normalise), cdf.data_ptr(), ws.data_ptr(), st), "asp_cdf_exact")
+    else:
+        tile_stats = _f64(tile_stats, "tile_stats")
+        check(lib.asp_cdf_set_tile_stats(tile_stats.data_ptr(), n, ws.data_ptr(), st), "asp_cdf_set_tile_stats")
+        check(lib.asp_cdf_plan(n, None, ws.data_ptr(), st), "asp_cdf_plan")
+        check(lib.asp_cdf_aggregate(p.data_ptr(), n, ws.data_ptr(), st), "asp_cdf_aggregate")
+        check(lib.asp_cdf_resolve(p.data_ptr(), n, None, cdf.data_ptr(), None, ws.data_ptr(), st), "asp_cdf_resolve")
+        check(lib.asp_cdf_write(p.data_ptr(), n, None, int(normalise), cdf.data_ptr(), ws.data_ptr(), st),
+              "asp_cdf_write")
+    if return_info:
+        return cdf, cdf_info(ws)
+    return cdf
+
+
+def cdf_info(ws) -> dict:
+    info = (C.c_int64 * 4)()
+    check(_lib.load().asp_cdf_info(ws.data_ptr(), info, _stream()), "asp_cdf_info")
+    return dict(n_tiles=info[0], n_dirty=info[1], n_phases=info[2], error_flags=info[3])
+
+
+# ---- K6 / K7 --------------------------------------------------------------
+def search_multinomial(cdf, u) -> torch.Tensor:
+    cdf, u = _f64(cdf, "cdf"), _f64(u, "u")
+    idx = torch.empty(u.numel(), dtype=torch.int64, device=cdf.device)
+    if u.numel() == 0:
+        return idx
+    check(_lib.load().asp_search_multinomial(cdf.data_ptr(), cdf.numel(), u.data_ptr(), u.numel(), idx.data_ptr(),
+                                             _stream()), "asp_search_multinomial")
+    return idx
+
+
+def search_systematic(cdf, u0: float, m: int, j0: int = 0, m_total: int | None = None) -> torch.Tensor:
+    cdf = _f64(cdf, "cdf")
+    m_total = m if m_total is None else m_total
+    idx = torch.empty(m, dtype=torch.int64, device=cdf.device)
+    if m == 0:
+        return idx
+    check(_lib.load().asp_search_systematic(cdf.data_ptr(), cdf.numel(), float(u0), j0, m, m_total, idx.data_ptr(),
+                                            _stream()), "asp_search_systematic")
+    return idx
+
+
+def gather_rows(x, idx, log_l=None, log_p=None, log_q=None):
+    x, idx = _f64(x, "x"), _i64(idx, "idx")
+    m, dims = idx.numel(), x.shape[1]
+    xo = torch.empty(m, dims, dtype=torch.float64, device=x.device)
+    logs = [None if t is None else _f64(t, "log") for t in (log_l, log_p, log_q)]
+    outs = [None if t is None else torch.empty(m, dtype=torch.float64, device=x.device) for t in logs]
+    if m:
+        check(_lib.load().asp_gather_rows(x.data_ptr(), dims, idx.data_ptr(), m, xo.data_ptr(), _ptr(logs[0]),
+                                          _ptr(logs[1]), _ptr(logs[2]), _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]),
+                                          _stream()), "asp_gather_rows")
+    return (xo, *outs)
+
+
+# ---- K8 -------------------------------------------------------------------
+def weighted_moments(x, d=None, dbeta: float = 0.0, c: float = 0.0) -> torch.Tensor:
+    """-> device tensor [1 + 2 D] = {sum w, sum w x_j, sum w x_j^2}, w = exp(dbeta d - c)
+    (w = 1 when ``d`` is None)."""
+    x = _f64(x, "x")
+    n, dims = x.shape
+    d = None if d is None else _f64(d, "d")
+    out = torch.empty(1 + 2 * dims, dtype=torch.float64, device=x.device)
+    ws = _sized_ws("moments", _lib.load().asp_moments_workspace_bytes(dims), x.device)
+    check(_lib.load().asp_weighted_moments(x.data_ptr(), dims, _ptr(d), n, dbeta, c, out.data_ptr(), ws.data_ptr(),
+                                           _stream()), "asp_weighted_moments")
+    return out
+
+
+def moments_to_mu_sigma(m: torch.Tensor, dims: int):
+    """One-pass mean / std from the moment sums (device tensors, no sync)."""
+    sw = m[0]
+    mu = m[1:1 + dims] / sw
+    var = m[1 + dims:1 + 2 * dims] / sw - mu * mu
+    return mu.contiguous(), torch.sqrt(torch.clamp_min(var, 0.0)).contiguous()
+
+
+def make_pcn_params(beta, rho, mu, sigma, n_moves, seed=0, stream0=0, index0=0, xi=None, log_u=None):
+    mu, sigma = _f64(mu, "mu"), _f64(sigma, "sigma")
+    prm = _lib.PcnParams()
+    prm.beta, prm.rho = float(beta), float(rho)
+    prm.d_mu, prm.d_sigma = mu.data_ptr(), sigma.data_ptr()
+    prm.n_moves = int(n_moves)
+    prm.noise_mode = 0 if xi is None else 1
+    prm.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    prm.stream0 = int(stream0) & 0xFFFFFFFF
+    prm.index0 = int(index0)
+    prm.d_xi = None if xi is None else _f64(xi, "xi").data_ptr()
+    prm.d_log_u = None if log_u is None else _f64(log_u, "log_u").data_ptr()
+    prm._keep = (mu, sigma, xi, log_u)  # keep the tensors alive
+    return prm
+
+
+def pcn_sweep(x, log_l, log_p, log_q, idx, like, prior, q, prm, out=None):
+    """Fused gather + ``n_moves`` pCN moves.  -> (x, log_l, log_p, log_q, accepts [n_moves] int64)."""
+    x, log_l, log_p, log_q = _f64(x, "x"), _f64(log_l, "log_l"), _f64(log_p, "log_p"), _f64(log_q, "log_q")
+    dims = x.shape[1]
+    n = x.shape[0] if idx is None else idx.numel()
+    idx = None if idx is None else _i64(idx, "idx")
+    if out is None:
+        out = (torch.empty(n, dims, dtype=torch.float64, device=x.device),
+               *(torch.empty(n, dtype=torch.float64, device=x.device) for _ in range(3)))
+    accepts = torch.zeros(max(prm.n_moves, 1), dtype=torch.int64, device=x.device)
+    check(_lib.load().asp_pcn_sweep(x.data_ptr(), log_l.data_ptr(), log_p.data_ptr(), log_q.data_ptr(), _ptr(idx), n,
+                                    dims, C.byref(like.struct()), C.byref(prior.struct()), C.byref(q.struct()),
+                                    C.byref(prm), out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
+                                    out[3].data_ptr(), accepts.data_ptr(), _stream()), "asp_pcn_sweep")
+    return (*out, accepts[:prm.n_moves])
+
+
+def pcn_propose(x, prm, move: int) -> torch.Tensor:
+    x = _f64(x, "x")
+    xp = torch.empty_like(x)
+    check(_lib.load().asp_pcn_propose(x.data_ptr(), x.shape[0], x.shape[1], C.byref(prm), move, xp.data_ptr(),
+                                      _stream()), "asp_pcn_propose")
+    return xp
+
+
+def pcn_accept(x, log_l, log_p, log_q, x_prop, log_l_prop, log_p_prop, log_q_prop, prm, move: int, accepts):
+    """In-place accept/reject of move ``move``; ``accepts`` is an int64 [n_moves] counter tensor."""
+    ts = [_f64(t, "tensor") for t in (x, log_l, log_p, log_q, x_prop, log_l_prop, log_p_prop, log_q_prop)]
+    for a, b in zip(ts[:4], (x, log_l, log_p, log_q)):
+        if a.data_ptr() != b.data_ptr():
+            raise AspireB200Error("pcn_accept updates in place: state tensors must be contiguous")
+    check(_lib.load().asp_pcn_accept(*(t.data_ptr() for t in ts), x.shape[0], x.shape[1], C.byref(prm), move,
+                                     accepts.data_ptr(), _stream()), "asp_pcn_accept")
+
+
+# ---- K13 ------------------------------------------------------------------
+def philox_uniform(seed: int, stream_id: int, n: int, device, index0: int = 0) -> torch.Tensor:
+    out = torch.empty(n, dtype=torch.float64, device=device)
+    if n:
+        check(_lib.load().asp_philox_uniform(int(seed) & 0xFFFFFFFFFFFFFFFF, stream_id & 0xFFFFFFFF, index0, n,
+                                             out.data_ptr(), _stream()), "asp_philox_uniform")
+    return out
+
+
+def philox_normal(seed: int, stream_id: int, n: int, dims: int, device, mean=None, sigma=None,
+                  index0: int = 0) -> torch.Tensor:
+    out = torch.empty(n, dims, dtype=torch.float64, device=device)
+    if n:
+        check(_lib.load().asp_philox_normal(int(seed) & 0xFFFFFFFFFFFFFFFF, stream_id & 0xFFFFFFFF, index0, n, dims,
+                                            _ptr(mean), _ptr(sigma), out.data_ptr(), _stream()), "asp_philox_normal")
+    return out
