@@ -118,7 +118,7 @@ SIGNATURES = {
     "asp_search_systematic": (C.c_int, [_P, _I64, _D, _I64, _I64, _I64, _P, _P]),
     "asp_gather_rows": (C.c_int, [_P, _I32, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _P]),
     "asp_moments_workspace_bytes": (C.c_size_t, [_I32]),
-    "asp_weighted_moments": (C.c_int, [_P, _I32, _P, _I64, _D, _D, _P, _P, _P]),
+    "asp_weighted_moments": (C.c_int, [_P, _I32, _P, _P, _I64, _D, _D, _P, _P, _P]),
     "asp_pcn_sweep": (
         C.c_int,
         [_P, _P, _P, _P, _P, _I64, _I32, C.POINTER(Density), C.POINTER(Density), C.POINTER(Density),
@@ -159,6 +159,14 @@ def last_error() -> str:
     return load().asp_last_error().decode("utf-8", "replace")
 
 
+# kernels launched per successful C call (for bench.py's gpu_launches)
+KERNELS_PER_CALL = {"asp_importance_weights": 3, "asp_cdf_exact": 6, "asp_cdf_tile_stats": 2,
+                    "asp_cdf_set_tile_stats": 2, "asp_cdf_info": 0, "asp_device_check": 0}
+launch_count = 0
+
+
 def check(rc: int, what: str = "") -> None:
+    global launch_count
+    launch_count += KERNELS_PER_CALL.get(what, 1)
     if rc != ASP_OK:
         raise AspireB200Error(f"{what or 'aspire_b200'} failed ({rc}): {last_error()}")

@@ -236,15 +236,17 @@ def gather_rows(x, idx, log_l=None, log_p=None, log_q=None):
 
 
 # ---- K8 -------------------------------------------------------------------
-def weighted_moments(x, d=None, dbeta: float = 0.0, c: float = 0.0) -> torch.Tensor:
-    """-> device tensor [1 + 2 D] = {sum w, sum w x_j, sum w x_j^2}, w = exp(dbeta d - c)
-    (w = 1 when ``d`` is None)."""
+def weighted_moments(x, d=None, dbeta: float = 0.0, c: float = 0.0, idx=None) -> torch.Tensor:
+    """-> device tensor [1 + 2 D] = {sum w, sum w x_j, sum w x_j^2} over rows ``idx`` (all rows
+    when None), w = exp(dbeta d - c) (w = 1 when ``d`` is None)."""
     x = _f64(x, "x")
-    n, dims = x.shape
+    dims = x.shape[1]
+    idx = None if idx is None else _i64(idx, "idx")
+    n = x.shape[0] if idx is None else idx.numel()
     d = None if d is None else _f64(d, "d")
     out = torch.empty(1 + 2 * dims, dtype=torch.float64, device=x.device)
     ws = _sized_ws("moments", _lib.load().asp_moments_workspace_bytes(dims), x.device)
-    check(_lib.load().asp_weighted_moments(x.data_ptr(), dims, _ptr(d), n, dbeta, c, out.data_ptr(), ws.data_ptr(),
+    check(_lib.load().asp_weighted_moments(x.data_ptr(), dims, _ptr(idx), _ptr(d), n, dbeta, c, out.data_ptr(), ws.data_ptr(),
                                            _stream()), "asp_weighted_moments")
     return out
 

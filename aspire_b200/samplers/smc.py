@@ -1,0 +1,394 @@
+"""``sampler="smc"`` - the tempering loop on the B200 kernels.
+
+Mirrors, name for name, ``SMCSampler`` (``src/aspire/samplers/smc/base.py:30-488``)
+and ``MiniPCNSMC`` (``src/aspire/samplers/smc/minipcn.py:14-135``) of the
+reference: same constructor, same ``sample`` keywords and defaults, same
+exceptions, same ``SMCHistory`` fields, same order of operations per trip of
+the loop (determine_beta -> history -> resample -> mutate).  The arithmetic is
+the C-ABI's: ``asp_reweight`` + device-driven bisection (``asp_beta_search_*``)
++ ``asp_smc_weights`` + the exact CDF / ancestor search + ``asp_pcn_sweep``.
+
+Two mutation paths:
+* fused   - likelihood / prior are built-in ``aspire_b200.targets`` densities and
+            the proposal flow exposes ``.density``: the resampling gather and
+            all pCN moves run in one kernel (particles read once, written once);
+* unfused - arbitrary Python callables: ``asp_pcn_propose`` / callables /
+            ``asp_pcn_accept`` per move.
+"""
+
+from __future__ import annotations
+
+import logging
+import math
+from typing import Any, Callable
+
+import numpy as np
+import torch
+
+from .. import ops
+from ..history import SMCHistory
+from ..rng import as_uniform_source
+from ..samples import Samples, SMCSamples
+from ..targets import Density
+from .base import Sampler, track_calls
+
+logger = logging.getLogger(__name__)
+
+DEFAULT_BETA_TOLERANCE = 1e-8  # smc/base.py:23
+SAMPLE_HISTORY_MAX_ELEMENTS = 20_000_000  # above this the per-step host copies are refused (SURVEY hard part 9)
+
+
+class BetaScheduleError(RuntimeError):
+    """smc/base.py:26"""
+
+
+class SMCSampler(Sampler):
+    default_beta_tolerance = DEFAULT_BETA_TOLERANCE
+
+    def __init__(
+        self,
+        log_likelihood: Callable,
+        log_prior: Callable,
+        dims: int,
+        prior_flow,
+        xp: Callable = None,
+        dtype: Any | str | None = None,
+        parameters: list[str] | None = None,
+        rng=None,
+        preconditioning_transform: Callable | None = None,
+    ):
+        super().__init__(log_likelihood, log_prior, dims, prior_flow, xp, dtype, parameters, preconditioning_transform)
+        self.rng = as_uniform_source(rng)
+        self._adaptive_target_efficiency = False
+        self.sampler_kwargs: dict | None = None
+        self._weights_cache = None
+
+    # ---- target efficiency (smc/base.py:80-121) ---------------------------
+    @property
+    def target_efficiency(self):
+        return self._target_efficiency
+
+    @target_efficiency.setter
+    def target_efficiency(self, value):
+        if isinstance(value, float):
+            if not (0 < value < 1):
+                raise ValueError("target_efficiency must be in (0, 1)")
+            self._target_efficiency = value
+            self._adaptive_target_efficiency = False
+        elif len(value) != 2:
+            raise ValueError("target_efficiency must be a float or tuple of two floats")
+        else:
+            value = tuple(map(float, value))
+            if not (0 < value[0] < value[1] < 1):
+                raise ValueError("target_efficiency tuple must be in (0, 1) and increasing")
+            self._target_efficiency = value
+            self._adaptive_target_efficiency = True
+
+    def current_target_efficiency(self, beta: float) -> float:
+        if self._adaptive_target_efficiency:
+            lo, hi = self._target_efficiency
+            return lo + (hi - lo) * (beta**self.target_efficiency_rate)
+        return self._target_efficiency
+
+    # ---- fused-path detection ---------------------------------------------
+    @property
+    def fused(self) -> bool:
+        return (isinstance(self._log_likelihood, Density) and isinstance(self._log_prior, Density)
+                and isinstance(getattr(self.prior_flow, "density", None), Density) and self.dims <= 128)
+
+    # ---- initial particles (samplers/mcmc.py:49-110) ------------------------
+    def draw_initial_samples(self, n_samples: int) -> Samples:
+        n_drawn, samples = 0, None
+        while n_drawn < n_samples:
+            x, log_q = self.prior_flow.sample_and_log_prob(n_samples)
+            log_q = torch.as_tensor(log_q, dtype=torch.float64, device=self.device)
+            if not bool(torch.isfinite(log_q).all()):
+                raise ValueError(
+                    "Proposal returned non-finite log probabilities. aspire assumes the proposal is a valid, "
+                    "normalized probability distribution and should therefore only return samples with finite "
+                    "log probabilities.")
+            new = Samples(x, log_q=log_q, parameters=self.parameters, device=self.device)
+            new.log_prior = self.log_prior(new)
+            new.log_likelihood = self.log_likelihood(new)
+            valid = torch.isfinite(new.log_prior) & torch.isfinite(new.log_likelihood)
+            n_valid = int(valid.sum())
+            if n_valid == len(new):
+                piece = new
+            elif n_valid > 0:
+                piece = new[valid]
+            else:
+                piece = None
+            if piece is not None:
+                samples = piece if samples is None else Samples.concatenate([samples, piece])
+                n_drawn += n_valid
+        if n_drawn > n_samples:
+            samples = samples[:n_samples]
+        return samples
+
+    # ---- beta (smc/base.py:123-213) ------------------------------------------
+    def determine_beta(self, samples: SMCSamples, beta: float, beta_step: float, min_beta_step: float,
+                       max_beta_step: float = 1.0, beta_tolerance: float = DEFAULT_BETA_TOLERANCE):
+        d, stats, st = samples._slope()
+        n = len(samples)
+        if st[2] > 0 or st[3] > 0:
+            raise ValueError(f"Log weights contain NaN values for beta={beta}")
+        beta_prev = beta
+        sums = None
+        ess_target = None
+        n_evals = 0
+        if not self.adaptive:
+            beta += beta_step
+            if beta >= 1.0:
+                beta = 1.0
+        else:
+            target_eff = self.current_target_efficiency(beta_prev)
+            state = ops.beta_search(d, stats, beta_prev, target_eff, beta_tolerance, n_total=n)
+            n_evals = state.n_evals
+            beta_star = state.beta_min
+            ess_target = state.eff_beta_max * n
+            if beta_star <= beta_prev + beta_tolerance and beta_prev < 1.0:
+                logger.warning(
+                    "Adaptive beta search could not find a beta above %.6g that satisfies the target efficiency "
+                    "%.3f within tolerance %.1e; beta may remain unchanged. Consider decreasing beta_tolerance or "
+                    "target_efficiency.", beta_prev, target_eff, beta_tolerance)
+            if self.adaptive_min_beta_step:
+                min_beta_step = min_beta_step * (1 - beta_prev) / (1 - beta_star)
+            beta = max(beta_star, beta_prev + min_beta_step)
+            beta = min(beta, beta_prev + max_beta_step, 1.0)
+            if beta == beta_prev:
+                raise BetaScheduleError(
+                    f"Beta did not increase from previous value {beta:.6g}. Adaptive beta search may have failed to "
+                    f"find a suitable beta. Consider adjusting beta_tolerance ({beta_tolerance}), min_beta_step "
+                    f"({min_beta_step}) or target_efficiency ({target_eff}) (values may be adaptive).")
+            if state.min_valid and beta == beta_star:
+                sums = (state.s1_min, state.s2_min)
+        dbeta = beta - beta_prev
+        if sums is None or ess_target is None:
+            s = ops.ess_sums(d, [dbeta, 1.0 - beta_prev], stats).cpu().numpy()
+            sums = (float(s[0, 0]), float(s[0, 1])) if sums is None else sums
+            ess_target = float(s[1, 0] ** 2 / s[1, 1]) if ess_target is None else ess_target
+        c = dbeta * (st[1] if dbeta >= 0 else st[0])
+        self._weights_cache = dict(beta_prev=beta_prev, beta=beta, d=d, dbeta=dbeta, c=c, s1=sums[0], s2=sums[1],
+                                   ess_target=ess_target, n_evals=n_evals)
+        return beta, min_beta_step
+
+    # ---- the loop (smc/base.py:215-488, smc/minipcn.py:22-67) ---------------
+    @track_calls
+    def sample(
+        self,
+        n_samples: int,
+        n_steps: int = None,
+        min_beta_step: float | None = None,
+        max_beta_step: float | None = None,
+        max_n_steps: int | None = None,
+        adaptive: bool = True,
+        target_efficiency: float = 0.5,
+        target_efficiency_rate: float = 1.0,
+        n_final_samples: int | None = None,
+        sampler_kwargs: dict | None = None,
+        rng=None,
+        checkpoint_callback=None,
+        checkpoint_every: int | None = None,
+        checkpoint_file_path: str | None = None,
+        resume_from=None,
+        beta_tolerance: float | None = None,
+        store_sample_history: bool = True,
+        resampling: str = "multinomial",
+    ):
+        if beta_tolerance is None:
+            beta_tolerance = self.default_beta_tolerance
+        if resume_from is not None or checkpoint_callback is not None:
+            raise NotImplementedError("checkpoint / resume is a later scope row (SURVEY 8f-3)")
+        if checkpoint_every is not None or checkpoint_file_path is not None:
+            logger.warning("aspire_b200: checkpoint_every / checkpoint_file_path are accepted but ignored")
+        self._configure_kernel(sampler_kwargs)
+        if rng is not None:
+            self.rng = as_uniform_source(rng)
+        self.resampling = resampling
+
+        samples = self.draw_initial_samples(n_samples)
+        samples = SMCSamples.from_samples(samples, beta=0.0)
+        beta, iterations = 0.0, 0
+        self.history = SMCHistory()
+        store_sample_history = store_sample_history and samples.x.numel() <= SAMPLE_HISTORY_MAX_ELEMENTS
+        if store_sample_history:
+            self.history.sample_history.append(samples.to_numpy())
+
+        if bool(torch.isnan(samples.log_q).any()):
+            raise ValueError("Log proposal contains NaN values")
+        if bool(torch.isnan(samples.log_prior).any()):
+            raise ValueError("Log prior contains NaN values")
+        if bool(torch.isnan(samples.log_likelihood).any()):
+            raise ValueError("Log likelihood contains NaN values")
+
+        n_final_steps = self.sampler_kwargs.pop("n_final_steps", None)
+        self.target_efficiency = target_efficiency
+        self.target_efficiency_rate = target_efficiency_rate
+        if n_steps is not None:
+            beta_step = 1 / n_steps
+        elif not adaptive:
+            raise ValueError("Either n_steps or adaptive=True must be set")
+        else:
+            beta_step = math.nan
+        self.adaptive = adaptive
+        if min_beta_step is None:
+            if max_n_steps is None:
+                min_beta_step, self.adaptive_min_beta_step = 0.0, False
+            else:
+                min_beta_step, self.adaptive_min_beta_step = 1 / max_n_steps, True
+        else:
+            self.adaptive_min_beta_step = False
+        if max_beta_step is not None:
+            if max_beta_step <= 0 or max_beta_step >= 1:
+                raise ValueError("max_beta_step must be in (0, 1)")
+            self.max_beta_step = max_beta_step
+        else:
+            self.max_beta_step = 1.0
+
+        while True:
+            iterations += 1
+            samples, beta, min_beta_step = self.tempering_step(samples, beta, beta_step, min_beta_step,
+                                                               beta_tolerance, iterations)
+            if store_sample_history:
+                self.history.sample_history.append(samples.to_numpy())
+            if beta == 1.0 or (max_n_steps is not None and iterations >= max_n_steps):
+                break
+
+        if n_final_samples is not None and len(samples.x) != n_final_samples:
+            logger.info(f"Generating {n_final_samples} final samples")
+            idx = samples.resample_indices(1.0, n_samples=n_final_samples, rng=self.rng, method=self.resampling)
+            samples = self.mutate(samples, 1.0, n_steps=n_final_steps, idx=idx)
+
+        samples.log_evidence = float(np.sum(np.asarray(self.history.log_norm_ratio)))
+        samples.log_evidence_error = float(np.sqrt(np.sum(np.asarray(self.history.log_norm_ratio_var))))
+        final = samples.to_standard_samples()
+        logger.info(f"Log evidence: {final.log_evidence:.2f} +/- {final.log_evidence_error:.2f}")
+        return final
+
+    def tempering_step(self, samples: SMCSamples, beta: float, beta_step: float, min_beta_step: float,
+                       beta_tolerance: float, iterations: int = 0, out=None, mark=None):
+        """One trip of the hot loop (smc/base.py:401-454): determine_beta, history,
+        evidence bookkeeping, resample, mutate.  ``out`` optionally supplies the
+        output buffers of the sweep, ``mark(name)`` is called between phases
+        (bench.py records CUDA events there).  -> (samples, beta, min_beta_step)"""
+        mark = mark or (lambda name: None)
+        n = len(samples)
+        beta, min_beta_step = self.determine_beta(samples, beta, beta_step, min_beta_step,
+                                                  max_beta_step=self.max_beta_step, beta_tolerance=beta_tolerance)
+        mark("beta_search")
+        w = self._weights_cache
+        self.history.eff_target.append(float(self.current_target_efficiency(beta)))
+        logger.info(f"it {iterations} - beta: {beta}")
+        self.history.beta.append(float(beta))
+        ess = w["s1"] ** 2 / w["s2"]
+        eff = ess / n
+        if eff < 0.1:
+            logger.warning(f"it {iterations} - Low sample efficiency: {eff:.2f}")
+        self.history.ess.append(float(ess))
+        self.history.ess_target.append(float(w["ess_target"]))
+        self.history.n_beta_evals.append(int(w["n_evals"]))
+        # evidence bookkeeping + resampling weights in one pass over d (samples.py:1226-1242, 1277)
+        p, result, tiles = ops.smc_weights(w["d"], w["dbeta"], w["c"], w["s1"])
+        log_ratio = w["c"] + math.log(w["s1"]) - math.log(n)
+        mean_u = w["s1"] / n
+        self.history.log_norm_ratio.append(float(log_ratio))
+        # resample: exact CDF + ancestor search (samples.py:1251-1287 / numpy Generator.choice)
+        cdf = ops.cdf_exact(p, tile_stats=tiles)
+        if self.resampling == "systematic":
+            idx = ops.search_systematic(cdf, self.rng.scalar_uniform(), n)
+        else:
+            idx = ops.search_multinomial(cdf, self.rng.uniform(n, self.device))
+        del p, cdf
+        mark("resample")
+        samples = self.mutate(samples, beta, idx=idx, out=out, mark=mark)
+        var_sum = float(result[0])
+        self.history.log_norm_ratio_var.append(var_sum / n / (n * mean_u * mean_u) if mean_u != 0 else math.nan)
+        logger.info(f"it {iterations} - ESS: {ess:.1f} ({eff:.2f} efficiency), log evidence ratio {log_ratio:.2f}")
+        return samples, beta, min_beta_step
+
+    # ---- kernel configuration (smc/minipcn.py:44-50) ---------------------------
+    def _configure_kernel(self, sampler_kwargs):
+        kw = dict(sampler_kwargs or {})
+        kw.setdefault("n_steps", 5 * self.dims)
+        kw.setdefault("target_acceptance_rate", 0.234)
+        kw.setdefault("step_fn", "pcn")
+        kw.setdefault("verbose", False)
+        kw.setdefault("rho", 0.5)
+        kw.setdefault("adapt_rho", True)
+        if kw["step_fn"] != "pcn":
+            raise NotImplementedError(
+                f"step_fn={kw['step_fn']!r}: only the pCN step is built (tpCN is scope row 8f-2 of SURVEY.md)")
+        self.sampler_kwargs = kw
+        self.rho = float(kw["rho"])
+
+    # ---- tempered target for the unfused path (smc/base.py:507-519) ----------
+    def log_prob(self, x, beta=None):
+        s = SMCSamples(x, beta=beta, device=self.device, parameters=self.parameters)
+        s.log_q = torch.as_tensor(self.prior_flow.log_prob(s.x), dtype=torch.float64, device=self.device)
+        s.log_prior = self.log_prior(s)
+        s.log_likelihood = self.log_likelihood(s)
+        lp = s.log_p_t(beta)
+        return torch.where(torch.isnan(lp), torch.full_like(lp, -math.inf), lp)
+
+    # ---- mutation (smc/minipcn.py:69-135) --------------------------------------
+    def mutate(self, particles: SMCSamples, beta: float, n_steps: int | None = None, idx=None, out=None,
+               mark=None) -> SMCSamples:
+        n_moves = int(n_steps or self.sampler_kwargs["n_steps"])
+        n = len(particles) if idx is None else idx.numel()
+        dims = self.dims
+        # reference measure of the pCN proposal: moments of the (resampled) ensemble
+        mom = ops.weighted_moments(particles.x, idx=idx)
+        mu, sigma = ops.moments_to_mu_sigma(mom, dims)
+        sigma = torch.clamp_min(sigma, 1e-150)
+        if mark:
+            mark("moments")
+        if self.rng.is_host:  # parity mode: noise drawn on the host in a fixed order, then uploaded
+            xi = torch.from_numpy(self.rng.rng.standard_normal((n_moves, n, dims))).to(self.device)
+            log_u = torch.from_numpy(np.log(1.0 - self.rng.rng.random((n_moves, n)))).to(self.device)
+            prm = ops.make_pcn_params(beta, self.rho, mu, sigma, n_moves, xi=xi, log_u=log_u)
+        else:
+            prm = ops.make_pcn_params(beta, self.rho, mu, sigma, n_moves, seed=self.rng.seed,
+                                      stream0=self.rng.next_stream(n_moves), index0=getattr(self, "index0", 0))
+        if self.fused:
+            x, ll, lp, lq, accepts = ops.pcn_sweep(particles.x, particles.log_likelihood, particles.log_prior,
+                                                   particles.log_q, idx, self._log_likelihood, self._log_prior,
+                                                   self.prior_flow.density, prm, out=out)
+            if mark:
+                mark("pcn_sweep")
+            self.n_likelihood_evaluations += n * n_moves
+        else:
+            if idx is not None:
+                x, ll, lp, lq = ops.gather_rows(particles.x, idx, particles.log_likelihood, particles.log_prior,
+                                                particles.log_q)
+            else:
+                x, ll, lp, lq = (t.clone() for t in (particles.x, particles.log_likelihood, particles.log_prior,
+                                                     particles.log_q))
+            accepts = torch.zeros(max(n_moves, 1), dtype=torch.int64, device=self.device)
+            for t in range(n_moves):
+                xp = ops.pcn_propose(x, prm, t)
+                prop = SMCSamples(xp, beta=beta, device=self.device, parameters=self.parameters)
+                lq2 = torch.as_tensor(self.prior_flow.log_prob(xp), dtype=torch.float64, device=self.device).contiguous()
+                prop.log_q = lq2
+                lp2 = self.log_prior(prop)
+                prop.log_prior = lp2
+                ll2 = self.log_likelihood(prop)
+                ops.pcn_accept(x, ll, lp, lq, xp, ll2, lp2, lq2, prm, t, accepts)
+            accepts = accepts[:n_moves]
+        acc = float(accepts.sum()) / max(n_moves * n, 1)
+        self.history.mcmc_acceptance.append(acc)
+        self.history.rho.append(self.rho)
+        if self.sampler_kwargs.get("adapt_rho", True):
+            target = self.sampler_kwargs["target_acceptance_rate"]
+            self.rho = float(min(max(self.rho * math.exp(acc - target), 1e-3), 1.0))
+        out = SMCSamples(x, log_likelihood=ll, log_prior=lp, log_q=lq, beta=beta, parameters=self.parameters,
+                         device=self.device)
+        if bool(torch.isnan(lq).any()):
+            raise ValueError("Log proposal contains NaN values")  # smc/minipcn.py:133-134
+        return out
+
+
+class MiniPCNSMC(SMCSampler):
+    """``sampler="smc"`` / ``"minipcn_smc"`` (reference ``aspire.py:288-289``); its
+    ``beta_tolerance`` default is 1e-6 (``smc/minipcn.py:40``), not the base class's 1e-8."""
+
+    default_beta_tolerance = 1e-6

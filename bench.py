@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""Headline benchmark: particles/sec per SMC tempering step (BASELINE.json).
+
+Workload (config C3 of SURVEY 8d / BASELINE.json configs[2]): 32-D Rosenbrock
+likelihood, N(0, 3^2) prior, diagonal-Gaussian proposal, N = 1e8 particles, one
+full tempering step = reweight + ESS / adaptive-beta bisection (tol 1e-6) +
+evidence bookkeeping + exact-CDF multinomial resampling + 10 pCN moves with
+accept/reject, fp64 throughout.  Every timed step starts from the same resident
+particle set (25.6 GB, far larger than L2) and runs exactly the code
+``SMCSampler.sample`` runs per trip of its loop (``tempering_step``).
+
+    python bench.py --gpus 1 --steps 5 --warmup 3
+    python bench.py --impl reference            # the CPU baseline arm
+
+Prints ONE JSON line (see the task contract); add --verbose for per-phase times.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "particles/sec per SMC step"
+UNIT = "particles/s"
+SEED = 20251104
+
+
+def algorithmic_bytes_per_particle(dims: int) -> int:
+    """W(D) of SURVEY 8d: reweight 32 + beta search 72 + weights/scan 16 + search 16
+    + gather 16D+48 + pCN sweep 16D+48 = 232 + 32 D."""
+    return 232 + 32 * dims
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        super().__init__(daemon=True)
+        self.gpu_index = gpu_index
+        self.rows = []
+        self._stop = threading.Event()
+
+    def run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.gpu_index)], capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    self.rows.append([c.strip() for c in line.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=5)
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------
+# CPU baseline (oracle port) - also the --impl reference arm
+# ---------------------------------------------------------------------------
+def cpu_step_time(n_cpu: int, dims: int, moves: int, steps: int = 1):
+    import numpy as np
+
+    from oracle import cpu_step, problems
+
+    prob = problems.rosenbrock_problem(dims)
+    x, ll, lp, lq = problems.draw(prob, n_cpu, SEED % 2**31)
+    best = float("inf")
+    for s in range(steps):
+        t0 = time.perf_counter()
+        cpu_step.smc_step(x, ll, lp, lq, prob, beta0=0.0, n_moves=moves, rho=0.5, target_efficiency=0.5,
+                          beta_tolerance=1e-6, seed=s)
+        best = min(best, time.perf_counter() - t0)
+    del np
+    return best
+
+
+def cpu_baseline(n_cpu: int, dims: int, moves: int):
+    t = cpu_step_time(n_cpu, dims, moves)
+    return {"value": n_cpu / t, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{n_cpu} particles x {dims} dims, same step (numpy restatement of the reference loop body; "
+                      f"pCN restated, minipcn absent), {t:.1f} s on 1 of {os.cpu_count()} host cores"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_cpu = args.cpu_particles
+    times = []
+    for s in range(args.warmup + args.steps):
+        t = cpu_step_time(n_cpu, args.dims, args.moves)
+        if s >= args.warmup:
+            times.append(t)
+    t_step = sum(times) / len(times)
+    value = n_cpu / t_step
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True,
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, n_cpu, sample=True),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": f"{n_cpu} particles x {args.dims} dims per step (bounded sample of the workload)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, n_total, sample=False):
+    return {
+        "workload": "C3: 32-D Rosenbrock SMC tempering step (reweight + ESS/beta bisection + exact multinomial "
+                    "resample + 10 pCN moves), BASELINE.json configs[2]",
+        "particles": int(n_total), "dims": args.dims, "pcn_moves": args.moves, "target_efficiency": 0.5,
+        "beta_tolerance": 1e-6, "resampling": "multinomial", "rng": "philox4x32-10",
+        "l2_policy": "inputs (>= 26 GB/GPU at full size) exceed the 126 MB L2; no flush needed",
+        **({"note": "bounded CPU sample of the same workload"} if sample else {}),
+    }
+
+
+# ---------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+
+    from aspire_b200 import _lib, ops
+    from aspire_b200 import targets as tg
+    from aspire_b200.flows import DiagGaussianFlow
+    from aspire_b200.rng import PhiloxRNG
+    from aspire_b200.samplers import SMCSampler
+    from aspire_b200.samples import SMCSamples
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    ops.device_check()
+    if world > 1:
+        from aspire_b200 import distributed as dist_engine
+
+        return dist_engine.run_bench(args, rank, world, dev, METRIC, UNIT, workload_config,
+                                     algorithmic_bytes_per_particle, measured_peaks, ClockSampler, cpu_baseline)
+
+    n, dims, moves = args.particles, args.dims, args.moves
+    prob = tg.rosenbrock_problem(dims, device=dev)
+    flow = DiagGaussianFlow(dims, device=dev, mean=prob["q"].mean_np, sigma=prob["q"].sigma_np, rng=PhiloxRNG(SEED))
+    sampler = SMCSampler(prob["like"], prob["prior"], dims, flow, rng=PhiloxRNG(SEED + 1))
+    sampler._configure_kernel(dict(n_steps=moves, rho=0.5, adapt_rho=False))
+    sampler.resampling = "multinomial"
+    sampler.target_efficiency = 0.5
+    sampler.target_efficiency_rate = 1.0
+    sampler.adaptive, sampler.adaptive_min_beta_step, sampler.max_beta_step = True, False, 1.0
+    from aspire_b200.history import SMCHistory
+
+    sampler.history = SMCHistory()
+
+    # resident particle set P0 (synthetic: drawn from the proposal with Philox)
+    x0, lq0 = flow.sample_and_log_prob(n)
+    p0 = SMCSamples(x0, log_likelihood=prob["like"].log_prob(x0), log_prior=prob["prior"].log_prob(x0), log_q=lq0,
+                    beta=0.0, device=dev)
+    out = (torch.empty(n, dims, dtype=torch.float64, device=dev),
+           *(torch.empty(n, dtype=torch.float64, device=dev) for _ in range(3)))
+    phases = ["beta_search", "resample", "moments", "pcn_sweep"]
+    stream = torch.cuda.current_stream()
+
+    def one_step(record=None):
+        evs = []
+
+        def mark(name):
+            if record is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(stream)
+                evs.append((name, e))
+
+        if record is not None:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            evs.append(("start", e0))
+        p0.__dict__.pop("_slope_cache", None)  # the reweight pass is part of every step
+        new, beta, _ = sampler.tempering_step(p0, 0.0, float("nan"), 0.0, 1e-6, out=out, mark=mark)
+        if record is not None:
+            record.append(evs)
+        return new, beta
+
+    for _ in range(args.warmup):
+        one_step()
+    torch.cuda.synchronize()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    records = []
+    launches0 = _lib.launch_count
+    torch.cuda.synchronize()
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record(stream)
+    for _ in range(args.steps):
+        new, beta = one_step(records)
+    t_end.record(stream)
+    torch.cuda.synchronize()
+    launches = _lib.launch_count - launches0
+    clock_info = clocks.stop()
+    total_ms = t_start.elapsed_time(t_end)
+    ms_per_step = total_ms / args.steps
+    value = n / (ms_per_step * 1e-3)
+
+    phase_ms = {k: 0.0 for k in phases}
+    for evs in records:
+        for (_, a), (name, b) in zip(evs[:-1], evs[1:]):
+            phase_ms[name] += a.elapsed_time(b) / len(records)
+
+    peaks, peak_kind = measured_peaks()
+    sweep_bytes = n * (16 * dims + 48)
+    sweep_ms = phase_ms["pcn_sweep"]
+    achieved = sweep_bytes / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else 0.0
+    roofline = {
+        "kernel": "pcn_sweep_kernel (fused resampling gather + 10 pCN moves)", "bound": "hbm",
+        "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+        "traffic": None, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
+        "algorithmic_bytes_per_launch": sweep_bytes, "ms_per_launch": sweep_ms,
+        "note": "the sweep is bound by fp64 density arithmetic and Philox/Box-Muller issue, not by HBM "
+                "(SURVEY hard part 3); the HBM fraction is reported as the contract asks",
+    }
+    step_bytes = n * algorithmic_bytes_per_particle(dims)
+    step_roofline = {"achieved": step_bytes / (ms_per_step * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "algorithmic_bytes_per_step": step_bytes}
+    step_roofline["frac"] = step_roofline["achieved"] / peaks["hbm_gbs"]
+
+    e2e = run_e2e(args, sampler, prob, flow, dev, out) if not args.no_e2e else None
+    cpu = cpu_baseline(args.cpu_particles, dims, moves) if not args.no_cpu else None
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": workload_config(args, n),
+        "clocks": clock_info, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+        "step_roofline": step_roofline, "cpu_baseline": cpu, "phase_ms": phase_ms,
+        "beta_after_step": beta, "acceptance": sampler.history.mcmc_acceptance[-1],
+        "n_beta_evals": sampler.history.n_beta_evals[-1],
+    }
+    print(json.dumps(line))
+
+
+def run_e2e(args, sampler, prob, flow, dev, out):
+    """Same step through the public sampler API with HOST buffers: pinned host particles -> device,
+    ``tempering_step``, results -> pinned host, all inside the timed region."""
+    import psutil
+    import torch
+
+    from aspire_b200.samples import SMCSamples
+
+    dims = args.dims
+    row_bytes = 8 * (dims + 3)
+    avail = psutil.virtual_memory().available
+    n = min(args.particles, int(0.2 * avail / (2 * row_bytes)))
+    n = max(n, 1)
+    host_in = [torch.empty(n, dims, dtype=torch.float64).pin_memory()] + [
+        torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(3)]
+    host_out = [torch.empty(n, dims, dtype=torch.float64).pin_memory()] + [
+        torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(3)]
+    # fill the host buffers with a real particle set
+    x0, lq0 = flow.sample_and_log_prob(n)
+    for h, d in zip(host_in, (x0, prob["like"].log_prob(x0), prob["prior"].log_prob(x0), lq0)):
+        h.copy_(d)
+    del x0, lq0
+    dev_in = [torch.empty_like(h, device=dev) for h in host_in]
+    out_n = tuple(o[:n] for o in out)
+    stream = torch.cuda.current_stream()
+
+    def step():
+        for d, h in zip(dev_in, host_in):
+            d.copy_(h, non_blocking=True)
+        p = SMCSamples(dev_in[0], log_likelihood=dev_in[1], log_prior=dev_in[2], log_q=dev_in[3], beta=0.0, device=dev)
+        new, _, _ = sampler.tempering_step(p, 0.0, float("nan"), 0.0, 1e-6, out=out_n)
+        for h, d in zip(host_out, (new.x, new.log_likelihood, new.log_prior, new.log_q)):
+            h.copy_(d, non_blocking=True)
+
+    steps = max(1, min(args.steps, 3))
+    step()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    for _ in range(steps):
+        step()
+    b.record(stream)
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    return {"value": n / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n * row_bytes,
+            "d2h_bytes_per_step": n * row_bytes, "particles": n, "ms_per_step": ms, "steps": steps,
+            "api": "SMCSampler.tempering_step on pinned host buffers (H2D + step + D2H timed)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--particles", type=int, default=100_000_000, help="total particles (sharded over --gpus)")
+    ap.add_argument("--dims", type=int, default=32)
+    ap.add_argument("--moves", type=int, default=10)
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong: --particles is the global count (BASELINE config); weak: per GPU")
+    ap.add_argument("--cpu-particles", type=int, default=200_000, help="bounded CPU sample (about 8 s per step)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3  # timing rule: W >= 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -203,10 +203,11 @@ int asp_gather_rows(const double* d_x, int32_t dims, const int64_t* d_idx, int64
  * src/aspire/samplers/smc/base.py:507-519.  Step spec: oracle/pcn.py (parity
  * with minipcn itself is UNPINNED - the package is absent).
  * Reference measure moments: d_moments[1 + 2*dims] = {sum w, sum w x_j, sum w x_j^2}
- * over the local slice with w = exp(dbeta d - c). */
+ * over rows r_i = d_idx ? d_idx[i] : i, i < n, with w = d_d ? exp(dbeta d_d[r_i] - c) : 1
+ * (d_idx given, d_d NULL: plain moments of the resampled ensemble, never materialised). */
 size_t asp_moments_workspace_bytes(int32_t dims);
-int asp_weighted_moments(const double* d_x, int32_t dims, const double* d_d, int64_t n, double dbeta, double c,
-                         double* d_moments, void* ws, void* stream);
+int asp_weighted_moments(const double* d_x, int32_t dims, const int64_t* d_idx, const double* d_d, int64_t n,
+                         double dbeta, double c, double* d_moments, void* ws, void* stream);
 
 typedef struct asp_pcn_params {
     double beta;          /* inverse temperature of the target                  */
