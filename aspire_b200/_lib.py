@@ -81,6 +81,7 @@ class PcnParams(C.Structure):
         ("index0", C.c_int64),
         ("d_xi", C.c_void_p),
         ("d_log_u", C.c_void_p),
+        ("d_slot", C.c_void_p),
     ]
 
 
@@ -115,6 +116,8 @@ SIGNATURES = {
     "asp_cdf_exact": (C.c_int, [_P, _I64, C.c_int, _P, _P, _P]),
     "asp_cdf_info": (C.c_int, [_P, C.POINTER(C.c_int64), _P]),
     "asp_search_multinomial": (C.c_int, [_P, _I64, _P, _I64, _P, _P]),
+    "asp_search_workspace_bytes": (C.c_size_t, [_I64]),
+    "asp_search_multinomial_guided": (C.c_int, [_P, _I64, _P, _I64, _P, _P, _P]),
     "asp_search_systematic": (C.c_int, [_P, _I64, _D, _I64, _I64, _I64, _P, _P]),
     "asp_gather_rows": (C.c_int, [_P, _I32, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _P]),
     "asp_moments_workspace_bytes": (C.c_size_t, [_I32]),
@@ -129,6 +132,8 @@ SIGNATURES = {
         C.c_int,
         [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, C.POINTER(PcnParams), _I32, _P, _P],
     ),
+    "asp_select_workspace_bytes": (C.c_size_t, []),
+    "asp_select_uniforms": (C.c_int, [C.c_uint64, C.c_uint32, _P, _I64, _D, _D, _I64, _P, _P, _P, _P, _P]),
     "asp_philox_uniform": (C.c_int, [C.c_uint64, C.c_uint32, _I64, _I64, _P, _P]),
     "asp_philox_normal": (C.c_int, [C.c_uint64, C.c_uint32, _I64, _I64, _I32, _P, _P, _P, _P]),
 }
@@ -161,7 +166,8 @@ def last_error() -> str:
 
 # kernels launched per successful C call (for bench.py's gpu_launches)
 KERNELS_PER_CALL = {"asp_importance_weights": 3, "asp_cdf_exact": 6, "asp_cdf_tile_stats": 2,
-                    "asp_cdf_set_tile_stats": 2, "asp_cdf_info": 0, "asp_device_check": 0}
+                    "asp_cdf_set_tile_stats": 2, "asp_cdf_info": 0, "asp_device_check": 0,
+                    "asp_search_multinomial_guided": 2, "asp_select_uniforms": 3}
 launch_count = 0
 
 

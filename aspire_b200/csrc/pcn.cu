@@ -12,127 +12,10 @@
 
 #include "common.cuh"
 #include "density.cuh"
+#include "pcn_sweep.cuh"
 #include "philox.cuh"
 
 namespace asp {
-
-struct SweepArgs {
-    const double *x, *ll, *lp, *lq;
-    const int64_t* idx;
-    int64_t n;
-    int dims;
-    asp_density_t like, prior, q;
-    asp_pcn_params_t prm;
-    double *xo, *llo, *lpo, *lqo;
-    unsigned long long* accepts;
-};
-
-__device__ __forceinline__ double tempered(double ll, double lp, double lq, double beta) {
-    const double t = (1.0 - beta) * lq + beta * (ll + lp);
-    return (t != t) ? identity(OP_MAX) : t;
-}
-
-template <int G>
-__device__ __forceinline__ double ref_quad(const double (&x)[kDPL], const double (&mu)[kDPL],
-                                           const double (&isig)[kDPL], int lane, int dims) {
-    double s = 0.0;
-#pragma unroll
-    for (int k = 0; k < kDPL; ++k) {
-        const double z = (x[k] - mu[k]) * isig[k];
-        s += (lane * kDPL + k < dims) ? z * z : 0.0;
-    }
-    return 0.5 * group_sum<G>(s);
-}
-
-constexpr int kMaxMovesSmem = 1024;
-
-template <int G>
-__global__ void __launch_bounds__(kBlock) pcn_sweep_kernel(const SweepArgs A) {
-    __shared__ unsigned int s_acc[kMaxMovesSmem];
-    const int dims = A.dims;
-    const int lane = threadIdx.x % G;
-    const int n_moves = A.prm.n_moves;
-    for (int t = threadIdx.x; t < n_moves; t += blockDim.x) s_acc[t] = 0;
-    __syncthreads();
-
-    DensityLane like, prior, q;
-    density_load(like, A.like, lane, dims);
-    density_load(prior, A.prior, lane, dims);
-    density_load(q, A.q, lane, dims);
-    double mu[kDPL], sg[kDPL], isig[kDPL], rs[kDPL];
-    const double rho = A.prm.rho, beta = A.prm.beta;
-    const double ca = sqrt(1.0 - rho * rho);
-#pragma unroll
-    for (int k = 0; k < kDPL; ++k) {
-        const int j = lane * kDPL + k;
-        mu[k] = j < dims ? __ldg(A.prm.d_mu + j) : 0.0;
-        sg[k] = j < dims ? __ldg(A.prm.d_sigma + j) : 1.0;
-        isig[k] = 1.0 / sg[k];
-        rs[k] = rho * sg[k];
-    }
-    const bool vec = (dims % kDPL == 0) && ((reinterpret_cast<uintptr_t>(A.x) & 15) == 0) &&
-                     ((reinterpret_cast<uintptr_t>(A.xo) & 15) == 0);
-    const bool vec_xi = (dims % kDPL == 0) && ((reinterpret_cast<uintptr_t>(A.prm.d_xi) & 15) == 0);
-    const int64_t groups = ((int64_t)gridDim.x * blockDim.x) / G;
-    const int64_t g0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
-    // warp-uniform trip count: all 32 lanes stay converged for the shuffles
-    const int64_t warp_first = ((int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31)) / G;
-    for (int64_t base = warp_first; base < A.n; base += groups) {
-        const int64_t i_raw = base + (g0 - warp_first);
-        const bool active = i_raw < A.n;
-        const int64_t i = active ? i_raw : A.n - 1;
-        const int64_t src = A.idx ? A.idx[i] : i;
-        double x[kDPL];
-        row_load(A.x, src, dims, lane, vec, x);
-        double ll = A.ll[src], lp = A.lp[src], lq = A.lq[src];
-        double cur = tempered(ll, lp, lq, beta);
-        double rx = ref_quad<G>(x, mu, isig, lane, dims);
-        const uint64_t pidx = (uint64_t)(A.prm.index0 + i);
-        for (int t = 0; t < n_moves; ++t) {
-            double xi[kDPL], log_u;
-            if (A.prm.noise_mode == 0) {
-                float z[4];
-                philox_normal4(A.prm.seed, A.prm.stream0 + (uint32_t)t, pidx, (uint32_t)lane, z);
-#pragma unroll
-                for (int k = 0; k < kDPL; ++k) xi[k] = (double)z[k];
-                double lu = 0.0;
-                if (lane == 0) lu = philox_accept_log_u(A.prm.seed, A.prm.stream0 + (uint32_t)t, pidx);
-                log_u = __shfl_sync(0xffffffffu, lu, 0, G);
-            } else {
-                row_load(A.prm.d_xi + (size_t)t * A.n * dims, i, dims, lane, vec_xi, xi);
-                log_u = A.prm.d_log_u[(size_t)t * A.n + i];
-            }
-            double xp[kDPL];
-#pragma unroll
-            for (int k = 0; k < kDPL; ++k) xp[k] = mu[k] + (ca * (x[k] - mu[k]) + rs[k] * xi[k]);
-            const double lq2 = density_eval<G>(q, xp, lane, dims);
-            const double lp2 = density_eval<G>(prior, xp, lane, dims);
-            const double ll2 = density_eval<G>(like, xp, lane, dims);
-            const double nw = tempered(ll2, lp2, lq2, beta);
-            const double rx2 = ref_quad<G>(xp, mu, isig, lane, dims);
-            const double log_a = (nw - cur) + (rx2 - rx);
-            const bool acc = log_u < log_a;
-            if (acc) {
-#pragma unroll
-                for (int k = 0; k < kDPL; ++k) x[k] = xp[k];
-                ll = ll2; lp = lp2; lq = lq2; cur = nw; rx = rx2;
-            }
-            const unsigned int votes = __ballot_sync(0xffffffffu, acc && active && lane == 0);
-            if ((threadIdx.x & 31) == 0 && votes) atomicAdd(&s_acc[t], __popc(votes));
-        }
-        if (active) {
-            row_store(A.xo, i, dims, lane, vec, x);
-            if (lane == 0) {
-                A.llo[i] = ll;
-                A.lpo[i] = lp;
-                A.lqo[i] = lq;
-            }
-        }
-    }
-    __syncthreads();
-    for (int t = threadIdx.x; t < n_moves; t += blockDim.x)
-        if (s_acc[t]) atomicAdd(&A.accepts[t], (unsigned long long)s_acc[t]);
-}
 
 // ---- unfused halves (user-supplied Python callables evaluate the densities) ----
 template <int G>
@@ -157,7 +40,8 @@ __global__ void __launch_bounds__(kBlock) pcn_propose_kernel(const double* __res
         row_load(xin, i, dims, lane, vec, x);
         if (prm.noise_mode == 0) {
             float z[4];
-            philox_normal4(prm.seed, prm.stream0 + (uint32_t)move, (uint64_t)(prm.index0 + i), (uint32_t)lane, z);
+            philox_normal4(prm.seed, prm.stream0 + (uint32_t)move, (uint64_t)(prm.d_slot ? prm.d_slot[i] : prm.index0 + i),
+                           (uint32_t)lane, z);
 #pragma unroll
             for (int k = 0; k < kDPL; ++k) xi[k] = (double)z[k];
         } else {
@@ -187,7 +71,7 @@ __global__ void __launch_bounds__(kBlock) pcn_accept_kernel(double* __restrict__
     for (int k = 0; k < kDPL; ++k) {
         const int j = lane * kDPL + k;
         mu[k] = j < dims ? __ldg(prm.d_mu + j) : 0.0;
-        isig[k] = j < dims ? 1.0 / __ldg(prm.d_sigma + j) : 1.0;
+        isig[k] = j < dims ? 1.0 / __ldg(prm.d_sigma + j) : 0.0;
     }
     const bool vec = (dims % kDPL == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
                      ((reinterpret_cast<uintptr_t>(xp_) & 15) == 0);
@@ -203,13 +87,12 @@ __global__ void __launch_bounds__(kBlock) pcn_accept_kernel(double* __restrict__
         row_load(xp_, i, dims, lane, vec, xn);
         const double cur = tempered(ll[i], lp[i], lq[i], prm.beta);
         const double nw = tempered(ll2_[i], lp2_[i], lq2_[i], prm.beta);
-        const double rx = ref_quad<G>(xc, mu, isig, lane, dims);
-        const double rx2 = ref_quad<G>(xn, mu, isig, lane, dims);
+        const double rx = ref_quad<G>(xc, mu, isig);
+        const double rx2 = ref_quad<G>(xn, mu, isig);
         double log_u;
         if (prm.noise_mode == 0) {
-            double lu = 0.0;
-            if (lane == 0) lu = philox_accept_log_u(prm.seed, prm.stream0 + (uint32_t)move, (uint64_t)(prm.index0 + i));
-            log_u = __shfl_sync(0xffffffffu, lu, 0, G);
+            log_u = accept_log_u(accept_words(prm.seed, prm.stream0, move,
+                                              (uint64_t)(prm.d_slot ? prm.d_slot[i] : prm.index0 + i)), move);
         } else {
             log_u = prm.d_log_u[(size_t)move * n + i];
         }
@@ -232,13 +115,13 @@ __global__ void __launch_bounds__(kBlock) pcn_accept_kernel(double* __restrict__
 }
 
 // ---- K1: standalone log-density ----
-template <int G>
+template <int G, int KIND>
 __global__ void __launch_bounds__(kBlock) logdensity_kernel(const asp_density_t D, const double* __restrict__ x,
                                                             int64_t n, double* __restrict__ out) {
     const int dims = D.dims;
     const int lane = threadIdx.x % G;
-    DensityLane L;
-    density_load(L, D, lane, dims);
+    Dens<KIND> L;
+    L.load(D, lane, dims);
     const bool vec = (dims % kDPL == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
     const int64_t groups = ((int64_t)gridDim.x * blockDim.x) / G;
     const int64_t g0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
@@ -249,7 +132,7 @@ __global__ void __launch_bounds__(kBlock) logdensity_kernel(const asp_density_t 
         const int64_t i = active ? i_raw : n - 1;
         double v[kDPL];
         row_load(x, i, dims, lane, vec, v);
-        const double r = density_eval<G>(L, v, lane, dims);
+        const double r = L.template eval<G>(v, lane, dims);
         if (active && lane == 0) out[i] = r;
     }
 }
@@ -381,7 +264,21 @@ int asp_logdensity(const asp_density_t* dens, const double* d_x, int64_t n, doub
     if (rc) return rc;
     const int g = group_size_for(dens->dims);
     const int grid = grid_for(n * g, 1);
-    ASP_DISPATCH_G(g, (logdensity_kernel<G><<<grid, kBlock, 0, (cudaStream_t)stream>>>(*dens, d_x, n, d_out)));
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (dens->kind) {
+        case ASP_DENSITY_GAUSSIAN:
+            ASP_DISPATCH_G(g, (logdensity_kernel<G, ASP_DENSITY_GAUSSIAN><<<grid, kBlock, 0, s>>>(*dens, d_x, n, d_out)));
+            break;
+        case ASP_DENSITY_ROSENBROCK:
+            ASP_DISPATCH_G(g, (logdensity_kernel<G, ASP_DENSITY_ROSENBROCK><<<grid, kBlock, 0, s>>>(*dens, d_x, n, d_out)));
+            break;
+        case ASP_DENSITY_GMM:
+            ASP_DISPATCH_G(g, (logdensity_kernel<G, ASP_DENSITY_GMM><<<grid, kBlock, 0, s>>>(*dens, d_x, n, d_out)));
+            break;
+        default:
+            ASP_DISPATCH_G(g, (logdensity_kernel<G, ASP_DENSITY_UNIFORM><<<grid, kBlock, 0, s>>>(*dens, d_x, n, d_out)));
+            break;
+    }
     return check_launch("asp_logdensity");
 }
 
@@ -407,10 +304,21 @@ int asp_pcn_sweep(const double* d_x, const double* d_log_l, const double* d_log_
     SweepArgs A;
     A.x = d_x; A.ll = d_log_l; A.lp = d_log_p; A.lq = d_log_q; A.idx = d_idx; A.n = n; A.dims = dims;
     A.like = *like; A.prior = *prior; A.q = *q; A.prm = *params;
+    A.keys = philox_keys(params->seed);
     A.xo = d_x_out; A.llo = d_log_l_out; A.lpo = d_log_p_out; A.lqo = d_log_q_out; A.accepts = d_accepts;
+    ASP_REQUIRE(q->kind == ASP_DENSITY_GAUSSIAN, "the fused sweep needs a diagonal-Gaussian proposal density");
+    ASP_REQUIRE(prior->kind == ASP_DENSITY_GAUSSIAN || prior->kind == ASP_DENSITY_UNIFORM,
+                "the fused sweep needs a Gaussian or uniform prior");
     const int g = group_size_for(dims);
     const int grid = grid_for(n * g, 1);
-    ASP_DISPATCH_G(g, (pcn_sweep_kernel<G><<<grid, kBlock, 0, (cudaStream_t)stream>>>(A)));
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (like->kind) {
+        case ASP_DENSITY_GAUSSIAN: rc = launch_sweep_gaussian(A, g, grid, s); break;
+        case ASP_DENSITY_ROSENBROCK: rc = launch_sweep_rosenbrock(A, g, grid, s); break;
+        case ASP_DENSITY_GMM: rc = launch_sweep_gmm(A, g, grid, s); break;
+        default: rc = launch_sweep_uniform(A, g, grid, s); break;
+    }
+    if (rc) { set_error("asp_pcn_sweep: unsupported density combination"); return rc; }
     return check_launch("asp_pcn_sweep");
 }
 

@@ -29,18 +29,52 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
     return make_uint4(c0, c1, c2, c3);
 }
 
+// Round keys precomputed on the host and passed by value in the kernel parameters:
+// constant-bank operands fold straight into the LOP3 of each round.
+struct PhiloxKeys {
+    uint32_t k0[10], k1[10];
+};
+inline PhiloxKeys philox_keys(uint64_t seed) {
+    PhiloxKeys K;
+    uint32_t a = (uint32_t)seed, b = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+        K.k0[r] = a;
+        K.k1[r] = b;
+        a += kPhiloxW0;
+        b += kPhiloxW1;
+    }
+    return K;
+}
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                               const PhiloxKeys& K) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(kPhiloxM0, c0), lo0 = kPhiloxM0 * c0;
+        const uint32_t hi1 = __umulhi(kPhiloxM1, c2), lo1 = kPhiloxM1 * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ K.k0[r], n2 = hi0 ^ c3 ^ K.k1[r];
+        c0 = n0;
+        c1 = lo1;
+        c2 = n2;
+        c3 = lo0;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
 // fp32 uniform in (0, 1]
 __device__ __forceinline__ float u01_f32(uint32_t r) { return fmaf(__uint2float_rn(r), 0x1p-32f, 0x1p-33f); }
 
-// two fp32 normals from two words
+// two fp32 normals from two words: Box-Muller on the SFU (MUFU.LG2 / RSQ / SIN / COS).
+//   u = fma(ra, 2^-32, 2^-33) in (0, 1],  s = sqrt(-2 ln u) = sqrt(-2 ln2 * log2 u)
+//   theta = pi * t,  t = fma(rb, 2^-31, -1) in [-1, 1]   (the SFU's accurate range)
+// Absolute error of a normal ~1e-6 (spec: oracle/philox.py::box_muller_f32).
 __device__ __forceinline__ void box_muller_f32(uint32_t ra, uint32_t rb, float& z0, float& z1) {
     const float u = u01_f32(ra);
-    const float t = fmaf(__uint2float_rn(rb), 0x1p-31f, 0x1p-32f);
-    const float s = sqrtf(-2.0f * logf(u));
-    float sn, cs;
-    sincospif(t, &sn, &cs);
-    z0 = s * cs;
-    z1 = s * sn;
+    const float t = fmaf(__uint2float_rn(rb), 0x1p-31f, -1.0f);
+    const float x = -1.3862943611198906f * __log2f(u);
+    const float s = x * rsqrtf(fmaxf(x, 1e-30f));
+    const float th = 3.14159265358979f * t;
+    z0 = s * __cosf(th);
+    z1 = s * __sinf(th);
 }
 
 // four fp32 normals for (element index, stream, block)
@@ -52,11 +86,11 @@ __device__ __forceinline__ void philox_normal4(uint64_t seed, uint32_t stream, u
     box_muller_f32(r.z, r.w, z[2], z[3]);
 }
 
-// log(u) for the accept/reject test, fp32 logf promoted to fp64
-__device__ __forceinline__ double philox_accept_log_u(uint64_t seed, uint32_t stream, uint64_t index) {
-    const uint4 r = philox4x32_10((uint32_t)index, (uint32_t)(index >> 32), stream, kAcceptBlock, (uint32_t)seed,
-                                  (uint32_t)(seed >> 32));
-    return (double)logf(u01_f32(r.x));
+__device__ __forceinline__ void philox_normal4(const PhiloxKeys& K, uint32_t stream, uint64_t index, uint32_t block,
+                                               float (&z)[4]) {
+    const uint4 r = philox4x32_10((uint32_t)index, (uint32_t)(index >> 32), stream, block, K);
+    box_muller_f32(r.x, r.y, z[0], z[1]);
+    box_muller_f32(r.z, r.w, z[2], z[3]);
 }
 
 __device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {

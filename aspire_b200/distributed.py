@@ -1,0 +1,319 @@
+"""Particles sharded over the GPUs of one box: one process per GPU, ``torch.distributed``
+(NCCL over NVLink) for the plumbing.  No reference site - the reference is a single
+process; the per-rank arithmetic is the same C-ABI as on one GPU.
+
+Rank r owns a contiguous slice of the particle set (and of the weights / CDF).  Per
+tempering step the ranks exchange only scalars:
+
+* ``max``  all-reduce of {-min d, max d, #NaN, #inf}                       (1 x 4 doubles)
+* ``sum``  all-reduce of (S1, S2) per bisection pass                      (~22 x 2 doubles)
+* all-gather of {sum p, max p, var-sum, n} per rank                      (1 x 4 doubles)
+* exact-CDF carry chain: rank r-1 -> r, {exact running sum, running max} (G-1 hops x 2 doubles)
+* broadcast of the exact total                                           (1 double)
+* ``sum``  all-reduce of the pCN reference-measure moments                (1 + 2 D doubles)
+* ``sum``  all-reduce of the accept counters                              (n_moves int64)
+
+Resampling is OWNER-COMPUTES: every rank walks the same global stream of uniforms and
+keeps the output slots whose ancestor lies in its own CDF slice (``asp_select_uniforms``),
+so offspring are born on the rank that holds their ancestor and no particle row crosses
+NVLink.  The union over ranks of (slot, ancestor) is exactly the single-GPU result;
+shard sizes drift by O(sqrt(N/G)) per step (multinomial noise), far inside the buffers'
+head-room.  Particle order in the global array becomes (rank, slot) - a permutation of
+the single-process order, harmless because SMC particles are exchangeable.
+"""
+
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import torch
+
+
+class Comm:
+    """Thin wrapper over ``torch.distributed`` (NCCL on GPUs, gloo in the CPU tests)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+
+    def all_reduce_sum(self, t):
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def all_reduce_max(self, t):
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
+        return t
+
+    def all_gather(self, t):
+        out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        self.dist.all_gather_into_tensor(out.view(-1), t.contiguous().view(-1), group=self.group) \
+            if t.is_cuda else self.dist.all_gather(list(out.unbind(0)), t.contiguous(), group=self.group)
+        return out
+
+    def send(self, t, dst):
+        self.dist.send(t, dst, group=self.group)
+
+    def recv(self, t, src):
+        self.dist.recv(t, src, group=self.group)
+
+    def broadcast(self, t, src):
+        self.dist.broadcast(t, src, group=self.group)
+        return t
+
+    def barrier(self):
+        self.dist.barrier(group=self.group)
+
+
+@dataclass
+class Shard:
+    """This rank's particles: rows + logs + the global output slot of every row
+    (the Philox counter of its noise; contiguous at the start of a run)."""
+
+    x: torch.Tensor
+    log_l: torch.Tensor
+    log_p: torch.Tensor
+    log_q: torch.Tensor
+    slot: torch.Tensor | None = None
+
+    def __len__(self):
+        return self.x.shape[0]
+
+
+@dataclass
+class StepRecord:
+    beta: float
+    ess: float
+    ess_target: float
+    log_norm_ratio: float
+    log_norm_ratio_var: float
+    acceptance: float
+    n_total: int
+    n_local_out: int
+    n_beta_evals: int
+
+
+class ShardedSMC:
+    """One tempering step over sharded particles.  ``backend`` is ``aspire_b200.ops``
+    (the CPU tests inject an oracle-backed stand-in with the same functions)."""
+
+    def __init__(self, comm: Comm, like, prior, q, backend=None, seed: int = 0, n_moves: int = 10, rho: float = 0.5,
+                 target_efficiency: float = 0.5, beta_tolerance: float = 1e-6, headroom: float = 1.05):
+        if backend is None:
+            from . import ops as backend
+        self.ops = backend
+        self.comm = comm
+        self.like, self.prior, self.q = like, prior, q
+        self.seed = int(seed)
+        self.n_moves, self.rho = int(n_moves), float(rho)
+        self.target_efficiency, self.beta_tolerance = float(target_efficiency), float(beta_tolerance)
+        self.headroom = headroom
+        self._stream = 0
+
+    def next_stream(self, count=1):
+        s = self._stream
+        self._stream += count
+        return s
+
+    # -- global reweighting statistics ------------------------------------------
+    def global_stats(self, stats_local):
+        g = torch.stack([-stats_local[0], stats_local[1], stats_local[2], stats_local[3]])
+        self.comm.all_reduce_max(g)
+        return torch.stack([-g[0], g[1], g[2], g[3]]).contiguous()
+
+    # -- exact CDF over all ranks -------------------------------------------------
+    def global_cdf(self, p, tiles, info, n_total, mark=None):
+        """-> (local slice of the global normalised CDF, lo, hi): this rank's slice covers (lo, hi]."""
+        ops, comm = self.ops, self.comm
+        r, g = comm.rank, comm.world
+        dev = p.device
+        gathered = comm.all_gather(info)                     # [G, 4] = {sum p, max p, var-sum, n}
+        host = gathered.cpu()
+        offset = float(host[:r, 0].sum()) if r > 0 else 0.0
+        max_in = float(host[:r, 1].max()) if r > 0 else 0.0
+        carry = torch.tensor([offset, max_in, 0.0, float(n_total)], dtype=torch.float64, device=dev)
+        ops.cdf_plan_aggregate(p, tiles, carry)
+        if mark:
+            mark("cdf_local")
+        if r > 0:                                            # exact carry chain: rank r-1 -> r
+            inc = torch.empty(2, dtype=torch.float64, device=dev)
+            comm.recv(inc, r - 1)
+            carry[2] = inc[0]
+            carry[1] = torch.maximum(carry[1], inc[1])
+        carry_out = ops.cdf_resolve(p, carry)
+        if r < g - 1:
+            comm.send(carry_out, r + 1)
+        total = carry_out[:1].clone()
+        comm.broadcast(total, g - 1)
+        cdf = ops.cdf_write(p, total)
+        th = float(total)
+        lo = float(carry[2]) / th if r > 0 else 0.0          # == global cdf just before this slice (IEEE division)
+        hi = 1.0 if r == g - 1 else float(cdf[-1])
+        return cdf, lo, hi, host
+
+    # -- one tempering step ---------------------------------------------------------
+    def step(self, shard: Shard, beta_prev: float, u_all=None, mark=None) -> tuple[Shard, StepRecord]:
+        ops, comm = self.ops, self.comm
+        mark = mark or (lambda name: None)
+        dev = shard.x.device
+        n_local = len(shard)
+        d, stats_local = ops.reweight(shard.log_l, shard.log_p, shard.log_q)
+        stats = self.global_stats(stats_local)
+        counts = torch.tensor([float(n_local)], dtype=torch.float64, device=dev)
+        comm.all_reduce_sum(counts)
+        st = stats.cpu().numpy()
+        n_total = int(round(float(counts[0])))
+        if st[2] > 0 or st[3] > 0:
+            raise ValueError(f"Log weights contain NaN values for beta={beta_prev}")
+        state = ops.beta_search(d, stats, beta_prev, self.target_efficiency, self.beta_tolerance, n_total=n_total,
+                                allreduce=comm.all_reduce_sum)
+        mark("beta_search")
+        beta = min(max(state.beta_min, beta_prev), 1.0)
+        if beta == beta_prev:
+            raise RuntimeError(f"Beta did not increase from previous value {beta:.6g}.")
+        dbeta = beta - beta_prev
+        c = dbeta * st[1]
+        if state.min_valid:
+            s1, s2 = state.s1_min, state.s2_min
+        else:  # not reachable with max_beta_step = 1: beta* is always an evaluated beta
+            sums = ops.ess_sums(d, [dbeta], stats).reshape(-1).clone()
+            comm.all_reduce_sum(sums)
+            s1, s2 = float(sums[0]), float(sums[1])
+        p, result, tiles = ops.smc_weights(d, dbeta, c, s1, n_total=n_total)
+        info = torch.stack([result[1], tiles[1::2].max(), result[0], counts[0] * 0 + n_local]).contiguous()
+        cdf, lo, hi, host = self.global_cdf(p, tiles, info, n_total, mark)
+        var_sum = float(host[:, 2].sum())
+        mean_u = s1 / n_total
+        mark("cdf")
+        # owner-computes multinomial resampling
+        stream_u = self.next_stream()
+        capacity = int(max(n_local, n_total / comm.world) * self.headroom) + 1024
+        slot, u = ops.select_uniforms(n_total, lo, hi, capacity, dev, seed=self.seed, stream_id=stream_u, u_all=u_all)
+        idx = ops.search_multinomial(cdf, u)
+        n_out = slot.numel()
+        mark("resample")
+        dims = shard.x.shape[1]
+        mom = ops.weighted_moments(shard.x, idx=idx)
+        comm.all_reduce_sum(mom)
+        mu, sigma = ops.moments_to_mu_sigma(mom, dims)
+        sigma = torch.clamp_min(sigma, 1e-150)
+        mark("moments")
+        prm = ops.make_pcn_params(beta, self.rho, mu, sigma, self.n_moves, seed=self.seed,
+                                  stream0=self.next_stream(self.n_moves) + 0x40000000, slot=slot)
+        x, ll, lp, lq, accepts = ops.pcn_sweep(shard.x, shard.log_l, shard.log_p, shard.log_q, idx, self.like,
+                                               self.prior, self.q, prm)
+        mark("pcn_sweep")
+        acc = accepts.sum().reshape(1).to(torch.float64)
+        comm.all_reduce_sum(acc)
+        rec = StepRecord(
+            beta=beta, ess=s1 * s1 / s2, ess_target=state.eff_beta_max * n_total,
+            log_norm_ratio=c + math.log(s1) - math.log(n_total),
+            log_norm_ratio_var=var_sum / n_total / (n_total * mean_u * mean_u) if mean_u != 0 else math.nan,
+            acceptance=float(acc[0]) / max(self.n_moves * n_total, 1), n_total=n_total, n_local_out=n_out,
+            n_beta_evals=state.n_evals)
+        return Shard(x, ll, lp, lq, slot), rec
+
+
+# ---------------------------------------------------------------------------------
+# bench.py --gpus N (N > 1): launched by torch.distributed.run, one rank per GPU
+# ---------------------------------------------------------------------------------
+def run_bench(args, rank, world, dev, metric, unit, workload_config, bytes_per_particle, measured_peaks, ClockSampler,
+              cpu_baseline):
+    import json
+
+    import torch.distributed as dist
+
+    from . import _lib, ops
+    from . import targets as tg
+
+    dist.init_process_group("nccl", device_id=dev)
+    comm = Comm()
+    dims, moves = args.dims, args.moves
+    n_total = args.particles if args.scaling == "strong" else args.particles * world
+    base = n_total // world
+    n_local = base + (1 if rank < n_total % world else 0)
+    start = rank * base + min(rank, n_total % world)
+    prob = tg.rosenbrock_problem(dims, device=dev)
+    seed = 20251104
+    # P0: the same global particle set as the single-GPU run, this rank's contiguous slice
+    x0 = ops.philox_normal(seed, 0, n_local, dims, dev, mean=prob["q"].mean, sigma=prob["q"].sigma, index0=start)
+    shard0 = Shard(x0, prob["like"].log_prob(x0), prob["prior"].log_prob(x0), prob["q"].log_prob(x0))
+    engine = ShardedSMC(comm, prob["like"], prob["prior"], prob["q"], seed=seed + 1, n_moves=moves, rho=0.5)
+    phases = ["beta_search", "cdf_local", "cdf", "resample", "moments", "pcn_sweep"]
+    stream = torch.cuda.current_stream()
+
+    def one_step(record=None):
+        evs = []
+
+        def mark(name):
+            if record is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(stream)
+                evs.append((name, e))
+
+        mark("start")
+        new, rec = engine.step(shard0, 0.0, mark=mark)
+        if record is not None:
+            record.append(evs)
+        return new, rec
+
+    for _ in range(max(args.warmup, 3)):
+        one_step()
+    torch.cuda.synchronize()
+    comm.barrier()
+    clocks = ClockSampler(dev.index)
+    clocks.start()
+    records = []
+    launches0 = _lib.launch_count
+    torch.cuda.synchronize()
+    comm.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    for _ in range(args.steps):
+        new, rec = one_step(records)
+    b.record(stream)
+    torch.cuda.synchronize()
+    comm.barrier()
+    launches = _lib.launch_count - launches0
+    clock_info = clocks.stop()
+    ms = torch.tensor([a.elapsed_time(b) / args.steps], dtype=torch.float64, device=dev)
+    comm.all_reduce_max(ms)                                  # max over ranks, device-timed
+    ms_per_step = float(ms[0])
+    phase_ms = {k: 0.0 for k in phases}
+    for evs in records:
+        for (_, e0), (name, e1) in zip(evs[:-1], evs[1:]):
+            phase_ms[name] += e0.elapsed_time(e1) / len(records)
+    pm = torch.tensor([phase_ms[k] for k in phases], dtype=torch.float64, device=dev)
+    comm.all_reduce_max(pm)
+    phase_ms = {k: float(v) for k, v in zip(phases, pm)}
+    if rank == 0:
+        peaks, kind = measured_peaks()
+        value = n_total / (ms_per_step * 1e-3)
+        sweep_bytes = (n_total / world) * (16 * dims + 48)
+        sweep_ms = phase_ms["pcn_sweep"]
+        ach = sweep_bytes / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else 0.0
+        step_bytes = (n_total / world) * bytes_per_particle(dims)
+        step_ach = step_bytes / (ms_per_step * 1e-3) / 1e9
+        line = {
+            "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {**workload_config(args, n_total), "parallelism": f"particle-sharded x{world}, owner-computes "
+                       "resampling, scalar NCCL collectives only"},
+            "clocks": clock_info, "gpu_launches": launches,
+            "e2e": None,
+            "roofline": {"kernel": "pcn_sweep_kernel (per GPU)", "bound": "hbm", "achieved": ach,
+                         "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,
+                         "peak_source": f"MEASURED_PEAKS.json ({kind})",
+                         "note": "issue-bound kernel (fp64 + Philox); HBM fraction reported as the contract asks"},
+            "step_roofline": {"achieved": step_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s per GPU",
+                              "frac": step_ach / peaks["hbm_gbs"]},
+            "cpu_baseline": None, "phase_ms": phase_ms, "beta_after_step": rec.beta, "acceptance": rec.acceptance,
+            "n_local_out": rec.n_local_out,
+        }
+        print(json.dumps(line))
+    dist.destroy_process_group()

@@ -59,10 +59,10 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.gpu_index = gpu_index
         self.rows = []
-        self._stop = threading.Event()
+        self._halt = threading.Event()
 
     def run(self):
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
                                       "-i", str(self.gpu_index)], capture_output=True, text=True, timeout=5).stdout
@@ -70,10 +70,10 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in line.split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._halt.wait(0.2)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=5)
         sm, mx, reasons = [], [], set()
         for r in self.rows:

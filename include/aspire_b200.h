@@ -187,6 +187,12 @@ int asp_cdf_info(void* ws, int64_t* h_info, void* stream);
  * index by the caller when the CDF is a shard of a larger one. */
 int asp_search_multinomial(const double* d_cdf, int64_t n_cdf, const double* d_u, int64_t m, int64_t* d_idx,
                            void* stream);
+/* Same result through a guide table (one pass over the CDF to build it, then ~3
+ * random sectors per ancestor instead of a log2(n)-deep dependent chain); worth it
+ * when m is comparable to n_cdf.  ws: asp_search_workspace_bytes(n_cdf). */
+size_t asp_search_workspace_bytes(int64_t n_cdf);
+int asp_search_multinomial_guided(const double* d_cdf, int64_t n_cdf, const double* d_u, int64_t m, int64_t* d_idx,
+                                  void* ws, void* stream);
 int asp_search_systematic(const double* d_cdf, int64_t n_cdf, double u0, int64_t j0, int64_t m,
                           int64_t m_total, int64_t* d_idx, void* stream);
 
@@ -222,6 +228,8 @@ typedef struct asp_pcn_params {
     int64_t index0;       /* global index of local particle 0 (Philox counter)  */
     const double* d_xi;   /* [n_moves, n, dims] normals (noise_mode 1)          */
     const double* d_log_u;/* [n_moves, n] log-uniforms   (noise_mode 1)         */
+    const int64_t* d_slot;/* optional per-particle Philox counter (global output
+                             slot); NULL: index0 + i                            */
 } asp_pcn_params_t;
 
 /* Fused sweep: particle i starts from row d_idx[i] of the inputs (d_idx NULL
@@ -243,6 +251,17 @@ int asp_pcn_accept(double* d_x, double* d_log_l, double* d_log_p, double* d_log_
                    const double* d_log_l_prop, const double* d_log_p_prop, const double* d_log_q_prop, int64_t n,
                    int32_t dims, const asp_pcn_params_t* params, int32_t move, unsigned long long* d_accepts,
                    void* stream);
+
+/* ---- owner-computes multinomial resampling across GPUs (K12) ---------------
+ * (no reference site: the reference is single-process.)  Every rank walks the same
+ * global stream of n_total uniforms - Philox (seed, stream_id), identical to
+ * asp_philox_uniform, or the supplied device array d_u_all (parity mode) - and
+ * keeps, in slot order, the (slot j, u_j) with lo <= u_j < hi, i.e. the output slots
+ * whose ancestor lives in this rank's CDF slice.  d_count receives how many; at most
+ * `capacity` are written. */
+size_t asp_select_workspace_bytes(void);
+int asp_select_uniforms(uint64_t seed, uint32_t stream_id, const double* d_u_all, int64_t n_total, double lo, double hi,
+                        int64_t capacity, int64_t* d_slot, double* d_u, long long* d_count, void* ws, void* stream);
 
 /* ---- counter-based RNG (K13) --------------------------------------------
  * Philox4x32-10; layouts in oracle/philox.py.  uniform: fp64 in [0,1) with

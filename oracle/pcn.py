@@ -53,10 +53,11 @@ def propose(x, mu, sigma, rho, xi):
 
 
 def sweep(x, log_l, log_p, log_q, *, like, prior, q, beta, mu, sigma, rho, n_moves,
-          xi=None, log_u=None, seed=None, stream0=0, index0=0):
+          xi=None, log_u=None, seed=None, stream0=0, index0=0, index=None):
     """Run ``n_moves`` pCN moves.  Noise is either supplied (``xi`` [M,N,D],
     ``log_u`` [M,N]; parity mode) or generated with Philox (``seed``; move t
-    uses stream ``stream0 + t``, particle i uses element index ``index0 + i``).
+    uses stream ``stream0 + t``, particle i uses element index ``index0 + i``, or
+    ``index[i]`` when per-particle output slots are given).
     Returns (x, log_l, log_p, log_q, accepts_per_move)."""
     x = np.array(x, dtype=np.float64)
     log_l = np.array(log_l, dtype=np.float64)
@@ -65,14 +66,15 @@ def sweep(x, log_l, log_p, log_q, *, like, prior, q, beta, mu, sigma, rho, n_mov
     n, d = x.shape
     inv_sigma = 1.0 / sigma
     accepts = np.zeros(n_moves, dtype=np.int64)
-    index = np.arange(index0, index0 + n, dtype=np.uint64)
+    index = (np.arange(index0, index0 + n, dtype=np.uint64) if index is None
+             else np.asarray(index, dtype=np.uint64))
     for t in range(n_moves):
         if xi is not None:
             z = xi[t]
             lu = log_u[t]
         else:
             z = philox.normals_f32(seed, stream0 + t, index, d).astype(np.float64)
-            lu = philox.accept_log_uniform(seed, stream0 + t, index)
+            lu = philox.accept_log_uniform(seed, stream0, t, index)
         xp = propose(x, mu, sigma, rho, z)
         lq2 = densities.evaluate(q, xp)
         lp2 = densities.evaluate(prior, xp)

@@ -81,19 +81,18 @@ def _u01_f32(r):
 
 
 def box_muller_f32(ra, rb):
-    """Two fp32 normals from two uint32 words: ``s = sqrt(-2 log u)``,
-    ``(s cos(pi t), s sin(pi t))`` with ``u = fma(ra,2^-32,2^-33)``,
-    ``t = fma(rb, 2^-31, 2^-32)``.  fp32 throughout (CUDA ``logf``,
-    ``sincospif``; numpy float32 here - they agree to ~1 ulp, not bit for bit)."""
+    """Two fp32 normals from two uint32 words:
+    ``u = fma(ra, 2^-32, 2^-33)``, ``s = sqrt(-2 ln2 * log2(u))``,
+    ``theta = pi * t`` with ``t = fma(rb, 2^-31, -1)`` in [-1, 1],
+    ``(s cos(theta), s sin(theta))``.  The kernel evaluates log2 / rsqrt / sin /
+    cos on the SFU (absolute error ~1e-6 per normal); numpy float32 here - they
+    agree to ~1e-6, not bit for bit."""
     u = _u01_f32(ra)
-    t = (rb.astype(np.float32) * np.float32(2.0**-31) + np.float32(2.0**-32)).astype(np.float32)
-    s = np.sqrt(np.float32(-2.0) * np.log(u)).astype(np.float32)
-    ang = (np.float32(np.pi) * t).astype(np.float32)
-    # evaluate the trig in fp64 and round: closer to CUDA's sincospif than fp32 sin(pi*t)
-    c = np.cos(np.pi * t.astype(np.float64)).astype(np.float32)
-    sn = np.sin(np.pi * t.astype(np.float64)).astype(np.float32)
-    del ang
-    return (s * c).astype(np.float32), (s * sn).astype(np.float32)
+    t = (rb.astype(np.float32) * np.float32(2.0**-31) + np.float32(-1.0)).astype(np.float32)
+    x = (np.float32(-1.3862943611198906) * np.log2(u)).astype(np.float32)
+    s = np.sqrt(x).astype(np.float32)
+    th = (np.float32(3.14159265358979) * t).astype(np.float64)
+    return (s * np.cos(th).astype(np.float32)).astype(np.float32), (s * np.sin(th).astype(np.float32)).astype(np.float32)
 
 
 def normal_block_f32(seed: int, stream: int, index, block) -> np.ndarray:
@@ -115,13 +114,14 @@ def normals_f32(seed: int, stream: int, index, dims: int) -> np.ndarray:
     return z.reshape(len(index), nblk * 4)[:, :dims]
 
 
-def accept_log_uniform(seed: int, stream: int, index) -> np.ndarray:
-    """``log(u)`` for the accept/reject test: fp32 ``logf`` of word 0 of block
-    0xFFFFFFFF, promoted to fp64."""
+def accept_log_uniform(seed: int, stream0: int, move: int, index) -> np.ndarray:
+    """``log(u)`` for the accept/reject test of move ``move``: fp32 ``logf`` of word
+    ``move & 3`` of block 0xFFFFFFFF of stream ``stream0 + (move & ~3)`` (one Philox
+    call serves four moves), promoted to fp64."""
     c0, c1 = _split(index)
     k0, k1 = _key(seed)
-    r = philox4x32(c0, c1, np.uint32(stream), np.uint32(ACCEPT_BLOCK), k0, k1)
-    return np.log(_u01_f32(r[0])).astype(np.float32).astype(np.float64)
+    r = philox4x32(c0, c1, np.uint32((stream0 + (move & ~3)) & 0xFFFFFFFF), np.uint32(ACCEPT_BLOCK), k0, k1)
+    return np.log(_u01_f32(r[move & 3])).astype(np.float32).astype(np.float64)
 
 
 def normal_f64(seed: int, stream: int, index, dims: int) -> np.ndarray:

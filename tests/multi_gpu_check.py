@@ -1,0 +1,85 @@
+"""Launched by torchrun (one rank per GPU) from tests/test_gpu_multi.py: the sharded
+step on G GPUs against the single-GPU step on rank 0 (same global particles, same
+Philox streams).  Exits non-zero on mismatch."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from aspire_b200 import ops  # noqa: E402
+from aspire_b200 import targets as tg  # noqa: E402
+from aspire_b200.distributed import Comm, Shard, ShardedSMC  # noqa: E402
+
+
+def main():
+    n_total = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_003
+    dims, moves, seed = 32, 4, 4242
+    local_rank = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist.init_process_group("nccl", device_id=dev)
+    comm = Comm()
+    r, g = comm.rank, comm.world
+    prob = tg.rosenbrock_problem(dims, device=dev)
+    base = n_total // g
+    n_local = base + (1 if r < n_total % g else 0)
+    start = r * base + min(r, n_total % g)
+    x0 = ops.philox_normal(seed, 0, n_local, dims, dev, mean=prob["q"].mean, sigma=prob["q"].sigma, index0=start)
+    shard = Shard(x0, prob["like"].log_prob(x0), prob["prior"].log_prob(x0), prob["q"].log_prob(x0))
+    eng = ShardedSMC(comm, prob["like"], prob["prior"], prob["q"], seed=seed + 1, n_moves=moves, rho=0.5)
+    new, rec = eng.step(shard, 0.0)
+    # gather (slot, x, logL) on rank 0
+    cnt = torch.tensor([len(new)], dtype=torch.int64, device=dev)
+    counts = comm.all_gather(cnt).reshape(-1).tolist()
+    cap = max(counts)
+    pad = lambda t: torch.cat([t, t.new_zeros((cap - t.shape[0],) + tuple(t.shape[1:]))])  # noqa: E731
+    slots = comm.all_gather(pad(new.slot))
+    xs = comm.all_gather(pad(new.x))
+    lls = comm.all_gather(pad(new.log_l))
+    ok = True
+    if r == 0:
+        slot = torch.cat([slots[i, :c] for i, c in enumerate(counts)])
+        x = torch.cat([xs[i, :c] for i, c in enumerate(counts)])
+        ll = torch.cat([lls[i, :c] for i, c in enumerate(counts)])
+        assert sorted(slot.tolist()) == list(range(n_total)), "slots are not a partition"
+        order = torch.argsort(slot)
+        # single-GPU reference: the same engine with a trivial communicator
+        class Solo(Comm):
+            def __init__(self):
+                self.rank, self.world = 0, 1
+            def all_reduce_sum(self, t): return t
+            def all_reduce_max(self, t): return t
+            def all_gather(self, t): return t.unsqueeze(0)
+            def broadcast(self, t, src): return t
+            def send(self, t, dst): pass
+            def recv(self, t, src): pass
+            def barrier(self): pass
+        xg = ops.philox_normal(seed, 0, n_total, dims, dev, mean=prob["q"].mean, sigma=prob["q"].sigma)
+        full = Shard(xg, prob["like"].log_prob(xg), prob["prior"].log_prob(xg), prob["q"].log_prob(xg))
+        solo = ShardedSMC(Solo(), prob["like"], prob["prior"], prob["q"], seed=seed + 1, n_moves=moves, rho=0.5)
+        ref, rrec = solo.step(full, 0.0)
+        assert torch.equal(ref.slot, torch.arange(n_total, device=dev))
+        assert rrec.beta == rec.beta, (rrec.beta, rec.beta)
+        np.testing.assert_allclose(rec.ess, rrec.ess, rtol=1e-12)
+        np.testing.assert_allclose(rec.log_norm_ratio, rrec.log_norm_ratio, rtol=1e-12)
+        np.testing.assert_allclose(rec.log_norm_ratio_var, rrec.log_norm_ratio_var, rtol=1e-10)
+        dx = (x[order] - ref.x).abs().max(dim=1).values
+        frac_bad = float((dx > 1e-9).double().mean())
+        print(f"G={g} N={n_total} beta={rec.beta:.6g} acc={rec.acceptance:.4f} shard sizes={counts} "
+              f"max|dx|={float(dx.max()):.3e} frac(|dx|>1e-9)={frac_bad:.2e}")
+        ok = frac_bad < 1e-5 and abs(rec.acceptance - rrec.acceptance) < 1e-5
+        np.testing.assert_allclose(ll[order][dx <= 1e-9].cpu().numpy(), ref.log_l[dx <= 1e-9].cpu().numpy(),
+                                   rtol=1e-9, atol=1e-9)
+    flag = torch.tensor([1.0 if ok else 0.0], device=dev)
+    comm.broadcast(flag, 0)
+    dist.destroy_process_group()
+    sys.exit(0 if float(flag[0]) == 1.0 else 1)
+
+
+if __name__ == "__main__":
+    main()

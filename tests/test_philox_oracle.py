@@ -29,5 +29,5 @@ def test_moments():
     assert abs(z.mean()) < 5e-3 and abs(z.std() - 1) < 5e-3
     z = philox.normal_f64(1, 3, np.arange(200_000), 3)
     assert abs(z.mean()) < 5e-3 and abs(z.std() - 1) < 5e-3
-    lu = philox.accept_log_uniform(1, 4, np.arange(100_000))
+    lu = philox.accept_log_uniform(1, 4, 2, np.arange(100_000))
     assert abs(lu.mean() + 1.0) < 2e-2
