@@ -55,7 +55,7 @@ __device__ __forceinline__ uint4 accept_words(const PhiloxKeys& K, uint32_t stre
 }
 __device__ __forceinline__ double accept_log_u(const uint4& w, int move) {
     const uint32_t r = (move & 3) == 0 ? w.x : (move & 3) == 1 ? w.y : (move & 3) == 2 ? w.z : w.w;
-    return (double)logf(u01_f32(r));
+    return (double)sfu_log(u01_f32(r));
 }
 
 // The accept/reject test only needs  T(x') - T(x),
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(kBlock, ASP_SWEEP_MIN_BLOCKS) pcn_sweep_kernel
     const int dims = A.dims;
     const int lane = threadIdx.x % G;
     const int n_moves = A.prm.n_moves;
-    for (int t = threadIdx.x; t < n_moves; t += blockDim.x) s_acc[t] = 0;
+    for (int t = threadIdx.x; t < max(n_moves, 1); t += blockDim.x) s_acc[t] = 0;
     __syncthreads();
 
     constexpr bool kLikeQuad = LIKE == ASP_DENSITY_GAUSSIAN;
@@ -160,6 +160,8 @@ __global__ void __launch_bounds__(kBlock, ASP_SWEEP_MIN_BLOCKS) pcn_sweep_kernel
                      ((reinterpret_cast<uintptr_t>(A.xo) & 15) == 0);
     const bool vec_xi = (dims % kDPL == 0) && ((reinterpret_cast<uintptr_t>(A.prm.d_xi) & 15) == 0);
     const bool philox = A.prm.noise_mode == 0;
+    const bool per_move = A.prm.reserved == 0;  // reserved = 1: only the total lands in accepts[0]
+    unsigned int n_acc = 0;
     const int64_t groups = ((int64_t)gridDim.x * blockDim.x) / G;
     const int64_t g0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
     // warp-uniform trip count: all 32 lanes stay converged for the shuffles
@@ -183,6 +185,7 @@ __global__ void __launch_bounds__(kBlock, ASP_SWEEP_MIN_BLOCKS) pcn_sweep_kernel
             for (int k = 0; k < kDPL; ++k) x[k] = mu[k] + y[k];
             cur = target(y, x);
         }
+        if (!active) cur = identity(OP_MIN);  // +inf: a padding group never accepts, so the loop needs no mask
         bool moved = false;
         const uint64_t pidx = (uint64_t)(A.prm.d_slot ? A.prm.d_slot[i] : A.prm.index0 + i);
         uint4 aw = make_uint4(0, 0, 0, 0);
@@ -213,8 +216,12 @@ __global__ void __launch_bounds__(kBlock, ASP_SWEEP_MIN_BLOCKS) pcn_sweep_kernel
                 cur = nw;
                 moved = true;
             }
-            const unsigned int votes = __ballot_sync(0xffffffffu, acc && active && lane == 0);
-            if ((threadIdx.x & 31) == 0 && votes) atomicAdd(&s_acc[t], __popc(votes));
+            if (per_move) {
+                const unsigned int votes = __ballot_sync(0xffffffffu, acc && lane == 0);
+                if ((threadIdx.x & 31) == 0 && votes) atomicAdd(&s_acc[t], __popc(votes));
+            } else {
+                n_acc += acc ? 1u : 0u;
+            }
         }
         // final state and its logs: carried over untouched if the particle never moved, evaluated once
         // otherwise (by every group, so that the shuffles stay converged)
@@ -242,8 +249,14 @@ __global__ void __launch_bounds__(kBlock, ASP_SWEEP_MIN_BLOCKS) pcn_sweep_kernel
             }
         }
     }
+    if (!per_move) {
+        n_acc = lane == 0 ? n_acc : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) n_acc += __shfl_xor_sync(0xffffffffu, n_acc, o);
+        if ((threadIdx.x & 31) == 0 && n_acc) atomicAdd(&s_acc[0], n_acc);
+    }
     __syncthreads();
-    for (int t = threadIdx.x; t < n_moves; t += blockDim.x)
+    for (int t = threadIdx.x; t < (per_move ? n_moves : 1); t += blockDim.x)
         if (s_acc[t]) atomicAdd(&A.accepts[t], (unsigned long long)s_acc[t]);
 }
 

@@ -16,8 +16,9 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
                                                uint32_t k1) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = __umulhi(kPhiloxM0, c0), lo0 = kPhiloxM0 * c0;
-        const uint32_t hi1 = __umulhi(kPhiloxM1, c2), lo1 = kPhiloxM1 * c2;
+        const uint64_t p0 = (uint64_t)kPhiloxM0 * c0, p1 = (uint64_t)kPhiloxM1 * c2;  // one IMAD.WIDE each
+        const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+        const uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
         const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
         c0 = n0;
         c1 = lo1;
@@ -49,8 +50,9 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
                                                const PhiloxKeys& K) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = __umulhi(kPhiloxM0, c0), lo0 = kPhiloxM0 * c0;
-        const uint32_t hi1 = __umulhi(kPhiloxM1, c2), lo1 = kPhiloxM1 * c2;
+        const uint64_t p0 = (uint64_t)kPhiloxM0 * c0, p1 = (uint64_t)kPhiloxM1 * c2;  // one IMAD.WIDE each
+        const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+        const uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
         const uint32_t n0 = hi1 ^ c1 ^ K.k0[r], n2 = hi0 ^ c3 ^ K.k1[r];
         c0 = n0;
         c1 = lo1;
@@ -59,6 +61,13 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
     }
     return make_uint4(c0, c1, c2, c3);
 }
+
+__device__ __forceinline__ float sfu_lg2(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float sfu_rsqrt(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float sfu_sin(float x) { float r; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float sfu_cos(float x) { float r; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+// natural log on the SFU (absolute error ~1e-7 for u in (0, 1])
+__device__ __forceinline__ float sfu_log(float x) { return 0.6931471805599453f * sfu_lg2(x); }
 
 // fp32 uniform in (0, 1]
 __device__ __forceinline__ float u01_f32(uint32_t r) { return fmaf(__uint2float_rn(r), 0x1p-32f, 0x1p-33f); }
@@ -70,11 +79,11 @@ __device__ __forceinline__ float u01_f32(uint32_t r) { return fmaf(__uint2float_
 __device__ __forceinline__ void box_muller_f32(uint32_t ra, uint32_t rb, float& z0, float& z1) {
     const float u = u01_f32(ra);
     const float t = fmaf(__uint2float_rn(rb), 0x1p-31f, -1.0f);
-    const float x = -1.3862943611198906f * __log2f(u);
-    const float s = x * rsqrtf(fmaxf(x, 1e-30f));
+    const float x = -1.3862943611198906f * sfu_lg2(u);
+    const float s = x * sfu_rsqrt(fmaxf(x, 1e-30f));
     const float th = 3.14159265358979f * t;
-    z0 = s * __cosf(th);
-    z1 = s * __sinf(th);
+    z0 = s * sfu_cos(th);
+    z1 = s * sfu_sin(th);
 }
 
 // four fp32 normals for (element index, stream, block)

@@ -203,7 +203,8 @@ class ShardedSMC:
         sigma = torch.clamp_min(sigma, 1e-150)
         mark("moments")
         prm = ops.make_pcn_params(beta, self.rho, mu, sigma, self.n_moves, seed=self.seed,
-                                  stream0=self.next_stream(self.n_moves) + 0x40000000, slot=slot)
+                                  stream0=self.next_stream(self.n_moves) + 0x40000000, slot=slot,
+                                  total_accepts_only=True)
         x, ll, lp, lq, accepts = ops.pcn_sweep(shard.x, shard.log_l, shard.log_p, shard.log_q, idx, self.like,
                                                self.prior, self.q, prm)
         mark("pcn_sweep")

@@ -309,7 +309,8 @@ def moments_to_mu_sigma(m: torch.Tensor, dims: int):
     return mu.contiguous(), torch.sqrt(torch.clamp_min(var, 0.0)).contiguous()
 
 
-def make_pcn_params(beta, rho, mu, sigma, n_moves, seed=0, stream0=0, index0=0, xi=None, log_u=None, slot=None):
+def make_pcn_params(beta, rho, mu, sigma, n_moves, seed=0, stream0=0, index0=0, xi=None, log_u=None, slot=None,
+                    total_accepts_only=False):
     mu, sigma = _f64(mu, "mu"), _f64(sigma, "sigma")
     prm = _lib.PcnParams()
     prm.beta, prm.rho = float(beta), float(rho)
@@ -319,6 +320,7 @@ def make_pcn_params(beta, rho, mu, sigma, n_moves, seed=0, stream0=0, index0=0, 
     prm.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
     prm.stream0 = int(stream0) & 0xFFFFFFFF
     prm.index0 = int(index0)
+    prm.reserved = 1 if total_accepts_only else 0
     prm.d_xi = None if xi is None else _f64(xi, "xi").data_ptr()
     prm.d_log_u = None if log_u is None else _f64(log_u, "log_u").data_ptr()
     prm.d_slot = None if slot is None else _i64(slot, "slot").data_ptr()
@@ -340,7 +342,7 @@ def pcn_sweep(x, log_l, log_p, log_q, idx, like, prior, q, prm, out=None):
                                     dims, C.byref(like.struct()), C.byref(prior.struct()), C.byref(q.struct()),
                                     C.byref(prm), out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
                                     out[3].data_ptr(), accepts.data_ptr(), _stream()), "asp_pcn_sweep")
-    return (*out, accepts[:prm.n_moves])
+    return (*out, accepts[:1] if prm.reserved else accepts[:prm.n_moves])
 
 
 def pcn_propose(x, prm, move: int) -> torch.Tensor:

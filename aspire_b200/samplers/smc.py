@@ -348,7 +348,8 @@ class SMCSampler(Sampler):
             prm = ops.make_pcn_params(beta, self.rho, mu, sigma, n_moves, xi=xi, log_u=log_u)
         else:
             prm = ops.make_pcn_params(beta, self.rho, mu, sigma, n_moves, seed=self.rng.seed,
-                                      stream0=self.rng.next_stream(n_moves), index0=getattr(self, "index0", 0))
+                                      stream0=self.rng.next_stream(n_moves), index0=getattr(self, "index0", 0),
+                                      total_accepts_only=True)
         if self.fused:
             x, ll, lp, lq, accepts = ops.pcn_sweep(particles.x, particles.log_likelihood, particles.log_prior,
                                                    particles.log_q, idx, self._log_likelihood, self._log_prior,

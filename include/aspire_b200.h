@@ -224,7 +224,7 @@ typedef struct asp_pcn_params {
     int32_t noise_mode;   /* 0: Philox in-kernel, 1: supplied d_xi / d_log_u    */
     uint64_t seed;        /* Philox key                                         */
     uint32_t stream0;     /* Philox stream of move 0 (move t uses stream0 + t)  */
-    uint32_t reserved;
+    uint32_t reserved;    /* 0: d_accepts[move] per move; 1: only the total, in d_accepts[0] */
     int64_t index0;       /* global index of local particle 0 (Philox counter)  */
     const double* d_xi;   /* [n_moves, n, dims] normals (noise_mode 1)          */
     const double* d_log_u;/* [n_moves, n] log-uniforms   (noise_mode 1)         */

@@ -115,13 +115,14 @@ def normals_f32(seed: int, stream: int, index, dims: int) -> np.ndarray:
 
 
 def accept_log_uniform(seed: int, stream0: int, move: int, index) -> np.ndarray:
-    """``log(u)`` for the accept/reject test of move ``move``: fp32 ``logf`` of word
+    """``log(u)`` for the accept/reject test of move ``move``: fp32 ``ln2 * log2`` (SFU) of word
     ``move & 3`` of block 0xFFFFFFFF of stream ``stream0 + (move & ~3)`` (one Philox
     call serves four moves), promoted to fp64."""
     c0, c1 = _split(index)
     k0, k1 = _key(seed)
     r = philox4x32(c0, c1, np.uint32((stream0 + (move & ~3)) & 0xFFFFFFFF), np.uint32(ACCEPT_BLOCK), k0, k1)
-    return np.log(_u01_f32(r[move & 3])).astype(np.float32).astype(np.float64)
+    lu = (np.float32(0.6931471805599453) * np.log2(_u01_f32(r[move & 3]))).astype(np.float32)
+    return lu.astype(np.float64)
 
 
 def normal_f64(seed: int, stream: int, index, dims: int) -> np.ndarray:

@@ -124,7 +124,8 @@ def moments_to_mu_sigma(m, dims):
     return mu.contiguous(), torch.sqrt(torch.clamp_min(var, 0.0)).contiguous()
 
 
-def make_pcn_params(beta, rho, mu, sigma, n_moves, seed=0, stream0=0, index0=0, xi=None, log_u=None, slot=None):
+def make_pcn_params(beta, rho, mu, sigma, n_moves, seed=0, stream0=0, index0=0, xi=None, log_u=None, slot=None,
+                    total_accepts_only=False):
     return types.SimpleNamespace(beta=beta, rho=rho, mu=_np(mu), sigma=_np(sigma), n_moves=n_moves, seed=seed,
                                  stream0=stream0, index0=index0, slot=None if slot is None else _np(slot))
 
