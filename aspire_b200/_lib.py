@@ -167,7 +167,7 @@ def last_error() -> str:
 # kernels launched per successful C call (for bench.py's gpu_launches)
 KERNELS_PER_CALL = {"asp_importance_weights": 3, "asp_cdf_exact": 6, "asp_cdf_tile_stats": 2,
                     "asp_cdf_set_tile_stats": 2, "asp_cdf_info": 0, "asp_device_check": 0,
-                    "asp_search_multinomial_guided": 2, "asp_select_uniforms": 3}
+                    "asp_search_multinomial_guided": 4, "asp_select_uniforms": 3}
 launch_count = 0
 
 

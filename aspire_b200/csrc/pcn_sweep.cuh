@@ -24,6 +24,10 @@ struct SweepArgs {
 };
 
 constexpr int kMaxMovesSmem = 1024;
+#ifndef ASP_SWEEP_UNROLL
+#define ASP_SWEEP_UNROLL 4
+#endif
+constexpr int kSweepUnroll = ASP_SWEEP_UNROLL;
 #ifndef ASP_SWEEP_MIN_BLOCKS
 #define ASP_SWEEP_MIN_BLOCKS 2
 #endif
@@ -189,6 +193,7 @@ __global__ void __launch_bounds__(kBlock, ASP_SWEEP_MIN_BLOCKS) pcn_sweep_kernel
         bool moved = false;
         const uint64_t pidx = (uint64_t)(A.prm.d_slot ? A.prm.d_slot[i] : A.prm.index0 + i);
         uint4 aw = make_uint4(0, 0, 0, 0);
+#pragma unroll kSweepUnroll
         for (int t = 0; t < n_moves; ++t) {
             double xi[kDPL], log_u;
             if (philox) {

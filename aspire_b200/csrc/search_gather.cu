@@ -59,6 +59,79 @@ __global__ void __launch_bounds__(kBlock) build_guide_kernel(const double* __res
         guide[b] = (GT)upper_bound(cdf, n, __ddiv_rn(__ll2double_rn(b), Bd));
 }
 
+// Streaming build: CDF entry k owns the buckets b with cdf[k-1] <= q_b < cdf[k] (their
+// guide value is k), so one coalesced pass over the CDF writes the whole table: O(n)
+// instead of a binary search per bucket.  Short ranges are written by their thread,
+// medium ones by the warp, ranges longer than 2^16 buckets (collapsed weights) are
+// deferred to a second, full-grid pass.
+constexpr int kLongRange = 1 << 16;
+struct GuideDeferred {
+    unsigned int count;
+    unsigned int pad;
+    long long entry[1][3];  // {b_lo, b_hi, k}; capacity = B / kLongRange + 2
+};
+
+__device__ __forceinline__ int64_t first_bucket_geq(double c, int64_t B, double Bd) {
+    // smallest b in [0, B + 1] with q_b = b / B >= c   (B + 1 if none)
+    if (!(c > 0.0)) return 0;
+    double e = ceil(c * Bd);
+    int64_t b = e > (double)(B + 1) ? B + 1 : (int64_t)e;
+    while (b > 0 && __ddiv_rn(__ll2double_rn(b - 1), Bd) >= c) --b;
+    while (b <= B && __ddiv_rn(__ll2double_rn(b), Bd) < c) ++b;
+    return b;
+}
+
+template <typename GT>
+__global__ void __launch_bounds__(kBlock) build_guide_stream_kernel(const double* __restrict__ cdf, int64_t n,
+                                                                    int64_t B, GT* __restrict__ guide,
+                                                                    GuideDeferred* __restrict__ deferred) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const double Bd = (double)B;
+    const int lane = threadIdx.x & 31;
+    // k = n is the virtual tail entry (cdf = +inf): buckets at or beyond cdf[n-1] count all n entries
+    const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t base = first - lane; base <= n; base += stride) {  // warp-uniform trip count
+        const int64_t k = base + lane;
+        int64_t b_lo = 0, b_hi = 0;
+        if (k <= n) {
+            b_lo = k > 0 ? first_bucket_geq(__ldg(cdf + k - 1), B, Bd) : 0;
+            b_hi = k < n ? first_bucket_geq(__ldg(cdf + k), B, Bd) : B + 1;
+        }
+        const int64_t len = b_hi - b_lo;
+        if (len > 0 && len <= 16) {
+            for (int64_t b = b_lo; b < b_hi; ++b) guide[b] = (GT)k;
+        } else if (len > kLongRange) {
+            const unsigned int slot = atomicAdd(&deferred->count, 1u);
+            deferred->entry[slot][0] = b_lo;
+            deferred->entry[slot][1] = b_hi;
+            deferred->entry[slot][2] = k;
+        }
+        unsigned int medium = __ballot_sync(0xffffffffu, len > 16 && len <= kLongRange);
+        while (medium) {
+            const int src = __ffs(medium) - 1;
+            medium &= medium - 1;
+            const int64_t lo = __shfl_sync(0xffffffffu, b_lo, src);
+            const int64_t hi = __shfl_sync(0xffffffffu, b_hi, src);
+            const int64_t kk = __shfl_sync(0xffffffffu, k, src);
+            for (int64_t b = lo + lane; b < hi; b += 32) guide[b] = (GT)kk;
+        }
+    }
+}
+
+template <typename GT>
+__global__ void __launch_bounds__(kBlock) build_guide_deferred_kernel(GT* __restrict__ guide,
+                                                                      GuideDeferred* __restrict__ deferred) {
+    const unsigned int count = deferred->count;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (unsigned int e = 0; e < count; ++e) {
+        const int64_t lo = deferred->entry[e][0], hi = deferred->entry[e][1];
+        const GT kk = (GT)deferred->entry[e][2];
+        for (int64_t b = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < hi; b += stride) guide[b] = kk;
+    }
+}
+
+__global__ void guide_reset_kernel(GuideDeferred* deferred) { deferred->count = 0; }
+
 template <typename GT>
 __global__ void __launch_bounds__(kBlock) search_guided_kernel(const double* __restrict__ cdf, int64_t n,
                                                                const GT* __restrict__ guide, int64_t B,
@@ -125,9 +198,12 @@ int asp_search_multinomial(const double* d_cdf, int64_t n_cdf, const double* d_u
     return check_launch("asp_search_multinomial");
 }
 
+static inline size_t guide_bytes(int64_t n_cdf) {
+    return (((size_t)(n_cdf + 1) * (n_cdf < 0xFFFFFFFFLL ? 4 : 8)) + 255) & ~(size_t)255;
+}
 size_t asp_search_workspace_bytes(int64_t n_cdf) {
     if (n_cdf < 1) n_cdf = 1;
-    return (size_t)(n_cdf + 1) * (n_cdf < 0xFFFFFFFFLL ? 4 : 8) + 256;
+    return guide_bytes(n_cdf) + 256 + sizeof(long long) * 3 * (size_t)(n_cdf / kLongRange + 4);
 }
 
 int asp_search_multinomial_guided(const double* d_cdf, int64_t n_cdf, const double* d_u, int64_t m, int64_t* d_idx,
@@ -137,12 +213,17 @@ int asp_search_multinomial_guided(const double* d_cdf, int64_t n_cdf, const doub
     ASP_REQUIRE(n_cdf > 0 && m > 0, "sizes must be positive");
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t B = n_cdf;
+    GuideDeferred* def = (GuideDeferred*)((char*)ws + guide_bytes(n_cdf));
+    const int gb = grid_for(n_cdf + 1, 1);
+    guide_reset_kernel<<<1, 1, 0, s>>>(def);
     if (n_cdf < 0xFFFFFFFFLL) {
-        build_guide_kernel<uint32_t><<<grid_for(B + 1, 1), kBlock, 0, s>>>(d_cdf, n_cdf, B, (uint32_t*)ws);
+        build_guide_stream_kernel<uint32_t><<<gb, kBlock, 0, s>>>(d_cdf, n_cdf, B, (uint32_t*)ws, def);
+        build_guide_deferred_kernel<uint32_t><<<kNumSMs * 4, kBlock, 0, s>>>((uint32_t*)ws, def);
         search_guided_kernel<uint32_t><<<grid_for(m, 1), kBlock, 0, s>>>(d_cdf, n_cdf, (const uint32_t*)ws, B, d_u, m,
                                                                          d_idx);
     } else {
-        build_guide_kernel<int64_t><<<grid_for(B + 1, 1), kBlock, 0, s>>>(d_cdf, n_cdf, B, (int64_t*)ws);
+        build_guide_stream_kernel<int64_t><<<gb, kBlock, 0, s>>>(d_cdf, n_cdf, B, (int64_t*)ws, def);
+        build_guide_deferred_kernel<int64_t><<<kNumSMs * 4, kBlock, 0, s>>>((int64_t*)ws, def);
         search_guided_kernel<int64_t><<<grid_for(m, 1), kBlock, 0, s>>>(d_cdf, n_cdf, (const int64_t*)ws, B, d_u, m,
                                                                         d_idx);
     }

@@ -102,7 +102,8 @@ class ShardedSMC:
     (the CPU tests inject an oracle-backed stand-in with the same functions)."""
 
     def __init__(self, comm: Comm, like, prior, q, backend=None, seed: int = 0, n_moves: int = 10, rho: float = 0.5,
-                 target_efficiency: float = 0.5, beta_tolerance: float = 1e-6, headroom: float = 1.05):
+                 target_efficiency: float = 0.5, beta_tolerance: float = 1e-6, headroom: float = 1.05,
+                 moment_particles: int = 1 << 22):
         if backend is None:
             from . import ops as backend
         self.ops = backend
@@ -112,6 +113,7 @@ class ShardedSMC:
         self.n_moves, self.rho = int(n_moves), float(rho)
         self.target_efficiency, self.beta_tolerance = float(target_efficiency), float(beta_tolerance)
         self.headroom = headroom
+        self.moment_particles = int(moment_particles)
         self._stream = 0
 
     def next_stream(self, count=1):
@@ -197,7 +199,14 @@ class ShardedSMC:
         n_out = slot.numel()
         mark("resample")
         dims = shard.x.shape[1]
-        mom = ops.weighted_moments(shard.x, idx=idx)
+        # reference measure: moments of the offspring in output slots < moment_particles (slots are
+        # sorted on every rank, so these are a prefix) - the same set whatever the sharding
+        m_use = int(torch.searchsorted(slot, torch.tensor([self.moment_particles], dtype=slot.dtype,
+                                                           device=slot.device))[0]) if n_out else 0
+        if m_use > 0:
+            mom = ops.weighted_moments(shard.x, idx=idx[:m_use])
+        else:
+            mom = torch.zeros(1 + 2 * dims, dtype=torch.float64, device=dev)
         comm.all_reduce_sum(mom)
         mu, sigma = ops.moments_to_mu_sigma(mom, dims)
         sigma = torch.clamp_min(sigma, 1e-150)

@@ -315,6 +315,7 @@ class SMCSampler(Sampler):
         kw.setdefault("verbose", False)
         kw.setdefault("rho", 0.5)
         kw.setdefault("adapt_rho", True)
+        kw.setdefault("moment_particles", 1 << 22)
         if kw["step_fn"] != "pcn":
             raise NotImplementedError(
                 f"step_fn={kw['step_fn']!r}: only the pCN step is built (tpCN is scope row 8f-2 of SURVEY.md)")
@@ -336,8 +337,13 @@ class SMCSampler(Sampler):
         n_moves = int(n_steps or self.sampler_kwargs["n_steps"])
         n = len(particles) if idx is None else idx.numel()
         dims = self.dims
-        # reference measure of the pCN proposal: moments of the (resampled) ensemble
-        mom = ops.weighted_moments(particles.x, idx=idx)
+        # reference measure of the pCN proposal: moments of the (resampled) ensemble; beyond
+        # `moment_particles` rows (default 2^22) the first rows - an iid sample of it - are used
+        m_use = min(n, int(self.sampler_kwargs.get("moment_particles", 1 << 22)))
+        if idx is not None:
+            mom = ops.weighted_moments(particles.x, idx=idx[:m_use])
+        else:
+            mom = ops.weighted_moments(particles.x[:m_use])
         mu, sigma = ops.moments_to_mu_sigma(mom, dims)
         sigma = torch.clamp_min(sigma, 1e-150)
         if mark:
