@@ -85,6 +85,22 @@ class PcnParams(C.Structure):
     ]
 
 
+class Flow(C.Structure):
+    _fields_ = [
+        ("dims", C.c_int32),
+        ("hidden", C.c_int32),
+        ("n_layers", C.c_int32),
+        ("reserved", C.c_int32),
+        ("d_weights", C.c_void_p),
+        ("d_bias", C.c_void_p),
+        ("d_mean", C.c_void_p),
+        ("d_inv_std", C.c_void_p),
+        ("d_std", C.c_void_p),
+        ("log_det0", C.c_double),
+        ("d_error", C.c_void_p),
+    ]
+
+
 _P = C.c_void_p
 _I64 = C.c_int64
 _I32 = C.c_int32
@@ -132,6 +148,9 @@ SIGNATURES = {
         C.c_int,
         [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, C.POINTER(PcnParams), _I32, _P, _P],
     ),
+    "asp_flow_weights_bytes": (C.c_size_t, [_I32, _I32]),
+    "asp_flow_logprob_bf16": (C.c_int, [C.POINTER(Flow), _P, _I64, _P, _P, _P]),
+    "asp_flow_sample_bf16": (C.c_int, [C.POINTER(Flow), _P, _I64, _P, _P, _P]),
     "asp_select_workspace_bytes": (C.c_size_t, []),
     "asp_select_uniforms": (C.c_int, [C.c_uint64, C.c_uint32, _P, _I64, _D, _D, _I64, _P, _P, _P, _P, _P]),
     "asp_philox_uniform": (C.c_int, [C.c_uint64, C.c_uint32, _I64, _I64, _P, _P]),

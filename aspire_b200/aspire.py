@@ -16,13 +16,14 @@ from typing import Any, Callable
 
 import torch
 
-from .flows import DiagGaussianFlow, Flow
+from .flows import CouplingFlow, DiagGaussianFlow, Flow
 from .samplers import ImportanceSampler, MiniPCNSMC
 from .samples import Samples
 
 logger = logging.getLogger(__name__)
 
-_FLOW_CLASSES = {"diag_gaussian": DiagGaussianFlow, "DiagGaussianFlow": DiagGaussianFlow}
+_FLOW_CLASSES = {"diag_gaussian": DiagGaussianFlow, "DiagGaussianFlow": DiagGaussianFlow,
+                 "coupling": CouplingFlow, "CouplingFlow": CouplingFlow}
 
 
 class Aspire:

@@ -1,0 +1,456 @@
+// K9/K10: affine-coupling flow log_prob / sample on the 5th-gen tensor cores.
+//
+// Replaces the dense contraction of ZukoFlow.log_prob / sample_and_log_prob
+// (/root/reference/src/aspire/flows/torch/flows.py:327-387; data transform
+// src/aspire/transforms.py:618-628).  Spec: oracle/flow.py.
+//
+// One CTA = 4 warps = one tile of 128 particles; thread i owns particle i: its state
+// z[D] lives in fp32 registers, its TMEM lane i receives the accumulators.  Per coupling
+// layer three GEMMs  [128 x K] . [K x N]  run as tcgen05.mma.kind::f16 (bf16 x bf16 ->
+// fp32 in TMEM), issued by one thread:
+//   A = activations, written by their owner threads as bf16 into shared memory in the
+//       no-swizzle K-major core-matrix layout (8 rows x 16 B per core matrix);
+//   B = the layer's weights, resident in shared memory for the whole kernel, brought in
+//       once by a TMA bulk copy (cp.async.bulk -> UBLKCP) of the host-packed blob;
+//   D = 64 (or D) fp32 TMEM columns, read back with tcgen05.ld.32x32b for the fp32
+//       epilogue (bias + ReLU + bf16 pack, or soft-clip / exp / affine update).
+// Two CTAs are resident per SM so that one CTA's epilogue overlaps the other's MMAs.
+#include <cuda_bf16.h>
+#include <math.h>
+
+#include "common.cuh"
+
+namespace asp {
+
+constexpr int kFlowH = 64;        // hidden width
+constexpr int kFlowM = 128;       // particles per tile (UMMA M)
+constexpr int kFlowThreads = 128;
+constexpr int kFlowMaxLayers = 8;
+constexpr float kFlowLimit = 6.907755278982137f;  // log(1e3): zuko's soft clip
+constexpr float kLog2Pi = 1.8378770664093453f;
+
+struct FlowArgs {
+    const double* x;        // log_prob: particles [n, D];  sample: base normals [n, D]
+    double* x_out;          // sample: particles [n, D]  (log_prob: optional z [n, D], may be null)
+    double* logq;           // [n]
+    int64_t n;
+    const uint16_t* weights;  // packed bf16 blob (all layers)
+    const float* bias;        // [L][3][64]  (b3 padded to 64)
+    const double* mean;       // [D]
+    const double* inv_std;    // [D]   (sample: std)
+    double log_det0;          // -sum log std
+    int n_layers;
+    unsigned int* error;
+};
+
+// ---- raw PTX wrappers -------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// bounded wait: returns false if the barrier never flipped (reported, never hangs)
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+#pragma unroll 1
+    for (int it = 0; it < (1 << 24); ++it) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (ok) return true;
+    }
+    return false;
+}
+__device__ __forceinline__ void tma_bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]   (one K = 16 step)
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// 32 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+        "[%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor: no swizzle, K-major; LBO = stride between core
+// matrices along K, SBO = stride between 8-row groups; version 1 (sm_100)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+// instruction descriptor: D = f32, A = B = bf16, both K-major, M = 128, N
+__host__ __device__ constexpr uint32_t umma_idesc(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kFlowM >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// write 8 consecutive K elements (one core-matrix row) of this thread's A-tile row
+__device__ __forceinline__ void a_tile_store8(unsigned char* a_tile, int row, int kchunk, const float* v) {
+    uint4 q = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    *reinterpret_cast<uint4*>(a_tile + kchunk * (kFlowM * 16) + (row >> 3) * 128 + (row & 7) * 16) = q;
+}
+
+template <int D>
+struct FlowSizes {
+    static constexpr int kHalf = D / 2;
+    static constexpr int kKA = kHalf < 16 ? 16 : kHalf;       // K of the first GEMM (padded to 16)
+    static constexpr int kW1 = kFlowH * kKA * 2;              // bytes
+    static constexpr int kW2 = kFlowH * kFlowH * 2;
+    static constexpr int kW3 = D * kFlowH * 2;
+    static constexpr int kLayer = kW1 + kW2 + kW3;
+    static constexpr int kTmemCols = 64;                      // >= max(64, D) accumulators, power of two
+};
+
+// issue one GEMM [128 x K] . [K x N] -> TMEM (thread 0 only), then commit to `bar`
+template <int K, int N>
+__device__ __forceinline__ void issue_gemm(uint32_t tmem, const unsigned char* a_tile, const unsigned char* w,
+                                           uint64_t* bar) {
+    const uint32_t a0 = smem_u32(a_tile), b0 = smem_u32(w);
+    constexpr uint32_t idesc = umma_idesc(N);
+#pragma unroll
+    for (int s = 0; s < K / 16; ++s) {
+        const uint64_t ad = umma_desc(a0 + s * 2 * (kFlowM * 16), kFlowM * 16, 128);
+        const uint64_t bd = umma_desc(b0 + s * 2 * (N * 16), N * 16, 128);
+        umma_f16(tmem, ad, bd, idesc, s > 0 ? 1u : 0u);
+    }
+    umma_commit(bar);
+}
+
+// One coupling layer for this thread's particle; ODD selects which half conditions which
+// (compile time, so z[] keeps static indices and stays in registers).
+template <int D, bool INVERSE, bool ODD>
+__device__ __forceinline__ bool coupling_layer(float (&z)[D], float& ladj, int layer, const unsigned char* s_w,
+                                               unsigned char* s_a, const float* s_bias, uint64_t* s_bar, uint32_t tmem,
+                                               uint32_t lane_taddr, uint32_t& phase, int tid) {
+    using S = FlowSizes<D>;
+    constexpr int HALF = S::kHalf;
+    constexpr bool odd = ODD;
+    bool ok = true;
+    const unsigned char* w1 = s_w + layer * S::kLayer;
+    const unsigned char* w2 = w1 + S::kW1;
+    const unsigned char* w3 = w2 + S::kW2;
+    const float* b1 = s_bias + layer * 192;
+    // ---- GEMM 1: A = bf16(z_a) ----
+#pragma unroll
+    for (int c = 0; c < S::kKA / 8; ++c) {
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            constexpr int last = HALF - 1;
+            const int j = c * 8 + k < HALF ? c * 8 + k : last;   // (K padding beyond HALF is zero)
+            v[k] = c * 8 + k < HALF ? (odd ? z[HALF + j] : z[j]) : 0.f;
+        }
+        a_tile_store8(s_a, tid, c, v);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+        tc_fence_after();
+        issue_gemm<S::kKA, kFlowH>(tmem, s_a, w1, &s_bar[1]);
+    }
+    ok &= mbar_wait(&s_bar[1], phase);
+    phase ^= 1;
+    tc_fence_after();
+    // ---- epilogue 1 -> A = bf16(relu(acc + b1)); GEMM 2 ----
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        float acc[32];
+        tmem_ld32(lane_taddr + half * 32, acc);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = fmaxf(acc[c * 8 + k] + b1[half * 32 + c * 8 + k], 0.f);
+            a_tile_store8(s_a, tid, half * 4 + c, v);
+        }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+        tc_fence_after();
+        issue_gemm<kFlowH, kFlowH>(tmem, s_a, w2, &s_bar[1]);
+    }
+    ok &= mbar_wait(&s_bar[1], phase);
+    phase ^= 1;
+    tc_fence_after();
+    // ---- epilogue 2 -> A = bf16(relu(acc + b2)); GEMM 3 (N = D) ----
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        float acc[32];
+        tmem_ld32(lane_taddr + half * 32, acc);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = fmaxf(acc[c * 8 + k] + b1[64 + half * 32 + c * 8 + k], 0.f);
+            a_tile_store8(s_a, tid, half * 4 + c, v);
+        }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+        tc_fence_after();
+        issue_gemm<kFlowH, D>(tmem, s_a, w3, &s_bar[1]);
+    }
+    ok &= mbar_wait(&s_bar[1], phase);
+    phase ^= 1;
+    tc_fence_after();
+    // ---- epilogue 3: columns [0, HALF) = shift, [HALF, D) = raw log-scale ----
+#pragma unroll
+    for (int c = 0; c < HALF / 16; ++c) {
+        float sh[16], raw[16];
+        tmem_ld16(lane_taddr + c * 16, sh);
+        tmem_ld16(lane_taddr + HALF + c * 16, raw);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int j = c * 16 + k;
+            const float shift = sh[k] + b1[128 + j];
+            const float r = raw[k] + b1[128 + HALF + j];
+            const float log_s = __fdividef(r, 1.0f + fabsf(r) * (1.0f / kFlowLimit));
+            ladj += log_s;
+            // z_b is the half NOT fed to the conditioner
+            float& zb = odd ? z[j] : z[HALF + j];
+            zb = INVERSE ? (zb - shift) * __expf(-log_s) : fmaf(zb, __expf(log_s), shift);
+        }
+    }
+    return ok;
+}
+
+template <int D, bool INVERSE>
+__global__ void __launch_bounds__(kFlowThreads, 2) flow_kernel(const FlowArgs A) {
+    using S = FlowSizes<D>;
+    constexpr int HALF = S::kHalf;
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* s_w = smem;                                             // weights blob
+    unsigned char* s_a = smem + kFlowMaxLayers * 0 + A.n_layers * S::kLayer;  // A tile (16 KB)
+    float* s_bias = reinterpret_cast<float*>(s_a + kFlowM * kFlowH * 2);
+    double* s_mean = reinterpret_cast<double*>(s_bias + A.n_layers * 3 * 64);
+    double* s_scale = s_mean + D;
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_scale + D);           // [0]: weights TMA, [1]: MMA
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int wbytes = A.n_layers * S::kLayer;
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) tmem_alloc(s_tmem, S::kTmemCols);
+    for (int i = tid; i < A.n_layers * 3 * 64; i += kFlowThreads) s_bias[i] = A.bias[i];
+    for (int i = tid; i < D; i += kFlowThreads) {
+        s_mean[i] = A.mean[i];
+        s_scale[i] = A.inv_std[i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *s_tmem;
+    if (tid == 0) {  // weights: one TMA bulk copy per layer blob, all on one mbarrier
+        mbar_expect_tx(&s_bar[0], (uint32_t)wbytes);
+        for (int l = 0; l < A.n_layers; ++l)
+            tma_bulk_load(s_w + l * S::kLayer, reinterpret_cast<const unsigned char*>(A.weights) + (size_t)l * S::kLayer,
+                          S::kLayer, &s_bar[0]);
+    }
+    bool ok = mbar_wait(&s_bar[0], 0);
+    uint32_t phase = 0;
+    const uint32_t lane_taddr = tmem + ((uint32_t)(warp * 32) << 16);
+
+    const int64_t n_tiles = (A.n + kFlowM - 1) / kFlowM;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t row = tile * kFlowM + tid;
+        const bool live = row < A.n;
+        float z[D];
+        {
+            const double* src = A.x + (live ? row : A.n - 1) * D;
+#pragma unroll
+            for (int j = 0; j < D; j += 2) {
+                const double2 v = *reinterpret_cast<const double2*>(src + j);
+                if (INVERSE) {
+                    z[j] = (float)v.x;
+                    z[j + 1] = (float)v.y;
+                } else {
+                    z[j] = (float)((v.x - s_mean[j]) * s_scale[j]);
+                    z[j + 1] = (float)((v.y - s_mean[j + 1]) * s_scale[j + 1]);
+                }
+            }
+        }
+        float base = 0.f;
+        if (INVERSE) {
+#pragma unroll
+            for (int j = 0; j < D; ++j) base = fmaf(z[j], z[j], base);
+        }
+        float ladj = 0.f;
+        for (int li = 0; li < A.n_layers; ++li) {
+            const int layer = INVERSE ? A.n_layers - 1 - li : li;
+            if (layer & 1)
+                ok &= coupling_layer<D, INVERSE, true>(z, ladj, layer, s_w, s_a, s_bias, s_bar, tmem, lane_taddr, phase, tid);
+            else
+                ok &= coupling_layer<D, INVERSE, false>(z, ladj, layer, s_w, s_a, s_bias, s_bar, tmem, lane_taddr, phase, tid);
+        }
+        // ---- outputs ----
+        if (live) {
+            if (INVERSE) {
+                double* dst = A.x_out + row * D;
+#pragma unroll
+                for (int j = 0; j < D; j += 2) {
+                    const double a = (double)z[j] * s_scale[j] + s_mean[j];
+                    const double b = (double)z[j + 1] * s_scale[j + 1] + s_mean[j + 1];
+                    *reinterpret_cast<double2*>(dst + j) = make_double2(a, b);
+                }
+                A.logq[row] = (double)(-0.5f * base - 0.5f * D * kLog2Pi + ladj) + A.log_det0;
+            } else {
+                float q = 0.f;
+#pragma unroll
+                for (int j = 0; j < D; ++j) q = fmaf(z[j], z[j], q);
+                A.logq[row] = (double)(-0.5f * q - 0.5f * D * kLog2Pi + ladj) + A.log_det0;
+                if (A.x_out) {
+                    double* dst = A.x_out + row * D;
+#pragma unroll
+                    for (int j = 0; j < D; j += 2) *reinterpret_cast<double2*>(dst + j) = make_double2(z[j], z[j + 1]);
+                }
+            }
+        }
+    }
+    if (!ok && tid == 0) atomicOr(A.error, 1u);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, S::kTmemCols);
+}
+
+template <int D>
+static size_t flow_smem_bytes(int n_layers) {
+    using S = FlowSizes<D>;
+    return (size_t)n_layers * S::kLayer + kFlowM * kFlowH * 2 + (size_t)n_layers * 3 * 64 * 4 + 2 * D * 8 + 2 * 8 + 16 + 128;
+}
+
+template <int D, bool INV>
+static int launch_flow(const FlowArgs& A, cudaStream_t s) {
+    const size_t smem = flow_smem_bytes<D>(A.n_layers);
+    cudaError_t e = cudaFuncSetAttribute(flow_kernel<D, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+        set_error("flow kernel: %s", cudaGetErrorString(e));
+        return ASP_ERR_CUDA;
+    }
+    const int64_t n_tiles = (A.n + kFlowM - 1) / kFlowM;
+    const int grid = (int)(n_tiles < 2 * kNumSMs ? n_tiles : 2 * kNumSMs);
+    flow_kernel<D, INV><<<grid, kFlowThreads, smem, s>>>(A);
+    return check_launch("asp_flow");
+}
+
+}  // namespace asp
+
+using namespace asp;
+
+extern "C" {
+
+size_t asp_flow_weights_bytes(int32_t dims, int32_t n_layers) {
+    switch (dims) {
+        case 32: return (size_t)n_layers * FlowSizes<32>::kLayer;
+        case 64: return (size_t)n_layers * FlowSizes<64>::kLayer;
+        default: return 0;
+    }
+}
+
+static int flow_dispatch(const asp_flow_t* f, const double* d_in, int64_t n, double* d_x_out, double* d_logq,
+                         bool inverse, void* stream) {
+    ASP_DEVICE_OR_RETURN();
+    ASP_REQUIRE(f && d_in && d_logq, "null pointer");
+    ASP_REQUIRE(f->d_weights && f->d_bias && f->d_mean && f->d_inv_std && f->d_std && f->d_error,
+                "flow descriptor incomplete");
+    ASP_REQUIRE(n > 0, "n must be positive");
+    ASP_REQUIRE(f->hidden == kFlowH, "hidden width must be 64");
+    ASP_REQUIRE(f->n_layers >= 1 && f->n_layers <= kFlowMaxLayers, "n_layers must be in [1, 8]");
+    ASP_REQUIRE(!inverse || d_x_out, "sample needs an output buffer");
+    FlowArgs A;
+    A.x = d_in; A.x_out = d_x_out; A.logq = d_logq; A.n = n;
+    A.weights = (const uint16_t*)f->d_weights; A.bias = f->d_bias; A.mean = f->d_mean; A.inv_std = inverse ? f->d_std : f->d_inv_std;
+    A.log_det0 = f->log_det0; A.n_layers = f->n_layers; A.error = f->d_error;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (f->dims) {
+        case 32: return inverse ? launch_flow<32, true>(A, s) : launch_flow<32, false>(A, s);
+        case 64: return inverse ? launch_flow<64, true>(A, s) : launch_flow<64, false>(A, s);
+        default: set_error("asp_flow: dims must be 32 or 64"); return ASP_ERR_ARG;
+    }
+}
+
+int asp_flow_logprob_bf16(const asp_flow_t* flow, const double* d_x, int64_t n, double* d_logq, double* d_z, void* stream) {
+    return flow_dispatch(flow, d_x, n, d_z, d_logq, false, stream);
+}
+
+int asp_flow_sample_bf16(const asp_flow_t* flow, const double* d_u, int64_t n, double* d_x, double* d_logq, void* stream) {
+    return flow_dispatch(flow, d_u, n, d_x, d_logq, true, stream);
+}
+
+}  // extern "C"

@@ -175,6 +175,10 @@ __global__ void __launch_bounds__(kBlock, ASP_SWEEP_MIN_BLOCKS) pcn_sweep_kernel
         const bool active = i_raw < A.n;
         const int64_t i = active ? i_raw : A.n - 1;
         const int64_t src = A.idx ? A.idx[i] : i;
+        // the next particle of this group: its ancestor index is loaded now, its row is
+        // prefetched during the moves (the gather is a dependent idx -> row load chain)
+        const int64_t i_next = i_raw + groups;
+        const int64_t src_next = i_next < A.n ? (A.idx ? A.idx[i_next] : i_next) : src;
         double y[kDPL];
         {
             double x[kDPL];
@@ -196,6 +200,7 @@ __global__ void __launch_bounds__(kBlock, ASP_SWEEP_MIN_BLOCKS) pcn_sweep_kernel
 #pragma unroll kSweepUnroll
         for (int t = 0; t < n_moves; ++t) {
             double xi[kDPL], log_u;
+            if (t == 1) asm volatile("prefetch.global.L1 [%0];" ::"l"(A.x + src_next * dims + lane * kDPL));
             if (philox) {
                 float z[4];
                 philox_normal4(A.keys, A.prm.stream0 + (uint32_t)t, pidx, (uint32_t)lane, z);

@@ -10,6 +10,8 @@ in-kernel.  Any other object with the same methods works through the unfused pat
 
 from __future__ import annotations
 
+import math
+
 import numpy as np
 import torch
 
@@ -78,3 +80,160 @@ class DiagGaussianFlow(Flow):
         self._require()
         x = self.rng.normal(n_samples, self.dims, self.device, mean=self.density.mean, sigma=self.density.sigma)
         return x, self.density.log_prob(x)
+
+
+# ---------------------------------------------------------------------------
+# Affine-coupling flow on the tensor cores (scope row a12 / config C4)
+# ---------------------------------------------------------------------------
+SOFT_CLIP_LIMIT = 6.907755278982137  # log(1e3), zuko's MonotonicAffineTransform clip
+
+
+def _bf16_bits(t: torch.Tensor) -> torch.Tensor:
+    """float tensor -> bf16 bit patterns (int16 view), round-to-nearest-even."""
+    return t.to(torch.float32).to(torch.bfloat16).view(torch.int16)
+
+
+def pack_umma_kmajor(w: torch.Tensor, k_pad: int | None = None) -> torch.Tensor:
+    """[N, K] weights -> bf16 bits in the tcgen05 no-swizzle K-major core-matrix layout:
+    element (n, k) at byte (k/8)*(N*16) + (n/8)*128 + (n%8)*16 + (k%8)*2  (see oracle/flow.py)."""
+    n, k = w.shape
+    k_pad = k if k_pad is None else k_pad
+    wp = torch.zeros(n, k_pad, dtype=torch.float32, device=w.device)
+    wp[:, :k] = w
+    bits = _bf16_bits(wp)
+    nn = torch.arange(n, device=w.device).view(-1, 1).expand(n, k_pad)
+    kk = torch.arange(k_pad, device=w.device).view(1, -1).expand(n, k_pad)
+    off = (kk // 8) * (n * 8) + (nn // 8) * 64 + (nn % 8) * 8 + (kk % 8)
+    out = torch.zeros(n * k_pad, dtype=torch.int16, device=w.device)
+    out[off.reshape(-1)] = bits.reshape(-1)
+    return out
+
+
+class CouplingFlow(Flow):
+    """T affine-coupling layers (alternating half masks), conditioner MLP(D/2 -> 64 -> 64 -> D)
+    with ReLU, soft-clipped log-scale, standard-normal base, input standardisation.
+
+    ``log_prob`` / ``sample_and_log_prob`` run on tcgen05 (``asp_flow_*_bf16``); ``fit`` trains the
+    same weight tensors with torch autograd (scaffolding - SURVEY 8f-1 - not part of the hot path).
+    """
+
+    hidden = 64
+
+    def __init__(self, dims: int, device=None, data_transform=None, dtype=None, n_layers: int = 3, rng=None,
+                 seed: int = 0):
+        super().__init__(dims, device, data_transform, dtype)
+        if dims not in (32, 64):
+            raise ValueError("CouplingFlow kernels are built for dims in {32, 64}")
+        self.n_layers = int(n_layers)
+        self.rng = as_uniform_source(rng)
+        g = torch.Generator().manual_seed(seed)
+        half, h = dims // 2, self.hidden
+        mk = lambda *shape, s: (torch.randn(*shape, generator=g) * s).to(self.device)  # noqa: E731
+        self.layers = [dict(W1=mk(h, half, s=1.0 / math.sqrt(half)), b1=torch.zeros(h, device=self.device),
+                            W2=mk(h, h, s=1.0 / math.sqrt(h)), b2=torch.zeros(h, device=self.device),
+                            W3=mk(dims, h, s=0.01), b3=torch.zeros(dims, device=self.device))
+                       for _ in range(self.n_layers)]
+        self.mean = torch.zeros(dims, dtype=torch.float64, device=self.device)
+        self.std = torch.ones(dims, dtype=torch.float64, device=self.device)
+        self._struct = None
+
+    # -- parameters ------------------------------------------------------------
+    def set_params(self, params: dict):
+        """Load parameters given as numpy arrays (keys as in ``oracle/flow.py``)."""
+        t32 = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float32).to(self.device)  # noqa: E731
+        self.layers = [{k: t32(v) for k, v in layer.items()} for layer in params["layers"]]
+        self.n_layers = len(self.layers)
+        self.mean = torch.as_tensor(np.asarray(params["mean"]), dtype=torch.float64).to(self.device)
+        self.std = torch.as_tensor(np.asarray(params["std"]), dtype=torch.float64).to(self.device)
+        self._struct = None
+
+    def struct(self):
+        if self._struct is None:
+            from . import _lib
+
+            half = self.dims // 2
+            ka = max(16, half)
+            blobs, bias = [], torch.zeros(self.n_layers, 3, 64, dtype=torch.float32, device=self.device)
+            for i, layer in enumerate(self.layers):
+                blobs += [pack_umma_kmajor(layer["W1"], ka), pack_umma_kmajor(layer["W2"]), pack_umma_kmajor(layer["W3"])]
+                bias[i, 0, :self.hidden] = layer["b1"]
+                bias[i, 1, :self.hidden] = layer["b2"]
+                bias[i, 2, :self.dims] = layer["b3"]
+            weights = torch.cat(blobs).contiguous()
+            assert weights.numel() * 2 == _lib.load().asp_flow_weights_bytes(self.dims, self.n_layers)
+            inv_std = (1.0 / self.std).contiguous()
+            err = torch.zeros(1, dtype=torch.int32, device=self.device)
+            s = _lib.Flow()
+            s.dims, s.hidden, s.n_layers = self.dims, self.hidden, self.n_layers
+            s.d_weights, s.d_bias = weights.data_ptr(), bias.data_ptr()
+            s.d_mean, s.d_inv_std, s.d_std = self.mean.data_ptr(), inv_std.data_ptr(), self.std.data_ptr()
+            s.log_det0 = -float(torch.log(self.std).sum())
+            s.d_error = err.data_ptr()
+            s._keep = (weights, bias, inv_std, err, self.mean, self.std)
+            self._struct = s
+        return self._struct
+
+    def _check_error(self):
+        if int(self._struct._keep[3].item()) != 0:
+            from ._lib import AspireB200Error
+
+            raise AspireB200Error("tcgen05 flow kernel: a tensor-core barrier timed out")
+
+    # -- hot path ----------------------------------------------------------------
+    def log_prob(self, x):
+        x = torch.as_tensor(x, dtype=torch.float64, device=self.device)
+        return ops.flow_logprob(self.struct(), x)
+
+    def forward(self, x):
+        x = torch.as_tensor(x, dtype=torch.float64, device=self.device)
+        logq, z = ops.flow_logprob(self.struct(), x, want_z=True)
+        return z, logq
+
+    def sample_and_log_prob(self, n_samples):
+        u = self.rng.normal(n_samples, self.dims, self.device)
+        return ops.flow_sample(self.struct(), u)
+
+    # -- training scaffolding (torch autograd over the same tensors) -------------------
+    def _torch_forward(self, x32, layers):
+        half = self.dims // 2
+        z = (x32 - self.mean.float()) / self.std.float()
+        ladj = -torch.log(self.std.float()).sum().expand(z.shape[0])
+        for t, layer in enumerate(layers):
+            a = slice(0, half) if t % 2 == 0 else slice(half, self.dims)
+            b = slice(half, self.dims) if t % 2 == 0 else slice(0, half)
+            hdn = torch.relu(z[:, a] @ layer["W1"].T + layer["b1"])
+            hdn = torch.relu(hdn @ layer["W2"].T + layer["b2"])
+            o = hdn @ layer["W3"].T + layer["b3"]
+            shift, raw = o[:, :half], o[:, half:]
+            log_s = raw / (1.0 + torch.abs(raw / SOFT_CLIP_LIMIT))
+            zb = z[:, b] * torch.exp(log_s) + shift
+            z = torch.cat([z[:, a], zb], dim=1) if t % 2 == 0 else torch.cat([zb, z[:, a]], dim=1)
+            ladj = ladj + log_s.sum(dim=1)
+        return -0.5 * (z * z).sum(dim=1) - 0.5 * self.dims * math.log(2 * math.pi) + ladj
+
+    def fit(self, samples, n_epochs: int = 50, lr: float = 1e-3, batch_size: int = 500, **kwargs) -> FlowHistory:
+        """Maximum-likelihood fit (Adam), mirroring ``ZukoFlow.fit`` (flows/torch/flows.py:170-325) in outline."""
+        x = samples.x if hasattr(samples, "x") else samples
+        x = torch.as_tensor(x, dtype=torch.float64, device=self.device)
+        self.mean = x.mean(dim=0)
+        self.std = x.std(dim=0, unbiased=False).clamp_min(1e-12)
+        params = [p.requires_grad_(True) for layer in self.layers for p in layer.values()]
+        opt = torch.optim.Adam(params, lr=lr)
+        hist = FlowHistory()
+        x32 = x.float()
+        for _ in range(n_epochs):
+            perm = torch.randperm(x32.shape[0], device=self.device)
+            tot = 0.0
+            for i in range(0, x32.shape[0], batch_size):
+                xb = x32[perm[i:i + batch_size]]
+                loss = -self._torch_forward(xb, self.layers).mean()
+                opt.zero_grad()
+                loss.backward()
+                opt.step()
+                tot += float(loss.detach()) * xb.shape[0]
+            hist.training_loss.append(tot / x32.shape[0])
+        for layer in self.layers:
+            for k in layer:
+                layer[k] = layer[k].detach()
+        self._struct = None
+        return hist

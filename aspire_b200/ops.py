@@ -363,6 +363,31 @@ def pcn_accept(x, log_l, log_p, log_q, x_prop, log_l_prop, log_p_prop, log_q_pro
                                      accepts.data_ptr(), _stream()), "asp_pcn_accept")
 
 
+# ---- K9 / K10 ---------------------------------------------------------------
+def flow_logprob(flow_struct, x, want_z: bool = False):
+    """Coupling-flow log_prob on tcgen05 (bf16 GEMMs, fp32 epilogue).  -> log_q [n] (, z [n, D])"""
+    x = _f64(x, "x")
+    n = x.shape[0]
+    logq = torch.empty(n, dtype=torch.float64, device=x.device)
+    z = torch.empty_like(x) if want_z else None
+    if n:
+        check(_lib.load().asp_flow_logprob_bf16(C.byref(flow_struct), x.data_ptr(), n, logq.data_ptr(), _ptr(z), _stream()),
+              "asp_flow_logprob_bf16")
+    return (logq, z) if want_z else logq
+
+
+def flow_sample(flow_struct, u):
+    """Base normals u [n, D] -> (x [n, D], log_q [n])."""
+    u = _f64(u, "u")
+    n = u.shape[0]
+    x = torch.empty_like(u)
+    logq = torch.empty(n, dtype=torch.float64, device=u.device)
+    if n:
+        check(_lib.load().asp_flow_sample_bf16(C.byref(flow_struct), u.data_ptr(), n, x.data_ptr(), logq.data_ptr(),
+                                               _stream()), "asp_flow_sample_bf16")
+    return x, logq
+
+
 # ---- K12 ------------------------------------------------------------------
 def select_uniforms(n_total: int, lo: float, hi: float, capacity: int, device, seed: int = 0, stream_id: int = 0,
                     u_all=None):

@@ -1,0 +1,111 @@
+#!/usr/bin/env python
+"""Micro-benchmarks of BASELINE.json configs[1], [3], [4] (bench.py carries the headline, configs[2]).
+
+    python benchmarks/micro.py flow        # C4: coupling-flow log_prob, N = 1e7, D = 64 (tcgen05)
+    python benchmarks/micro.py resample    # C5: exact CDF + ancestor search, N = 1e4 .. 1e9
+    python benchmarks/micro.py importance  # C2: importance reweighting, N = 1e6, D = 16
+
+Each prints JSON lines; times are CUDA events over `--iters` launches after 3 warm-ups, on inputs
+larger than L2 where the size allows (noted per line otherwise).
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from aspire_b200 import ops  # noqa: E402
+from aspire_b200 import targets as tg  # noqa: E402
+
+PEAKS = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json"))) if os.path.exists(
+    os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
+
+
+def timed(fn, iters):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def flow(args):
+    from aspire_b200.flows import CouplingFlow
+
+    dev = torch.device("cuda")
+    for dims in (64, 32):
+        n = args.n or 10_000_000
+        f = CouplingFlow(dims, device=dev, n_layers=3)
+        x = ops.philox_normal(1, 0, n, dims, dev)
+        ms = timed(lambda: ops.flow_logprob(f.struct(), x), args.iters)
+        f._check_error()
+        half, h = dims // 2, 64
+        flops = 3 * 2 * (half * h + h * h + h * dims) * n
+        bytes_ = n * (8 * dims + 8)
+        print(json.dumps({"bench": "flow_logprob_bf16", "config": "C4" if dims == 64 else "C4 (D=32)", "particles": n,
+                          "dims": dims, "ms": ms, "particles_per_s": n / ms * 1e3, "tflops": flops / ms / 1e9,
+                          "tensor_frac_of_measured_bf16": flops / ms / 1e9 / PEAKS["bf16_tflops"],
+                          "hbm_gbs": bytes_ / ms / 1e6, "hbm_frac": bytes_ / ms / 1e6 / PEAKS["hbm_gbs"]}))
+        u = ops.philox_normal(2, 0, n, dims, dev)
+        ms = timed(lambda: ops.flow_sample(f.struct(), u), args.iters)
+        print(json.dumps({"bench": "flow_sample_bf16", "particles": n, "dims": dims, "ms": ms,
+                          "particles_per_s": n / ms * 1e3, "tflops": flops / ms / 1e9}))
+
+
+def resample(args):
+    dev = torch.device("cuda")
+    sizes = [args.n] if args.n else [10**4, 10**5, 10**6, 10**7, 10**8, 10**9]
+    for n in sizes:
+        g = torch.Generator(device=dev).manual_seed(7)
+        lw = torch.randn(n, dtype=torch.float64, device=dev, generator=g) * 2.0
+        p = torch.exp(lw - lw.max())
+        p /= p.sum()
+        del lw
+        u = ops.philox_uniform(7, 0, n, dev)
+        iters = args.iters if n <= 10**8 else 3
+        t_cdf = timed(lambda: ops.cdf_exact(p), iters)
+        cdf = ops.cdf_exact(p)
+        t_mult = timed(lambda: ops.search_multinomial(cdf, u), iters)
+        t_sys = timed(lambda: ops.search_systematic(cdf, 0.37, n), iters)
+        for name, t in (("multinomial", t_cdf + t_mult), ("systematic", t_cdf + t_sys)):
+            print(json.dumps({"bench": f"resample_{name}", "config": "C5", "particles": n, "ms_cdf": t_cdf,
+                              "ms_total": t, "indices_per_s": n / t * 1e3, "algorithmic_gbs": 32 * n / t / 1e6,
+                              "hbm_frac": 32 * n / t / 1e6 / PEAKS["hbm_gbs"],
+                              "note": "inputs L2-resident" if 24 * n < 126e6 else "inputs exceed L2"}))
+        del p, u, cdf
+
+
+def importance(args):
+    dev = torch.device("cuda")
+    n, dims = args.n or 1_000_000, 16
+    prob = tg.gaussian_problem(dims, device=dev)
+    x = ops.philox_normal(3, 0, n, dims, dev, mean=prob["q"].mean, sigma=prob["q"].sigma)
+
+    def step():
+        lq = prob["q"].log_prob(x)
+        lp = prob["prior"].log_prob(x)
+        ll = prob["like"].log_prob(x)
+        return ops.importance_weights(ll, lp, lq)
+
+    ms = timed(step, args.iters)
+    print(json.dumps({"bench": "importance_reweight", "config": "C2", "particles": n, "dims": dims, "ms": ms,
+                      "particles_per_s": n / ms * 1e3, "algorithmic_gbs": (16 * dims + 64) * n / ms / 1e6,
+                      "note": "launch-latency dominated at this size (6 kernels, 0.3 GB)"}))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("what", choices=["flow", "resample", "importance"])
+    ap.add_argument("--n", type=int, default=0)
+    ap.add_argument("--iters", type=int, default=10)
+    a = ap.parse_args()
+    ops.device_check()
+    {"flow": flow, "resample": resample, "importance": importance}[a.what](a)

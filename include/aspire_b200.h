@@ -252,6 +252,34 @@ int asp_pcn_accept(double* d_x, double* d_log_l, double* d_log_p, double* d_log_
                    int32_t dims, const asp_pcn_params_t* params, int32_t move, unsigned long long* d_accepts,
                    void* stream);
 
+/* ---- coupling-flow log_prob / sample on tcgen05 (K9/K10) ---------------------
+ * ZukoFlow.log_prob / sample_and_log_prob, src/aspire/flows/torch/flows.py:327-387, with
+ * the affine data transform of src/aspire/transforms.py:618-628 folded in.  Spec and
+ * weight layout: oracle/flow.py (T coupling layers, conditioner MLP(D/2 -> 64 -> 64 -> D),
+ * bf16 x bf16 -> fp32 tensor-core GEMMs, fp32 epilogue; stated tolerance in the tests).
+ *   d_weights  bf16 blob, per layer W1[64, max(16, D/2)] | W2[64, 64] | W3[D, 64], each in the
+ *              tcgen05 no-swizzle K-major core-matrix layout (asp_flow_weights_bytes)
+ *   d_bias     fp32 [n_layers][3][64]   (b1 | b2 | b3 padded to 64)
+ *   d_mean / d_inv_std / d_std  fp64 [dims];  log_det0 = -sum log std
+ *   d_error    device uint32, bit 0 set if a tensor-core barrier timed out
+ * dims in {32, 64}, hidden = 64, n_layers <= 8. */
+typedef struct asp_flow {
+    int32_t dims, hidden, n_layers, reserved;
+    const void* d_weights;
+    const float* d_bias;
+    const double* d_mean;
+    const double* d_inv_std;
+    const double* d_std;
+    double log_det0;
+    unsigned int* d_error;
+} asp_flow_t;
+
+size_t asp_flow_weights_bytes(int32_t dims, int32_t n_layers);
+/* d_logq[i] = log q(x_i); d_z (optional) receives the base-space point. */
+int asp_flow_logprob_bf16(const asp_flow_t* flow, const double* d_x, int64_t n, double* d_logq, double* d_z, void* stream);
+/* d_u: base normals [n, dims] -> d_x [n, dims], d_logq[i] = log q(x_i). */
+int asp_flow_sample_bf16(const asp_flow_t* flow, const double* d_u, int64_t n, double* d_x, double* d_logq, void* stream);
+
 /* ---- owner-computes multinomial resampling across GPUs (K12) ---------------
  * (no reference site: the reference is single-process.)  Every rank walks the same
  * global stream of n_total uniforms - Philox (seed, stream_id), identical to
