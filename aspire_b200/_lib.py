@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libaspire_b200.so")
+# ASPIRE_B200_LIB selects another build of the same library (kernel A/B experiments)
+LIB_PATH = os.environ.get("ASPIRE_B200_LIB") or os.path.join(_HERE, "lib", "libaspire_b200.so")
 
 ASP_OK = 0
 ASP_ERR_ARG = -1

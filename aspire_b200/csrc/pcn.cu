@@ -13,7 +13,10 @@
 #include "common.cuh"
 #include "density.cuh"
 #include "pcn_sweep.cuh"
+#include "pcn_sweep_tpp.cuh"
 #include "philox.cuh"
+
+#include <stdlib.h>
 
 namespace asp {
 
@@ -309,9 +312,25 @@ int asp_pcn_sweep(const double* d_x, const double* d_log_l, const double* d_log_
     ASP_REQUIRE(q->kind == ASP_DENSITY_GAUSSIAN, "the fused sweep needs a diagonal-Gaussian proposal density");
     ASP_REQUIRE(prior->kind == ASP_DENSITY_GAUSSIAN || prior->kind == ASP_DENSITY_UNIFORM,
                 "the fused sweep needs a Gaussian or uniform prior");
+    cudaStream_t s = (cudaStream_t)stream;
+    // fast path: particle-per-thread kernel (pcn_sweep_tpp.cuh) for the dims it is built for;
+    // ASP_SWEEP_LEGACY=1 forces the general lanes-per-particle kernel (A/B checks)
+    int dl = 0, gt = 0;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(d_x) | reinterpret_cast<uintptr_t>(d_x_out) |
+                           reinterpret_cast<uintptr_t>(params->d_xi)) & 15) == 0;
+    static const bool legacy = [] { const char* e = getenv("ASP_SWEEP_LEGACY"); return e && e[0] == '1'; }();
+    if (!legacy && aligned && tpp_shape(dims, like->kind, dl, gt)) {
+        switch (like->kind) {
+            case ASP_DENSITY_GAUSSIAN: rc = launch_tpp_gaussian(A, s); break;
+            case ASP_DENSITY_ROSENBROCK: rc = launch_tpp_rosenbrock(A, s); break;
+            case ASP_DENSITY_GMM: rc = launch_tpp_gmm(A, s); break;
+            default: rc = launch_tpp_uniform(A, s); break;
+        }
+        if (rc) { set_error("asp_pcn_sweep: unsupported density combination"); return rc; }
+        return check_launch("asp_pcn_sweep");
+    }
     const int g = group_size_for(dims);
     const int grid = grid_for(n * g, 1);
-    cudaStream_t s = (cudaStream_t)stream;
     switch (like->kind) {
         case ASP_DENSITY_GAUSSIAN: rc = launch_sweep_gaussian(A, g, grid, s); break;
         case ASP_DENSITY_ROSENBROCK: rc = launch_sweep_rosenbrock(A, g, grid, s); break;

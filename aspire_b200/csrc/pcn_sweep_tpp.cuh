@@ -1,0 +1,455 @@
+// K8, particle-per-thread form of the fused pCN sweep (the fast path of
+// asp_pcn_sweep; pcn_sweep.cuh keeps the general lanes-per-particle kernel).
+//
+// One thread (G = 1) or G adjacent lanes own a particle; each lane keeps DL
+// dimensions of the centred state y = x - mu and of the proposal in registers
+// for the whole sweep.  Compared with the 4-dims-per-lane kernel nothing is
+// replicated across lanes (accept test, log u, reductions are per thread), so
+// the instruction count per particle-move halves; the price is that the
+// per-dimension constants no longer fit in registers and are read from shared
+// memory as warp-uniform (broadcast) 128-bit loads.
+//
+// Step spec: oracle/pcn.py.  Noise layout: dimension j of particle slot p in
+// move t is word j % 4 of Philox block j / 4, stream stream0 + t, counter p -
+// the same stream as the general kernel, so both produce the same trajectory.
+#pragma once
+#include "pcn_sweep.cuh"
+
+namespace asp {
+
+constexpr int kTppBlock = 128;
+constexpr int kTppChunk = 4;         // mixture components evaluated together
+constexpr int kTppRegConstDims = 8;  // lanes with at most this many dims keep their constants in registers
+constexpr int kTppMaxDims = 64;
+
+// 32 dims per lane: 2 blocks/SM (255 registers, no spills) measured faster than 3 blocks (168, spills)
+template <int DL>
+constexpr int tpp_min_blocks() { return DL >= 32 ? 2 : (DL == 8 ? 3 : 4); }
+
+__device__ __forceinline__ double2 ldg2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
+// Shared-memory constant read that stays where it is written: a plain load is loop-invariant, so the
+// compiler hoists all 4 * DL constants out of the move loop into registers and spills the state.
+__device__ __forceinline__ double2 lds2(const double2* p) {
+    double2 r;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+    return r;
+}
+
+// branch-free streaming log-sum-exp update with one exp:  (m, acc) <- (m, acc) (+) t
+__device__ __forceinline__ void lse_push(double& m, double& acc, double t) {
+    const double ninf = identity(OP_MAX);
+    const double d = t - m;  // +inf on the first finite term
+    const double e = exp(-fabs(d));
+    const double up = fma(acc, e, 1.0), keep = acc + e;
+    if (t > ninf) {
+        acc = d > 0.0 ? up : keep;
+        m = fmax(m, t);
+    }
+}
+
+// log of the isotropic mixture at x = mu + v (descriptor staged in shared memory):
+//   s_gm [G*DL][ncp] component means, dimension-major;  s_gw [ncp] = {1/2 inv_sigma^2, logc}
+template <int DL, int G, class MuOf>
+__device__ __forceinline__ double tpp_gmm(const double (&v)[DL], MuOf mu_of, int lane,
+                                          const double* __restrict__ s_gm, const double2* __restrict__ s_gw, int n_comp,
+                                          int ncp) {
+    double m = identity(OP_MAX), acc = 0.0;
+    for (int c0 = 0; c0 < n_comp; c0 += kTppChunk) {
+        double d2[kTppChunk];
+#pragma unroll
+        for (int j = 0; j < kTppChunk; ++j) d2[j] = 0.0;
+#pragma unroll
+        for (int k = 0; k < DL; ++k) {
+            const double xk = mu_of(k) + v[k];
+            const double* mrow = s_gm + (size_t)(lane * DL + k) * ncp + c0;
+            const double2 m01 = lds2(reinterpret_cast<const double2*>(mrow));
+            const double2 m23 = lds2(reinterpret_cast<const double2*>(mrow + 2));
+            const double e0 = xk - m01.x, e1 = xk - m01.y, e2 = xk - m23.x, e3 = xk - m23.y;
+            d2[0] = fma(e0, e0, d2[0]);
+            d2[1] = fma(e1, e1, d2[1]);
+            d2[2] = fma(e2, e2, d2[2]);
+            d2[3] = fma(e3, e3, d2[3]);
+        }
+#pragma unroll
+        for (int j = 0; j < kTppChunk; ++j) {
+            const double dd = group_sum<G>(d2[j]);
+            if (c0 + j < n_comp) {  // warp-uniform
+                const double2 w = lds2(&s_gw[c0 + j]);
+                lse_push(m, acc, fma(-w.x, dd, w.y));
+            }
+        }
+    }
+    return m + log(acc);
+}
+
+template <int DL, int G, int LIKE, int PRIOR, bool PHILOX>
+__global__ void __launch_bounds__(kTppBlock, tpp_min_blocks<DL>()) pcn_sweep_tpp_kernel(const SweepArgs A) {
+    constexpr int DT = DL * G;  // == dims
+    constexpr int NQ = DL / 4;
+    constexpr bool kLikeQuad = LIKE == ASP_DENSITY_GAUSSIAN;
+    constexpr bool kPriorQuad = PRIOR == ASP_DENSITY_GAUSSIAN;
+    constexpr bool kRosen = LIKE == ASP_DENSITY_ROSENBROCK;
+    constexpr bool kGmm = LIKE == ASP_DENSITY_GMM;
+    constexpr bool kPBox = PRIOR == ASP_DENSITY_UNIFORM, kLBox = LIKE == ASP_DENSITY_UNIFORM;
+    constexpr bool kNeedX = kRosen || kPBox || kLBox;
+
+    constexpr bool kRC = DL <= kTppRegConstDims;  // constants in registers (4 DL doubles per lane), else shared memory
+    __shared__ double2 s_c01[DT];  // {rho sigma_k, mu_k}
+    __shared__ double2 s_c23[DT];  // {a2_k, a1_k}: folded quadratic of the accept test
+    __shared__ double2 s_pbox[kPBox ? DT : 1], s_lbox[kLBox ? DT : 1];
+    __shared__ unsigned int s_acc[kMaxMovesSmem];
+    extern __shared__ double s_dyn[];  // mixture: means [DT][ncp], then {1/2 is^2, logc}[ncp]
+
+    const int n_moves = A.prm.n_moves;
+    const bool per_move = A.prm.reserved == 0;
+    const double ninf = identity(OP_MAX);
+    const double rho = A.prm.rho, beta = A.prm.beta;
+    const double ca = sqrt(1.0 - rho * rho);
+    const double ros_w = kRosen ? -beta / A.like.s2 : 0.0;  // beta and the scale folded
+    const double ros_wa = ros_w * A.like.s0;
+    const int n_comp = kGmm ? A.like.n_comp : 0;
+    const int ncp = (n_comp + kTppChunk - 1) / kTppChunk * kTppChunk;
+    double* s_gm = s_dyn;
+    double2* s_gw = reinterpret_cast<double2*>(s_dyn + (size_t)DT * ncp);
+
+    for (int t = threadIdx.x; t < max(n_moves, 1); t += blockDim.x) s_acc[t] = 0;
+    for (int j = threadIdx.x; j < DT; j += blockDim.x) {
+        // T(x) = (1-beta) log_q + beta (logL + logP) + r,  r = 1/2 |(x - mu)/sigma|^2: every Gaussian term and
+        // Rosenbrock's (b - x_j)^2 are per-dimension quadratics in y = x - mu and fold into a2 y^2 + a1 y
+        const double sg = __ldg(A.prm.d_sigma + j), mu = __ldg(A.prm.d_mu + j);
+        const double isr = 1.0 / sg;
+        double c2 = 0.5 * isr * isr, c1 = 0.0;
+        const double isq = __ldg(A.q.p1 + j), wq = -0.5 * (1.0 - beta) * isq * isq;
+        c2 += wq;
+        c1 += 2.0 * wq * (mu - __ldg(A.q.p0 + j));
+        if constexpr (kPriorQuad) {
+            const double is = __ldg(A.prior.p1 + j), w = -0.5 * beta * is * is;
+            c2 += w;
+            c1 += 2.0 * w * (mu - __ldg(A.prior.p0 + j));
+        }
+        if constexpr (kLikeQuad) {
+            const double is = __ldg(A.like.p1 + j), w = -0.5 * beta * is * is;
+            c2 += w;
+            c1 += 2.0 * w * (mu - __ldg(A.like.p0 + j));
+        }
+        if constexpr (kRosen) {
+            if (j < DT - 1) {  // ros_w (b - mu - y)^2
+                c2 += ros_w;
+                c1 += 2.0 * ros_w * (mu - A.like.s1);
+            }
+        }
+        s_c01[j] = make_double2(rho * sg, mu);
+        s_c23[j] = make_double2(c2, c1);
+        if constexpr (kPBox) s_pbox[j] = make_double2(__ldg(A.prior.p0 + j), __ldg(A.prior.p1 + j));
+        if constexpr (kLBox) s_lbox[j] = make_double2(__ldg(A.like.p0 + j), __ldg(A.like.p1 + j));
+    }
+    if constexpr (kGmm) {
+        for (int e = threadIdx.x; e < DT * ncp; e += blockDim.x) {
+            const int k = e / ncp, c = e % ncp;
+            s_gm[e] = c < n_comp ? __ldg(A.like.p0 + (size_t)c * DT + k) : 0.0;
+        }
+        for (int c = threadIdx.x; c < ncp; c += blockDim.x) {
+            const double is = c < n_comp ? __ldg(A.like.p1 + c) : 0.0;
+            s_gw[c] = make_double2(0.5 * is * is, c < n_comp ? __ldg(A.like.p2 + c) : ninf);
+        }
+    }
+    __syncthreads();
+
+    const int lane = (G == 1) ? 0 : (int)(threadIdx.x % G);
+    // A plain shared-memory read of a constant is loop-invariant: the compiler hoists all 4 DL of them out of
+    // the move loop into registers and spills the state.  lds2 (volatile) keeps each read next to its use.
+    double2 rc01[kRC ? DL : 1] = {}, rc23[kRC ? DL : 1] = {}, rpb[kRC && kPBox ? DL : 1] = {}, rlb[kRC && kLBox ? DL : 1] = {};
+    if constexpr (kRC) {
+#pragma unroll
+        for (int k = 0; k < DL; ++k) {
+            rc01[k] = s_c01[lane * DL + k];
+            rc23[k] = s_c23[lane * DL + k];
+            if constexpr (kPBox) rpb[k] = s_pbox[lane * DL + k];
+            if constexpr (kLBox) rlb[k] = s_lbox[lane * DL + k];
+        }
+    }
+    auto C01 = [&](int k) -> double2 { if constexpr (kRC) return rc01[k]; else return lds2(&s_c01[lane * DL + k]); };
+    auto C23 = [&](int k) -> double2 { if constexpr (kRC) return rc23[k]; else return lds2(&s_c23[lane * DL + k]); };
+    auto PBOX = [&](int k) -> double2 { if constexpr (kRC) return rpb[kPBox ? k : 0]; else return lds2(&s_pbox[kPBox ? lane * DL + k : 0]); };
+    auto LBOX = [&](int k) -> double2 { if constexpr (kRC) return rlb[kLBox ? k : 0]; else return lds2(&s_lbox[kLBox ? lane * DL + k : 0]); };
+    auto MU = [&](int k) -> double { return C01(k).y; };
+    constexpr int kPerWarp = 32 / G;
+    const int sub = (threadIdx.x & 31) / G;
+    const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t stride = (((int64_t)gridDim.x * blockDim.x) >> 5) * kPerWarp;
+    const uint32_t stream0 = A.prm.stream0;
+    unsigned int n_acc = 0;
+
+    // separable part of T at centred state v (+ Rosenbrock's coupling term), group-reduced
+    auto target = [&](const double(&v)[DL]) -> double {
+        double sq[4] = {0.0, 0.0, 0.0, 0.0}, rr[4] = {0.0, 0.0, 0.0, 0.0};
+        double xprev = 0.0, xfirst = 0.0;
+        bool bad = false;
+#pragma unroll
+        for (int k = 0; k < DL; ++k) {
+            const double2 e = C23(k);
+            sq[k & 3] = fma(v[k], fma(e.x, v[k], e.y), sq[k & 3]);
+            if constexpr (kNeedX) {
+                const double xk = C01(k).y + v[k];
+                if constexpr (kRosen) {
+                    if (k > 0) {
+                        const double tt = fma(-xprev, xprev, xk);
+                        rr[k & 3] = fma(tt, tt, rr[k & 3]);
+                    } else {
+                        xfirst = xk;
+                    }
+                    xprev = xk;
+                }
+                if constexpr (kPBox) { const double2 b = PBOX(k); bad |= !(xk > b.x && xk < b.y); }
+                if constexpr (kLBox) { const double2 b = LBOX(k); bad |= !(xk > b.x && xk < b.y); }
+            }
+        }
+        double s = (sq[0] + sq[1]) + (sq[2] + sq[3]);
+        if constexpr (kRosen) {
+            if constexpr (G > 1) {
+                const double xn = __shfl_down_sync(0xffffffffu, xfirst, 1, G);
+                const double tt = fma(-xprev, xprev, xn);
+                if (lane < G - 1) rr[0] = fma(tt, tt, rr[0]);
+            }
+            s = fma(ros_wa, (rr[0] + rr[1]) + (rr[2] + rr[3]), s);
+        }
+        if constexpr (kPBox || kLBox) {
+            if (bad) s = ninf;  // -inf target: the move is rejected
+        }
+        double T = group_sum<G>(s);
+        if constexpr (kGmm) T = fma(beta, tpp_gmm<DL, G>(v, MU, lane, s_gm, s_gw, n_comp, ncp), T);
+        return T;
+    };
+
+    for (int64_t base = warp_id * kPerWarp; base < A.n; base += stride) {
+        const int64_t i_raw = base + sub;
+        const bool active = i_raw < A.n;
+        const int64_t i = active ? i_raw : A.n - 1;
+        const int64_t src = A.idx ? A.idx[i] : i;
+        const int64_t i_next = i_raw + stride;
+        const int64_t src_next = i_next < A.n ? (A.idx ? A.idx[i_next] : i_next) : src;
+        const double* row = A.x + src * DT + lane * DL;
+        double y[DL], yp[DL];
+#pragma unroll
+        for (int k = 0; k < DL; k += 2) {
+            const double2 v = ldg2(row + k);
+            y[k] = v.x - C01(k).y;
+            y[k + 1] = v.y - C01(k + 1).y;
+        }
+        double cur = target(y);
+        if (!active) cur = identity(OP_MIN);  // +inf: a padding particle never accepts
+        bool moved = false;
+        const uint64_t pidx = (uint64_t)(A.prm.d_slot ? A.prm.d_slot[i] : A.prm.index0 + i);
+        uint4 aw = make_uint4(0, 0, 0, 0);
+        for (int t = 0; t < n_moves; ++t) {
+            double log_u;
+            if constexpr (PHILOX) {
+                if ((t & 3) == 0) aw = accept_words(A.keys, stream0, t, pidx);
+                log_u = accept_log_u(aw, t);
+            } else {
+                log_u = A.prm.d_log_u[(size_t)t * A.n + i];
+            }
+            if (t == 1) {  // the next particle's row, fetched towards L2 while this one moves
+                const double* nx = A.x + src_next * DT + lane * DL;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+                if constexpr (DL * 8 > 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 16));
+            }
+            double stot = 0.0, rtot = 0.0;
+            double xprev = 0.0, xfirst = 0.0;
+            bool bad = false;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                double xi[4];
+                if constexpr (PHILOX) {
+                    float z[4];
+                    philox_normal4(A.keys, stream0 + (uint32_t)t, pidx, (uint32_t)(lane * NQ + q), z);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) xi[j] = (double)z[j];
+                } else {
+                    const double* p = A.prm.d_xi + ((size_t)t * A.n + i) * DT + lane * DL + q * 4;
+                    const double2 a = ldg2(p), b = ldg2(p + 2);
+                    xi[0] = a.x; xi[1] = a.y; xi[2] = b.x; xi[3] = b.y;
+                }
+                double sq = 0.0, rr = 0.0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int k = q * 4 + j;
+                    const double2 c = C01(k);
+                    const double v = fma(c.x, xi[j], ca * y[k]);
+                    yp[k] = v;
+                    const double2 e = C23(k);
+                    sq = fma(v, fma(e.x, v, e.y), sq);
+                    if constexpr (kNeedX) {
+                        const double xk = c.y + v;
+                        if constexpr (kRosen) {
+                            if (k > 0) {
+                                const double tt = fma(-xprev, xprev, xk);
+                                rr = fma(tt, tt, rr);
+                            } else {
+                                xfirst = xk;
+                            }
+                            xprev = xk;
+                        }
+                        if constexpr (kPBox) { const double2 b = PBOX(k); bad |= !(xk > b.x && xk < b.y); }
+                        if constexpr (kLBox) { const double2 b = LBOX(k); bad |= !(xk > b.x && xk < b.y); }
+                    }
+                }
+                stot += sq;
+                if constexpr (kRosen) rtot += rr;
+            }
+            double s = stot;
+            if constexpr (kRosen) {
+                if constexpr (G > 1) {
+                    const double xn = __shfl_down_sync(0xffffffffu, xfirst, 1, G);
+                    const double tt = fma(-xprev, xprev, xn);
+                    if (lane < G - 1) rtot = fma(tt, tt, rtot);
+                }
+                s = fma(ros_wa, rtot, s);
+            }
+            if constexpr (kPBox || kLBox) {
+                if (bad) s = ninf;
+            }
+            double nw = group_sum<G>(s);
+            if constexpr (kGmm) nw = fma(beta, tpp_gmm<DL, G>(yp, MU, lane, s_gm, s_gw, n_comp, ncp), nw);
+            const bool acc = log_u < nw - cur;  // NaN -> reject, like the reference's NaN -> -inf
+            if (acc) {
+#pragma unroll
+                for (int k = 0; k < DL; ++k) y[k] = yp[k];
+                cur = nw;
+                moved = true;
+            }
+            if (per_move) {
+                const unsigned int votes = __ballot_sync(0xffffffffu, acc && lane == 0);
+                if ((threadIdx.x & 31) == 0 && votes) atomicAdd(&s_acc[t], __popc(votes));
+            } else {
+                n_acc += (acc && lane == 0) ? 1u : 0u;
+            }
+        }
+        // final state and its logs: evaluated once (by every lane: the group shuffles stay converged);
+        // a particle that never moved keeps its input row and logs bit for bit
+        double x[DL];
+#pragma unroll
+        for (int k = 0; k < DL; ++k) x[k] = C01(k).y + y[k];
+        double sq_ = 0.0, sp_ = 0.0, sl_ = 0.0, r_ = 0.0;
+        bool pbad = false, lbad = false;
+#pragma unroll
+        for (int k = 0; k < DL; ++k) {
+            const int j = lane * DL + k;
+            const double zq = (x[k] - __ldg(A.q.p0 + j)) * __ldg(A.q.p1 + j);
+            sq_ = fma(zq, zq, sq_);
+            if constexpr (kPriorQuad) {
+                const double z = (x[k] - __ldg(A.prior.p0 + j)) * __ldg(A.prior.p1 + j);
+                sp_ = fma(z, z, sp_);
+            } else {
+                const double2 b = PBOX(k);
+                pbad |= !(x[k] > b.x && x[k] < b.y);
+            }
+            if constexpr (kLikeQuad) {
+                const double z = (x[k] - __ldg(A.like.p0 + j)) * __ldg(A.like.p1 + j);
+                sl_ = fma(z, z, sl_);
+            } else if constexpr (kLBox) {
+                const double2 b = LBOX(k);
+                lbad |= !(x[k] > b.x && x[k] < b.y);
+            } else if constexpr (kRosen) {
+                double x1;
+                if (k + 1 < DL) x1 = x[(k + 1) % DL];
+                else x1 = (G > 1) ? __shfl_down_sync(0xffffffffu, x[0], 1, G) : 0.0;
+                const double tt = x1 - x[k] * x[k];
+                const double u = A.like.s1 - x[k];
+                if (k + 1 < DL || lane < G - 1) r_ += A.like.s0 * tt * tt + u * u;
+            }
+        }
+        double lq = A.q.s0 - 0.5 * group_sum<G>(sq_);
+        double lp, ll;
+        if constexpr (kPriorQuad) lp = A.prior.s0 - 0.5 * group_sum<G>(sp_);
+        else lp = group_sum<G>(pbad ? 1.0 : 0.0) > 0.0 ? ninf : A.prior.s0;
+        if constexpr (kLikeQuad) ll = A.like.s0 - 0.5 * group_sum<G>(sl_);
+        else if constexpr (kLBox) ll = group_sum<G>(lbad ? 1.0 : 0.0) > 0.0 ? ninf : A.like.s0;
+        else if constexpr (kRosen) ll = -group_sum<G>(r_) / A.like.s2;
+        else ll = tpp_gmm<DL, G>(y, MU, lane, s_gm, s_gw, n_comp, ncp);
+        if (!moved) {
+#pragma unroll
+            for (int k = 0; k < DL; k += 2) {
+                const double2 v = ldg2(row + k);
+                x[k] = v.x;
+                x[k + 1] = v.y;
+            }
+            ll = A.ll[src];
+            lp = A.lp[src];
+            lq = A.lq[src];
+        }
+        if (active) {
+            double* dst = A.xo + i * DT + lane * DL;
+#pragma unroll
+            for (int k = 0; k < DL; k += 2) st_stream2(dst + k, x[k], x[k + 1]);
+            if (lane == 0) {
+                A.llo[i] = ll;
+                A.lpo[i] = lp;
+                A.lqo[i] = lq;
+            }
+        }
+    }
+    if (!per_move) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) n_acc += __shfl_xor_sync(0xffffffffu, n_acc, o);
+        if ((threadIdx.x & 31) == 0 && n_acc) atomicAdd(&s_acc[0], n_acc);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < (per_move ? n_moves : 1); t += blockDim.x)
+        if (s_acc[t]) atomicAdd(&A.accepts[t], (unsigned long long)s_acc[t]);
+}
+
+// dims the kernel is built for -> (dims per lane DL, lanes per particle G).  Measured on B200 (N = 2e7,
+// 10 moves, profiles/r1_sweep_variants.md): one thread per particle up to 32 dims beats the split
+// layouts - (32,1) 10.8 ms vs (8,4) 12.9 ms vs (16,2) 12.6 ms at D = 32; (16,1) 4.8 ms vs (8,2) 5.5 ms at D = 16.
+inline bool tpp_shape(int dims, int like_kind, int& dl, int& g) {
+    (void)like_kind;
+    switch (dims) {
+        case 4: case 8: case 16: case 32: dl = dims; g = 1; return true;
+        case 64: dl = 32; g = 2; return true;
+        default: return false;
+    }
+}
+
+inline size_t tpp_dyn_smem(const SweepArgs& A) {
+    if (A.like.kind != ASP_DENSITY_GMM) return 0;
+    const int ncp = (A.like.n_comp + kTppChunk - 1) / kTppChunk * kTppChunk;
+    return sizeof(double) * ((size_t)A.dims * ncp + 2 * (size_t)ncp);
+}
+
+template <int DL, int G, int LIKE, int PRIOR>
+inline int launch_tpp_n(const SweepArgs& A, cudaStream_t s) {
+    const int64_t per_block = (int64_t)kTppBlock / G;
+    const int64_t need = (A.n + per_block - 1) / per_block;
+    const int64_t cap = (int64_t)kNumSMs * tpp_min_blocks<DL>();
+    const int grid = (int)(need < cap ? need : cap);
+    const size_t smem = tpp_dyn_smem(A);
+    if (A.prm.noise_mode == 0) pcn_sweep_tpp_kernel<DL, G, LIKE, PRIOR, true><<<grid, kTppBlock, smem, s>>>(A);
+    else pcn_sweep_tpp_kernel<DL, G, LIKE, PRIOR, false><<<grid, kTppBlock, smem, s>>>(A);
+    return ASP_OK;
+}
+
+template <int LIKE, int PRIOR>
+inline int launch_tpp_shape(const SweepArgs& A, cudaStream_t s) {
+    int dl = 0, g = 0;
+    if (!tpp_shape(A.dims, LIKE, dl, g)) return ASP_ERR_ARG;
+    if (g == 2) return launch_tpp_n<32, 2, LIKE, PRIOR>(A, s);
+    if (dl == 32) return launch_tpp_n<32, 1, LIKE, PRIOR>(A, s);
+    if (dl == 16) return launch_tpp_n<16, 1, LIKE, PRIOR>(A, s);
+    if (dl == 8) return launch_tpp_n<8, 1, LIKE, PRIOR>(A, s);
+    return launch_tpp_n<4, 1, LIKE, PRIOR>(A, s);
+}
+
+template <int LIKE>
+inline int launch_tpp_like(const SweepArgs& A, cudaStream_t s) {
+    if (A.prior.kind == ASP_DENSITY_GAUSSIAN) return launch_tpp_shape<LIKE, ASP_DENSITY_GAUSSIAN>(A, s);
+    if (A.prior.kind == ASP_DENSITY_UNIFORM) return launch_tpp_shape<LIKE, ASP_DENSITY_UNIFORM>(A, s);
+    return ASP_ERR_ARG;
+}
+
+int launch_tpp_gaussian(const SweepArgs& A, cudaStream_t s);
+int launch_tpp_rosenbrock(const SweepArgs& A, cudaStream_t s);
+int launch_tpp_gmm(const SweepArgs& A, cudaStream_t s);
+int launch_tpp_uniform(const SweepArgs& A, cudaStream_t s);
+
+}  // namespace asp

@@ -72,16 +72,15 @@ __device__ __forceinline__ float sfu_log(float x) { return 0.6931471805599453f *
 // fp32 uniform in (0, 1]
 __device__ __forceinline__ float u01_f32(uint32_t r) { return fmaf(__uint2float_rn(r), 0x1p-32f, 0x1p-33f); }
 
-// two fp32 normals from two words: Box-Muller on the SFU (MUFU.LG2 / RSQ / SIN / COS).
-//   u = fma(ra, 2^-32, 2^-33) in (0, 1],  s = sqrt(-2 ln u) = sqrt(-2 ln2 * log2 u)
-//   theta = pi * t,  t = fma(rb, 2^-31, -1) in [-1, 1]   (the SFU's accurate range)
+// two fp32 normals from two words: Box-Muller on the SFU (MUFU.LG2 / SQRT / SIN / COS).
+//   u = fma(ra, 2^-32, 2^-33) in (0, 1],  s = sqrt(-2 ln2 * log2 u)
+//   theta = fma(rb, pi 2^-31, -pi) in [-pi, pi]   (the SFU's accurate range)
 // Absolute error of a normal ~1e-6 (spec: oracle/philox.py::box_muller_f32).
+__device__ __forceinline__ float sfu_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ void box_muller_f32(uint32_t ra, uint32_t rb, float& z0, float& z1) {
     const float u = u01_f32(ra);
-    const float t = fmaf(__uint2float_rn(rb), 0x1p-31f, -1.0f);
-    const float x = -1.3862943611198906f * sfu_lg2(u);
-    const float s = x * sfu_rsqrt(fmaxf(x, 1e-30f));
-    const float th = 3.14159265358979f * t;
+    const float th = fmaf(__uint2float_rn(rb), 1.4629180792671596e-09f, -3.14159265358979f);
+    const float s = sfu_sqrt(-1.3862943611198906f * sfu_lg2(u));
     z0 = s * sfu_cos(th);
     z1 = s * sfu_sin(th);
 }

@@ -4,6 +4,7 @@
     python benchmarks/micro.py flow        # C4: coupling-flow log_prob, N = 1e7, D = 64 (tcgen05)
     python benchmarks/micro.py resample    # C5: exact CDF + ancestor search, N = 1e4 .. 1e9
     python benchmarks/micro.py importance  # C2: importance reweighting, N = 1e6, D = 16
+    python benchmarks/micro.py sweep       # K8: fused gather + 10 pCN moves per benchmark problem
 
 Each prints JSON lines; times are CUDA events over `--iters` launches after 3 warm-ups, on inputs
 larger than L2 where the size allows (noted per line otherwise).
@@ -101,11 +102,58 @@ def importance(args):
                       "note": "launch-latency dominated at this size (6 kernels, 0.3 GB)"}))
 
 
+def sweep(args):
+    """K8 alone: fused resampling gather + 10 pCN moves (Philox noise), per benchmark problem.
+    --dump PATH also saves the result of a small run (A/B checks between kernel variants)."""
+    import numpy as np
+
+    dev = torch.device("cuda")
+    cases = [("rosenbrock", 32, 20_000_000), ("gmm", 64, 4_000_000), ("gauss", 16, 20_000_000)]
+    mk = dict(rosenbrock=tg.rosenbrock_problem, gmm=tg.gmm_problem, gauss=tg.gaussian_problem)
+    dump = {}
+    for name, dims, n in cases:
+        if args.only and args.only != name:
+            continue
+        n = args.n or n
+        pg = mk[name](dims, device=dev)
+        x = ops.philox_normal(5, 0, n, dims, dev, mean=pg["q"].mean, sigma=pg["q"].sigma)
+        lq, lp, ll = pg["q"].log_prob(x), pg["prior"].log_prob(x), pg["like"].log_prob(x)
+        idx = (ops.philox_uniform(6, 0, n, dev) * n).to(torch.int64).clamp_(0, n - 1)
+        mom = ops.weighted_moments(x[: 1 << 20])
+        mu, sigma = ops.moments_to_mu_sigma(mom, dims)
+        prm = ops.make_pcn_params(0.1, 0.3, mu, sigma, args.moves, seed=99, stream0=3, total_accepts_only=True)
+        out = tuple(torch.empty_like(t) for t in (x, ll, lp, lq))
+        res = {}
+
+        def run():
+            res["o"] = ops.pcn_sweep(x, ll, lp, lq, idx, pg["like"], pg["prior"], pg["q"], prm, out=out)
+
+        ms = timed(run, args.iters)
+        acc = float(res["o"][4].sum()) / (n * args.moves)
+        w = (16 * dims + 48) * n
+        print(json.dumps({"bench": "pcn_sweep", "problem": name, "particles": n, "dims": dims, "moves": args.moves,
+                          "ms": ms, "particle_moves_per_s": n * args.moves / ms * 1e3, "normals_per_s":
+                          n * args.moves * dims / ms * 1e3, "algorithmic_gbs": w / ms / 1e6,
+                          "hbm_frac": w / ms / 1e6 / PEAKS["hbm_gbs"], "acceptance": acc,
+                          "legacy": os.environ.get("ASP_SWEEP_LEGACY", "0"), "lib": os.environ.get("ASPIRE_B200_LIB", "")}))
+        if args.dump:
+            m = min(n, 20_000)
+            dump[name + "_x"] = res["o"][0][:m].cpu().numpy()
+            dump[name + "_ll"] = res["o"][1][:m].cpu().numpy()
+            dump[name + "_acc"] = res["o"][4].cpu().numpy()
+        del x, lq, lp, ll, idx, out, res
+    if args.dump:
+        np.savez(args.dump, **dump)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["flow", "resample", "importance"])
+    ap.add_argument("what", choices=["flow", "resample", "importance", "sweep"])
     ap.add_argument("--n", type=int, default=0)
     ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--moves", type=int, default=10)
+    ap.add_argument("--only", default="")
+    ap.add_argument("--dump", default="")
     a = ap.parse_args()
     ops.device_check()
-    {"flow": flow, "resample": resample, "importance": importance}[a.what](a)
+    {"flow": flow, "resample": resample, "importance": importance, "sweep": sweep}[a.what](a)
