@@ -253,19 +253,26 @@ def run_gpu(args):
     sweep_ms = phase_ms["pcn_sweep"]
     achieved = sweep_bytes / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else 0.0
     roofline = {
-        "kernel": "pcn_sweep_kernel (fused resampling gather + 10 pCN moves)", "bound": "hbm",
-        "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-        "traffic": None, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
+        "kernel": "pcn_sweep_tpp_kernel<32,1,rosenbrock,gaussian> (fused resampling gather + 10 pCN moves)",
+        "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+        "frac": achieved / peaks["hbm_gbs"],
+        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, ncu --set full at 5e7 particles
+        # (profiles/r1_ncu_v6.md: 13.11 + 13.95 GB), scaled per particle to this launch
+        "traffic": (13.112859e9 + 13.954770e9) / 5e7 * n if dims == 32 else None,
+        "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
         "algorithmic_bytes_per_launch": sweep_bytes, "ms_per_launch": sweep_ms,
-        "note": "the sweep is bound by fp64 density arithmetic and Philox/Box-Muller issue, not by HBM "
-                "(SURVEY hard part 3); the HBM fraction is reported as the contract asks",
+        "note": "the sweep is bound by instruction issue (Philox 32 %, Box-Muller 19 %, fp64 25 % of 1,058 "
+                "warp-instructions per 32 particle-moves), not by HBM: DRAM traffic equals the algorithmic bytes; "
+                "the HBM fraction is reported as the contract asks (profiles/r1_sweep_variants.md)",
     }
     step_bytes = n * algorithmic_bytes_per_particle(dims)
     step_roofline = {"achieved": step_bytes / (ms_per_step * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "algorithmic_bytes_per_step": step_bytes}
     step_roofline["frac"] = step_roofline["achieved"] / peaks["hbm_gbs"]
 
-    e2e = run_e2e(args, sampler, prob, flow, dev, out) if not args.no_e2e else None
+    del p0, out, new  # the end-to-end leg brings its own buffers
+    torch.cuda.empty_cache()
+    e2e = run_e2e(args, sampler, prob, flow, dev) if not args.no_e2e else None
     cpu = cpu_baseline(args.cpu_particles, dims, moves) if not args.no_cpu else None
 
     line = {
@@ -280,9 +287,12 @@ def run_gpu(args):
     print(json.dumps(line))
 
 
-def run_e2e(args, sampler, prob, flow, dev, out):
+def run_e2e(args, sampler, prob, flow, dev):
     """Same step through the public sampler API with HOST buffers: pinned host particles -> device,
-    ``tempering_step``, results -> pinned host, all inside the timed region."""
+    ``tempering_step``, results -> pinned host, all inside the timed region.  Consecutive steps are
+    software-pipelined over three streams with two device buffer sets: while step k computes, the inputs
+    of step k+1 are uploading and the results of step k-1 are downloading (PCIe is full duplex), so the
+    steady-state cost of a step is max(H2D, D2H) instead of H2D + step + D2H."""
     import psutil
     import torch
 
@@ -291,7 +301,8 @@ def run_e2e(args, sampler, prob, flow, dev, out):
     dims = args.dims
     row_bytes = 8 * (dims + 3)
     avail = psutil.virtual_memory().available
-    n = min(args.particles, int(0.2 * avail / (2 * row_bytes)))
+    free_dev, _ = torch.cuda.mem_get_info(dev)
+    n = min(args.particles, int(0.2 * avail / (2 * row_bytes)), int(0.8 * free_dev / (4.6 * row_bytes)))
     n = max(n, 1)
     host_in = [torch.empty(n, dims, dtype=torch.float64).pin_memory()] + [
         torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(3)]
@@ -302,31 +313,59 @@ def run_e2e(args, sampler, prob, flow, dev, out):
     for h, d in zip(host_in, (x0, prob["like"].log_prob(x0), prob["prior"].log_prob(x0), lq0)):
         h.copy_(d)
     del x0, lq0
-    dev_in = [torch.empty_like(h, device=dev) for h in host_in]
-    out_n = tuple(o[:n] for o in out)
-    stream = torch.cuda.current_stream()
+    dev_in = [[torch.empty_like(h, device=dev) for h in host_in] for _ in range(2)]
+    dev_out = [tuple(torch.empty_like(h, device=dev) for h in host_in) for _ in range(2)]
+    s_comp = torch.cuda.current_stream()
+    s_h2d, s_d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    comp_done, d2h_done = [None, None], [None, None]
 
-    def step():
-        for d, h in zip(dev_in, host_in):
-            d.copy_(h, non_blocking=True)
-        p = SMCSamples(dev_in[0], log_likelihood=dev_in[1], log_prior=dev_in[2], log_q=dev_in[3], beta=0.0, device=dev)
-        new, _, _ = sampler.tempering_step(p, 0.0, float("nan"), 0.0, 1e-6, out=out_n)
-        for h, d in zip(host_out, (new.x, new.log_likelihood, new.log_prior, new.log_q)):
-            h.copy_(d, non_blocking=True)
+    def upload(k):
+        b = k % 2
+        with torch.cuda.stream(s_h2d):
+            if comp_done[b] is not None:
+                s_h2d.wait_event(comp_done[b])  # step k-2 has finished reading this input set
+            for d, h in zip(dev_in[b], host_in):
+                d.copy_(h, non_blocking=True)
+            e = torch.cuda.Event()
+            e.record(s_h2d)
+        return e
 
-    steps = max(1, min(args.steps, 3))
-    step()
+    def run(steps):
+        up = upload(0)
+        for k in range(steps):
+            b = k % 2
+            nxt = upload(k + 1) if k + 1 < steps else None
+            s_comp.wait_event(up)
+            if d2h_done[b] is not None:
+                s_comp.wait_event(d2h_done[b])  # the results of step k-2 have left this output set
+            di = dev_in[b]
+            p = SMCSamples(di[0], log_likelihood=di[1], log_prior=di[2], log_q=di[3], beta=0.0, device=dev)
+            new, _, _ = sampler.tempering_step(p, 0.0, float("nan"), 0.0, 1e-6, out=dev_out[b])
+            comp_done[b] = torch.cuda.Event()
+            comp_done[b].record(s_comp)
+            with torch.cuda.stream(s_d2h):
+                s_d2h.wait_event(comp_done[b])
+                for h, d in zip(host_out, (new.x, new.log_likelihood, new.log_prior, new.log_q)):
+                    h.copy_(d, non_blocking=True)
+                d2h_done[b] = torch.cuda.Event()
+                d2h_done[b].record(s_d2h)
+            up = nxt
+        s_comp.wait_stream(s_d2h)
+
+    steps = max(2, min(args.steps, 5))
+    run(1)
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record(stream)
-    for _ in range(steps):
-        step()
-    b.record(stream)
+    a.record(s_comp)
+    s_h2d.wait_event(a)
+    run(steps)
+    b.record(s_comp)
     torch.cuda.synchronize()
     ms = a.elapsed_time(b) / steps
     return {"value": n / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n * row_bytes,
             "d2h_bytes_per_step": n * row_bytes, "particles": n, "ms_per_step": ms, "steps": steps,
-            "api": "SMCSampler.tempering_step on pinned host buffers (H2D + step + D2H timed)"}
+            "api": "SMCSampler.tempering_step on pinned host buffers; H2D of step k+1 and D2H of step k-1 overlap "
+                   "step k (three streams, two device buffer sets); timed from the first upload to the last download"}
 
 
 def main():

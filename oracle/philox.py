@@ -83,15 +83,14 @@ def _u01_f32(r):
 def box_muller_f32(ra, rb):
     """Two fp32 normals from two uint32 words:
     ``u = fma(ra, 2^-32, 2^-33)``, ``s = sqrt(-2 ln2 * log2(u))``,
-    ``theta = pi * t`` with ``t = fma(rb, 2^-31, -1)`` in [-1, 1],
-    ``(s cos(theta), s sin(theta))``.  The kernel evaluates log2 / rsqrt / sin /
-    cos on the SFU (absolute error ~1e-6 per normal); numpy float32 here - they
-    agree to ~1e-6, not bit for bit."""
+    ``theta = fma(rb, pi 2^-31, -pi)`` in [-pi, pi], ``(s cos(theta), s sin(theta))``.
+    The kernel evaluates log2 / sqrt / sin / cos on the SFU (absolute error ~1e-6
+    per normal); numpy float32 here - they agree to ~1e-6, not bit for bit."""
     u = _u01_f32(ra)
-    t = (rb.astype(np.float32) * np.float32(2.0**-31) + np.float32(-1.0)).astype(np.float32)
+    th = (rb.astype(np.float32) * np.float32(1.4629180792671596e-09) + np.float32(-3.14159265358979)).astype(np.float32)
     x = (np.float32(-1.3862943611198906) * np.log2(u)).astype(np.float32)
     s = np.sqrt(x).astype(np.float32)
-    th = (np.float32(3.14159265358979) * t).astype(np.float64)
+    th = th.astype(np.float64)
     return (s * np.cos(th).astype(np.float32)).astype(np.float32), (s * np.sin(th).astype(np.float32)).astype(np.float32)
 
 
