@@ -316,10 +316,10 @@ def run_bench(args, rank, world, dev, metric, unit, workload_config, bytes_per_p
                        "resampling, scalar NCCL collectives only"},
             "clocks": clock_info, "gpu_launches": launches,
             "e2e": None,
-            "roofline": {"kernel": "pcn_sweep_kernel (per GPU)", "bound": "hbm", "achieved": ach,
+            "roofline": {"kernel": "pcn_sweep_tpp_kernel<32,1,rosenbrock,gaussian> (per GPU)", "bound": "hbm", "achieved": ach,
                          "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,
                          "peak_source": f"MEASURED_PEAKS.json ({kind})",
-                         "note": "issue-bound kernel (fp64 + Philox); HBM fraction reported as the contract asks"},
+                         "note": "issue-bound kernel (Philox, Box-Muller, fp64); HBM fraction reported as the contract asks"},
             "step_roofline": {"achieved": step_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s per GPU",
                               "frac": step_ach / peaks["hbm_gbs"]},
             "cpu_baseline": None, "phase_ms": phase_ms, "beta_after_step": rec.beta, "acceptance": rec.acceptance,
