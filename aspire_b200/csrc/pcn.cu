@@ -319,7 +319,7 @@ int asp_pcn_sweep(const double* d_x, const double* d_log_l, const double* d_log_
     const bool aligned = ((reinterpret_cast<uintptr_t>(d_x) | reinterpret_cast<uintptr_t>(d_x_out) |
                            reinterpret_cast<uintptr_t>(params->d_xi)) & 15) == 0;
     static const bool legacy = [] { const char* e = getenv("ASP_SWEEP_LEGACY"); return e && e[0] == '1'; }();
-    if (!legacy && aligned && tpp_shape(dims, like->kind, dl, gt)) {
+    if (!legacy && aligned && params->rho < 1.0 && tpp_shape(dims, like->kind, dl, gt)) {
         switch (like->kind) {
             case ASP_DENSITY_GAUSSIAN: rc = launch_tpp_gaussian(A, s); break;
             case ASP_DENSITY_ROSENBROCK: rc = launch_tpp_rosenbrock(A, s); break;

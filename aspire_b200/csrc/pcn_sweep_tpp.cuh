@@ -21,10 +21,13 @@ constexpr int kTppBlock = 128;
 constexpr int kTppChunk = 4;         // mixture components evaluated together
 constexpr int kTppRegConstDims = 8;  // lanes with at most this many dims keep their constants in registers
 constexpr int kTppMaxDims = 64;
+#ifndef ASP_TPP_MINB32
+#define ASP_TPP_MINB32 2
+#endif
 
 // 32 dims per lane: 2 blocks/SM (255 registers, no spills) measured faster than 3 blocks (168, spills)
 template <int DL>
-constexpr int tpp_min_blocks() { return DL >= 32 ? 2 : (DL == 8 ? 3 : 4); }
+constexpr int tpp_min_blocks() { return DL >= 32 ? ASP_TPP_MINB32 : (DL == 8 ? 3 : 4); }
 
 __device__ __forceinline__ double2 ldg2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
 // Shared-memory constant read that stays where it is written: a plain load is loop-invariant, so the
@@ -238,6 +241,10 @@ __global__ void __launch_bounds__(kTppBlock, tpp_min_blocks<DL>()) pcn_sweep_tpp
         }
         double cur = target(y);
         if (!active) cur = identity(OP_MIN);  // +inf: a padding particle never accepts
+        // from here on y holds ca * (x - mu): the proposal is then one DFMA per dimension and accepting a
+        // move is one DMUL per dimension (instead of a DMUL + DFMA and two register moves)
+#pragma unroll
+        for (int k = 0; k < DL; ++k) y[k] *= ca;
         bool moved = false;
         const uint64_t pidx = (uint64_t)(A.prm.d_slot ? A.prm.d_slot[i] : A.prm.index0 + i);
         uint4 aw = make_uint4(0, 0, 0, 0);
@@ -275,7 +282,7 @@ __global__ void __launch_bounds__(kTppBlock, tpp_min_blocks<DL>()) pcn_sweep_tpp
                 for (int j = 0; j < 4; ++j) {
                     const int k = q * 4 + j;
                     const double2 c = C01(k);
-                    const double v = fma(c.x, xi[j], ca * y[k]);
+                    const double v = fma(c.x, xi[j], y[k]);
                     yp[k] = v;
                     const double2 e = C23(k);
                     sq = fma(v, fma(e.x, v, e.y), sq);
@@ -314,7 +321,7 @@ __global__ void __launch_bounds__(kTppBlock, tpp_min_blocks<DL>()) pcn_sweep_tpp
             const bool acc = log_u < nw - cur;  // NaN -> reject, like the reference's NaN -> -inf
             if (acc) {
 #pragma unroll
-                for (int k = 0; k < DL; ++k) y[k] = yp[k];
+                for (int k = 0; k < DL; ++k) y[k] = ca * yp[k];
                 cur = nw;
                 moved = true;
             }
@@ -328,8 +335,12 @@ __global__ void __launch_bounds__(kTppBlock, tpp_min_blocks<DL>()) pcn_sweep_tpp
         // final state and its logs: evaluated once (by every lane: the group shuffles stay converged);
         // a particle that never moved keeps its input row and logs bit for bit
         double x[DL];
+        const double inv_ca = 1.0 / ca;  // ca > 0: rho = 1 goes to the general kernel
 #pragma unroll
-        for (int k = 0; k < DL; ++k) x[k] = C01(k).y + y[k];
+        for (int k = 0; k < DL; ++k) {
+            y[k] *= inv_ca;
+            x[k] = C01(k).y + y[k];
+        }
         double sq_ = 0.0, sp_ = 0.0, sl_ = 0.0, r_ = 0.0;
         bool pbad = false, lbad = false;
 #pragma unroll

@@ -6,6 +6,8 @@
 // Both are HBM/L2 bound: the search is a branch-free binary search whose upper
 // levels stay L2-resident; the gather moves whole rows with 128-bit accesses,
 // one sub-warp group per row so every row is a single contiguous burst.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace asp {
@@ -65,6 +67,7 @@ __global__ void __launch_bounds__(kBlock) build_guide_kernel(const double* __res
 // medium ones by the warp, ranges longer than 2^16 buckets (collapsed weights) are
 // deferred to a second, full-grid pass.
 constexpr int kLongRange = 1 << 16;
+constexpr int kGuideShift = 2;  // measured at N = 1e8: 6.23 (0), 5.94 (2), 7.12 (3), 9.12 ms (4) for CDF + search
 struct GuideDeferred {
     unsigned int count;
     unsigned int pad;
@@ -212,7 +215,10 @@ int asp_search_multinomial_guided(const double* d_cdf, int64_t n_cdf, const doub
     ASP_REQUIRE(d_cdf && d_u && d_idx && ws, "null pointer");
     ASP_REQUIRE(n_cdf > 0 && m > 0, "sizes must be positive");
     cudaStream_t s = (cudaStream_t)stream;
-    const int64_t B = n_cdf;
+    // buckets: n_cdf >> kGuideShift.  Fewer buckets than CDF entries keep the table small enough to stay in
+    // L2 while each query still resolves inside one or two 64-byte DRAM bursts of the CDF.
+    static const int shift = [] { const char* e = getenv("ASP_GUIDE_SHIFT"); return e ? atoi(e) : kGuideShift; }();
+    const int64_t B = (n_cdf >> shift) > 0 ? (n_cdf >> shift) : 1;
     GuideDeferred* def = (GuideDeferred*)((char*)ws + guide_bytes(n_cdf));
     const int gb = grid_for(n_cdf + 1, 1);
     guide_reset_kernel<<<1, 1, 0, s>>>(def);

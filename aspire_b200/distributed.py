@@ -228,6 +228,63 @@ class ShardedSMC:
         return Shard(x, ll, lp, lq, slot), rec
 
 
+def _host_buffer_leg(args, comm, engine, shard0, n_total, dev, unit):
+    """The sharded step with HOST buffers: every rank uploads its slice from pinned host memory over its own
+    PCIe link, runs ``ShardedSMC.step`` and downloads its offspring; device-timed, max over ranks."""
+    import psutil
+
+    dims = shard0.x.shape[1]
+    row_bytes = 8 * (dims + 3)
+    n_local = len(shard0)
+    budget = int(0.2 * psutil.virtual_memory().available / comm.world / (2 * row_bytes))
+    free_dev, _ = torch.cuda.mem_get_info(dev)
+    m = max(1, min(n_local, budget, int(0.6 * free_dev / (3 * row_bytes))))
+    neg = torch.tensor([-m / n_local], dtype=torch.float64, device=dev)
+    comm.all_reduce_max(neg)  # every rank uses the smallest fraction, so slices stay comparable
+    m = max(1, int(n_local * float(-neg[0])))
+    src = (shard0.x[:m], shard0.log_l[:m], shard0.log_p[:m], shard0.log_q[:m])
+    host_in = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in src]
+    for h, t in zip(host_in, src):
+        h.copy_(t)
+    cap = int(m * 1.2) + 4096
+    host_out = [torch.empty((cap, dims), dtype=torch.float64).pin_memory()] + [
+        torch.empty(cap, dtype=torch.float64).pin_memory() for _ in range(3)]
+    dev_in = [torch.empty_like(h, device=dev) for h in host_in]
+    stream = torch.cuda.current_stream()
+    moved = [0, 0]
+
+    def step():
+        for d, h in zip(dev_in, host_in):
+            d.copy_(h, non_blocking=True)
+        new, _ = engine.step(Shard(*dev_in), 0.0)
+        k = min(len(new), cap)
+        for h, t in zip(host_out, (new.x, new.log_l, new.log_p, new.log_q)):
+            h[:k].copy_(t[:k], non_blocking=True)
+        moved[0] += m * row_bytes
+        moved[1] += k * row_bytes
+
+    steps = max(1, min(args.steps, 3))
+    step()
+    torch.cuda.synchronize()
+    comm.barrier()
+    moved[0] = moved[1] = 0
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    for _ in range(steps):
+        step()
+    b.record(stream)
+    torch.cuda.synchronize()
+    comm.barrier()
+    t = torch.tensor([a.elapsed_time(b) / steps], dtype=torch.float64, device=dev)
+    comm.all_reduce_max(t)
+    tot = torch.tensor([float(m), moved[0] / steps, moved[1] / steps], dtype=torch.float64, device=dev)
+    comm.all_reduce_sum(tot)
+    ms = float(t[0])
+    return {"value": float(tot[0]) / (ms * 1e-3), "unit": unit, "h2d_bytes_per_step": int(tot[1]),
+            "d2h_bytes_per_step": int(tot[2]), "particles": int(tot[0]), "ms_per_step": ms, "steps": steps,
+            "api": "ShardedSMC.step on pinned host buffers, one PCIe link per rank (H2D + step + D2H timed, max over ranks)"}
+
+
 # ---------------------------------------------------------------------------------
 # bench.py --gpus N (N > 1): launched by torch.distributed.run, one rank per GPU
 # ---------------------------------------------------------------------------------
@@ -300,6 +357,9 @@ def run_bench(args, rank, world, dev, metric, unit, workload_config, bytes_per_p
     pm = torch.tensor([phase_ms[k] for k in phases], dtype=torch.float64, device=dev)
     comm.all_reduce_max(pm)
     phase_ms = {k: float(v) for k, v in zip(phases, pm)}
+    e2e = None
+    if not getattr(args, "no_e2e", False):
+        e2e = _host_buffer_leg(args, comm, engine, shard0, n_total, dev, unit)
     if rank == 0:
         peaks, kind = measured_peaks()
         value = n_total / (ms_per_step * 1e-3)
@@ -315,7 +375,7 @@ def run_bench(args, rank, world, dev, metric, unit, workload_config, bytes_per_p
             "config": {**workload_config(args, n_total), "parallelism": f"particle-sharded x{world}, owner-computes "
                        "resampling, scalar NCCL collectives only"},
             "clocks": clock_info, "gpu_launches": launches,
-            "e2e": None,
+            "e2e": e2e,
             "roofline": {"kernel": "pcn_sweep_tpp_kernel<32,1,rosenbrock,gaussian> (per GPU)", "bound": "hbm", "achieved": ach,
                          "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,
                          "peak_source": f"MEASURED_PEAKS.json ({kind})",
