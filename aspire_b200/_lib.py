@@ -156,6 +156,7 @@ SIGNATURES = {
     "asp_select_uniforms": (C.c_int, [C.c_uint64, C.c_uint32, _P, _I64, _D, _D, _I64, _P, _P, _P, _P, _P]),
     "asp_philox_uniform": (C.c_int, [C.c_uint64, C.c_uint32, _I64, _I64, _P, _P]),
     "asp_philox_normal": (C.c_int, [C.c_uint64, C.c_uint32, _I64, _I64, _I32, _P, _P, _P, _P]),
+    "asp_pcg64_uniform": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, _I64, _I64, _P, _P]),
 }
 
 _lib = None

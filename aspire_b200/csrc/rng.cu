@@ -53,11 +53,75 @@ __global__ void __launch_bounds__(kBlock) philox_normal_kernel(uint64_t seed, ui
     }
 }
 
+// ---- PCG64 (numpy's default bit generator) -------------------------------------
+// Generator.random() of the reference's rng (src/aspire/samples.py:1278 -> Generator.choice ->
+// Generator.random) reproduced on the device: draw j is the XSL-RR output of the 128-bit LCG state
+// after j + 1 steps.  Thread g jumps to draw offset + g with the O(log) affine power of the LCG, then
+// strides by the grid size with the affine map of T steps (computed once per block), so stores are
+// coalesced.  Spec + pin against numpy: oracle/pcg64.py, tests/test_pcg64_oracle.py.
+typedef unsigned __int128 u128;
+__device__ __forceinline__ u128 pcg_mult() {
+    return ((u128)0x2360ED051FC65DA4ULL << 64) | (u128)0x4385DF649FCCF645ULL;
+}
+// (A, C) such that state_{t + delta} = A state_t + C
+__device__ __forceinline__ void pcg_affine_power(uint64_t delta, u128 inc, u128& a_out, u128& c_out) {
+    u128 acc_mult = 1, acc_plus = 0, cur_mult = pcg_mult(), cur_plus = inc;
+    while (delta > 0) {
+        if (delta & 1) {
+            acc_mult *= cur_mult;
+            acc_plus = acc_plus * cur_mult + cur_plus;
+        }
+        cur_plus = (cur_mult + 1) * cur_plus;
+        cur_mult *= cur_mult;
+        delta >>= 1;
+    }
+    a_out = acc_mult;
+    c_out = acc_plus;
+}
+__device__ __forceinline__ double pcg_double(u128 state) {
+    const uint64_t hi = (uint64_t)(state >> 64), lo = (uint64_t)state;
+    const uint64_t x = hi ^ lo;
+    const unsigned rot = (unsigned)(hi >> 58);
+    const uint64_t r = (x >> rot) | (x << ((64u - rot) & 63u));
+    return (double)(r >> 11) * 0x1p-53;
+}
+
+__global__ void __launch_bounds__(kBlock) pcg64_uniform_kernel(uint64_t s_hi, uint64_t s_lo, uint64_t i_hi,
+                                                               uint64_t i_lo, int64_t offset, int64_t n,
+                                                               double* __restrict__ out) {
+    __shared__ u128 s_stride[2];
+    const u128 inc = ((u128)i_hi << 64) | i_lo;
+    const int64_t T = (int64_t)gridDim.x * blockDim.x;
+    if (threadIdx.x == 0) pcg_affine_power((uint64_t)T, inc, s_stride[0], s_stride[1]);
+    __syncthreads();
+    const u128 a_t = s_stride[0], c_t = s_stride[1];
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    u128 a, c;
+    pcg_affine_power((uint64_t)(offset + g + 1), inc, a, c);
+    u128 state = a * (((u128)s_hi << 64) | s_lo) + c;
+    for (int64_t j = g; j < n; j += T) {
+        out[j] = pcg_double(state);
+        state = a_t * state + c_t;
+    }
+}
+
 }  // namespace asp
 
 using namespace asp;
 
 extern "C" {
+
+int asp_pcg64_uniform(uint64_t state_hi, uint64_t state_lo, uint64_t inc_hi, uint64_t inc_lo, int64_t offset,
+                      int64_t n, double* d_out, void* stream) {
+    ASP_DEVICE_OR_RETURN();
+    ASP_REQUIRE(d_out, "null pointer");
+    ASP_REQUIRE(n > 0 && offset >= 0, "bad sizes");
+    ASP_REQUIRE(inc_lo & 1, "PCG64 increment must be odd");
+    pcg64_uniform_kernel<<<grid_for(n, 64), kBlock, 0, (cudaStream_t)stream>>>(state_hi, state_lo, inc_hi, inc_lo,
+                                                                              offset, n, d_out);
+    return check_launch("asp_pcg64_uniform");
+}
 
 int asp_philox_uniform(uint64_t seed, uint32_t stream_id, int64_t index0, int64_t n, double* d_out, void* stream) {
     ASP_DEVICE_OR_RETURN();

@@ -424,3 +424,14 @@ def philox_normal(seed: int, stream_id: int, n: int, dims: int, device, mean=Non
         check(_lib.load().asp_philox_normal(int(seed) & 0xFFFFFFFFFFFFFFFF, stream_id & 0xFFFFFFFF, index0, n, dims,
                                             _ptr(mean), _ptr(sigma), out.data_ptr(), _stream()), "asp_philox_normal")
     return out
+
+
+def pcg64_uniform(state: int, inc: int, n: int, device, offset: int = 0) -> torch.Tensor:
+    """Draws ``offset .. offset+n-1`` of ``numpy.random.Generator.random`` for a PCG64 generator with the
+    given 128-bit ``(state, inc)`` (``rng.bit_generator.state['state']``), generated on the device."""
+    out = torch.empty(n, dtype=torch.float64, device=device)
+    m64 = (1 << 64) - 1
+    if n:
+        check(_lib.load().asp_pcg64_uniform((state >> 64) & m64, state & m64, (inc >> 64) & m64, inc & m64, int(offset),
+                                            n, out.data_ptr(), _stream()), "asp_pcg64_uniform")
+    return out

@@ -6,6 +6,12 @@ The reference passes a ``numpy.random.Generator`` (or ``orng.ArrayRNG``) around
 ``HostGenerator``  wraps a ``numpy.random.Generator``: draws on the host in the
                    reference's order and uploads - PARITY mode; with the same
                    seed the ancestors are bit-identical to the reference's.
+``Pcg64Generator`` a ``HostGenerator`` whose bit generator is PCG64 (numpy's default): the
+                   resampling uniforms - the bulk draw of the step - are generated ON THE
+                   DEVICE from the generator's (state, inc) (``asp_pcg64_uniform``) and the
+                   host generator is advanced by the same count, so the stream, and hence
+                   the ancestors, are bit-identical to the reference's with no host draw or
+                   upload.  Scalars and normals still come from the host generator.
 ``PhiloxRNG``      device-side counter-based Philox4x32-10 (``asp_philox_*`` and
                    the in-kernel stream of ``asp_pcn_sweep``) - THROUGHPUT mode;
                    results are independent of launch geometry and of how
@@ -79,13 +85,31 @@ class HostGenerator:
         return True
 
 
+class Pcg64Generator(HostGenerator):
+    """``HostGenerator`` with the bulk uniforms drawn on the device (same PCG64 stream)."""
+
+    def uniform(self, n: int, device, index0: int = 0) -> torch.Tensor:
+        bg = self.rng.bit_generator
+        st = bg.state
+        if st.get("has_uint32", 0):  # a buffered 32-bit half would be consumed first: keep numpy's order
+            return super().uniform(n, device, index0)
+        u = ops.pcg64_uniform(int(st["state"]["state"]), int(st["state"]["inc"]), n, device)
+        bg.advance(n)
+        return u
+
+
+def _is_pcg64(rng) -> bool:
+    bg = getattr(rng, "bit_generator", None)
+    return bg is not None and type(bg).__name__ == "PCG64" and hasattr(bg, "advance")
+
+
 def as_uniform_source(rng):
     if rng is None:
         return PhiloxRNG()
     if isinstance(rng, (PhiloxRNG, HostGenerator)):
         return rng
     if isinstance(rng, np.random.Generator):
-        return HostGenerator(rng)
+        return Pcg64Generator(rng) if _is_pcg64(rng) else HostGenerator(rng)
     if isinstance(rng, (int, np.integer)):
         return PhiloxRNG(int(rng))
     if hasattr(rng, "random"):

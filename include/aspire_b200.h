@@ -299,6 +299,14 @@ int asp_philox_uniform(uint64_t seed, uint32_t stream_id, int64_t index0, int64_
 int asp_philox_normal(uint64_t seed, uint32_t stream_id, int64_t index0, int64_t n, int32_t dims,
                       const double* d_mean, const double* d_sigma, double* d_out, void* stream);
 
+/* PCG64 (numpy's default bit generator): d_out[j] = draw (offset + j) of Generator.random() for a
+ * generator whose bit_generator.state is {state, inc} (128-bit, given as hi/lo words).  Replaces
+ * the host draw + upload of numpy.random.Generator.choice's uniforms (src/aspire/samples.py:1278):
+ * the same seed gives bit-identical ancestors.  The caller advances the host generator by n
+ * (bit_generator.advance) to keep it in step. */
+int asp_pcg64_uniform(uint64_t state_hi, uint64_t state_lo, uint64_t inc_hi, uint64_t inc_lo, int64_t offset,
+                      int64_t n, double* d_out, void* stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif
