@@ -1,11 +1,14 @@
 """Sampler contract of the drop-in boundary (reference ``src/aspire/samplers/base.py:19-147``):
-same constructor, likelihood-call counter and ``config_dict``; checkpoint helpers are out of
-scope."""
+same constructor, likelihood-call counter, ``config_dict`` and checkpoint helpers
+(``samplers/base.py:158-276``: the state is a picklable dict; files are pickle blobs - the
+reference's HDF5 container needs ``h5py``, which this image does not have)."""
 
 from __future__ import annotations
 
 import functools
 import logging
+import pickle
+from pathlib import Path
 from typing import Any, Callable
 
 import torch
@@ -81,3 +84,95 @@ class Sampler:
             config["sample_calls"] = calls[-1] if str(include_sample_calls).lower() == "last" else {
                 i: c for i, c in enumerate(calls)}
         return config
+
+    # ---- checkpointing (reference samplers/base.py:158-276) ---------------------
+    def _checkpoint_extra_state(self) -> dict:
+        return {}
+
+    def _restore_extra_state(self, state: dict) -> None:
+        _ = state
+
+    def build_checkpoint_state(self, samples, iteration: int | None = None, meta: dict | None = None,
+                               include_sample_calls: str | bool = "last") -> dict:
+        """Picklable payload with the reference's keys; ``samples`` is the host copy (``to_numpy()``)."""
+        host = samples.to_numpy() if hasattr(samples, "to_numpy") else samples
+        state = {"sampler": self.__class__.__name__, "iteration": iteration, "samples": host,
+                 "config": self.config_dict(include_sample_calls=include_sample_calls), "parameters": self.parameters,
+                 "meta": meta or {}}
+        state.update(self._checkpoint_extra_state())
+        return state
+
+    def serialize_checkpoint(self, state: dict, protocol: int | None = None) -> bytes:
+        return pickle.dumps(state, protocol=pickle.HIGHEST_PROTOCOL if protocol is None else int(protocol))
+
+    def default_checkpoint_callback(self, state: dict) -> None:
+        self._last_checkpoint_state = state
+        self._last_checkpoint_bytes = self.serialize_checkpoint(state)
+
+    def default_file_checkpoint_callback(self, file_path) -> Callable[[dict], None]:
+        """Overwrite ``file_path`` with the latest checkpoint.  ``.pkl`` files hold the pickled state;
+        ``.h5`` / ``.hdf5`` (the reference's container: dataset ``/checkpoint/state``) need h5py."""
+        if file_path is None:
+            return self.default_checkpoint_callback
+        file_path = Path(file_path)
+        is_hdf = file_path.name.lower().endswith((".h5", ".hdf5"))
+        if is_hdf:
+            try:
+                import h5py  # noqa: F401
+            except ImportError as e:  # pragma: no cover - depends on the image
+                raise RuntimeError("HDF5 checkpoints need h5py; use a .pkl checkpoint_file_path") from e
+
+        def _callback(state: dict) -> None:
+            self.default_checkpoint_callback(state)
+            if is_hdf:
+                import h5py
+                import numpy as np
+
+                with h5py.File(file_path, "a") as f:
+                    grp = f.require_group("checkpoint")
+                    if "state" in grp:
+                        del grp["state"]
+                    grp.create_dataset("state", data=np.frombuffer(self._last_checkpoint_bytes, dtype=np.uint8))
+            else:
+                tmp = file_path.with_suffix(file_path.suffix + ".tmp")
+                with open(tmp, "wb") as f:
+                    f.write(self._last_checkpoint_bytes)
+                tmp.replace(file_path)
+
+        return _callback
+
+    def load_checkpoint_from_file(self, file_path, h5_path: str = "checkpoint", dsetname: str = "state") -> dict:
+        file_path = Path(file_path)
+        if file_path.name.lower().endswith((".h5", ".hdf5")):
+            import h5py
+
+            with h5py.File(file_path, "r") as f:
+                blob = f[h5_path][dsetname][...].tobytes()
+        else:
+            with open(file_path, "rb") as f:
+                blob = f.read()
+        return pickle.loads(blob)
+
+    def restore_from_checkpoint(self, source):
+        """-> (host sample dict, state) from a file path, pickled bytes or a state dict."""
+        if isinstance(source, (str, Path)):
+            state = self.load_checkpoint_from_file(source)
+        elif isinstance(source, bytes):
+            state = pickle.loads(source)
+        elif isinstance(source, dict):
+            state = source
+        else:
+            raise TypeError("Unsupported checkpoint source type.")
+        saved = state.get("samples")
+        if saved is None:
+            raise ValueError("Checkpoint missing samples.")
+        self._restore_extra_state(state)
+        return saved, state
+
+    @property
+    def last_checkpoint_state(self):
+        return getattr(self, "_last_checkpoint_state", None)
+
+    @property
+    def last_checkpoint_bytes(self):
+        return getattr(self, "_last_checkpoint_bytes", None)

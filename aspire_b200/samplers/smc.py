@@ -197,19 +197,20 @@ class SMCSampler(Sampler):
     ):
         if beta_tolerance is None:
             beta_tolerance = self.default_beta_tolerance
-        if resume_from is not None or checkpoint_callback is not None:
-            raise NotImplementedError("checkpoint / resume is a later scope row (SURVEY 8f-3)")
-        if checkpoint_every is not None or checkpoint_file_path is not None:
-            logger.warning("aspire_b200: checkpoint_every / checkpoint_file_path are accepted but ignored")
         self._configure_kernel(sampler_kwargs)
         if rng is not None:
             self.rng = as_uniform_source(rng)
         self.resampling = resampling
 
-        samples = self.draw_initial_samples(n_samples)
-        samples = SMCSamples.from_samples(samples, beta=0.0)
-        beta, iterations = 0.0, 0
-        self.history = SMCHistory()
+        resumed = resume_from is not None
+        if resumed:  # smc/base.py:301-314
+            samples, beta, iterations = self.restore_from_checkpoint(resume_from)
+            logger.info(f"Resumed SMC sampling at iteration {iterations} with beta={beta:.4f}")
+        else:
+            samples = self.draw_initial_samples(n_samples)
+            samples = SMCSamples.from_samples(samples, beta=0.0)
+            beta, iterations = 0.0, 0
+            self.history = SMCHistory()
         store_sample_history = store_sample_history and samples.x.numel() <= SAMPLE_HISTORY_MAX_ELEMENTS
         if store_sample_history:
             self.history.sample_history.append(samples.to_numpy())
@@ -245,12 +246,26 @@ class SMCSampler(Sampler):
         else:
             self.max_beta_step = 1.0
 
-        while True:
+        iterations = iterations or 0
+        if checkpoint_callback is None and checkpoint_every is not None:  # smc/base.py:366-371
+            checkpoint_callback = self.default_file_checkpoint_callback(checkpoint_file_path)
+        if checkpoint_callback is not None and checkpoint_every is None:
+            checkpoint_every = 1
+        run_smc_loop = True
+        if resumed:
+            last_beta = self.history.beta[-1] if self.history.beta else beta
+            if last_beta >= 1.0:
+                run_smc_loop = False
+                logger.info(f"Checkpoint beta {last_beta:.4f} indicates the SMC loop already completed")
+
+        while run_smc_loop:
             iterations += 1
             samples, beta, min_beta_step = self.tempering_step(samples, beta, beta_step, min_beta_step,
                                                                beta_tolerance, iterations)
             if store_sample_history:
                 self.history.sample_history.append(samples.to_numpy())
+            if checkpoint_callback is not None and checkpoint_every > 0 and iterations % checkpoint_every == 0:
+                checkpoint_callback(self.build_checkpoint_state(samples, iterations, beta))
             if beta == 1.0 or (max_n_steps is not None and iterations >= max_n_steps):
                 break
 
@@ -305,6 +320,46 @@ class SMCSampler(Sampler):
         self.history.log_norm_ratio_var.append(var_sum / n / (n * mean_u * mean_u) if mean_u != 0 else math.nan)
         logger.info(f"it {iterations} - ESS: {ess:.1f} ({eff:.2f} efficiency), log evidence ratio {log_ratio:.2f}")
         return samples, beta, min_beta_step
+
+    # ---- checkpoint / resume (smc/base.py:521-562) ----------------------------------
+    def build_checkpoint_state(self, samples, iteration: int, beta: float) -> dict:
+        return super().build_checkpoint_state(samples, iteration, meta={"beta": beta})
+
+    def _rng_state(self):
+        gen = getattr(self.rng, "rng", None)
+        if gen is not None and hasattr(gen, "bit_generator"):
+            return gen.bit_generator.state
+        if hasattr(self.rng, "seed"):
+            return {"bit_generator": "Philox4x32-10 (aspire_b200)", "seed": self.rng.seed, "stream": self.rng._stream}
+        return None
+
+    def _checkpoint_extra_state(self) -> dict:
+        import copy
+
+        return {"history": copy.deepcopy(self.history), "rng_state": self._rng_state(),
+                "sampler_kwargs": dict(getattr(self, "sampler_kwargs", None) or {}), "rho": getattr(self, "rho", None)}
+
+    def restore_from_checkpoint(self, source):
+        """-> (SMCSamples on the device, beta, iteration); restores history, rng state and the pCN step."""
+        saved, state = super().restore_from_checkpoint(source)
+        meta = state.get("meta", {}) if isinstance(state, dict) else {}
+        beta = meta.get("beta") if isinstance(meta, dict) else None
+        if beta is None:
+            beta = state.get("beta", 0.0)
+        self.history = state.get("history") or SMCHistory()
+        rs = state.get("rng_state")
+        if rs is not None:
+            gen = getattr(self.rng, "rng", None)
+            if gen is not None and hasattr(gen, "bit_generator") and "state" in rs:
+                gen.bit_generator.state = rs
+            elif hasattr(self.rng, "seed") and "seed" in rs:
+                self.rng.seed, self.rng._stream = int(rs["seed"]), int(rs["stream"])
+        if state.get("rho") is not None:
+            self.rho = float(state["rho"])
+        get = (lambda k: saved.get(k)) if isinstance(saved, dict) else (lambda k: getattr(saved, k, None))
+        samples = SMCSamples(x=get("x"), log_likelihood=get("log_likelihood"), log_prior=get("log_prior"),
+                             log_q=get("log_q"), beta=float(beta), parameters=self.parameters, device=self.device)
+        return samples, float(beta), int(state.get("iteration") or 0)
 
     # ---- kernel configuration (smc/minipcn.py:44-50) ---------------------------
     def _configure_kernel(self, sampler_kwargs):
