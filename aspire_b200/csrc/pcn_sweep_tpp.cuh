@@ -38,6 +38,19 @@ __device__ __forceinline__ double2 lds2(const double2* p) {
     return r;
 }
 
+// bytes of the mixture descriptor staged in dynamic shared memory (means [dims][ncp] + {h, logc}[ncp]), 16-aligned
+__host__ __device__ inline size_t tpp_gmm_bytes(int dims, int n_comp) {
+    if (n_comp <= 0) return 0;
+    const int ncp = (n_comp + 3) / 4 * 4;
+    return (sizeof(double) * ((size_t)dims * ncp + 2 * (size_t)ncp) + 15) & ~(size_t)15;
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // branch-free streaming log-sum-exp update with one exp:  (m, acc) <- (m, acc) (+) t
 __device__ __forceinline__ void lse_push(double& m, double& acc, double t) {
     const double ninf = identity(OP_MAX);
@@ -101,7 +114,7 @@ __global__ void __launch_bounds__(kTppBlock, tpp_min_blocks<DL>()) pcn_sweep_tpp
     __shared__ double2 s_c23[DT];  // {a2_k, a1_k}: folded quadratic of the accept test
     __shared__ double2 s_pbox[kPBox ? DT : 1], s_lbox[kLBox ? DT : 1];
     __shared__ unsigned int s_acc[kMaxMovesSmem];
-    extern __shared__ double s_dyn[];  // mixture: means [DT][ncp], then {1/2 is^2, logc}[ncp]
+    extern __shared__ __align__(16) double s_dyn[];  // mixture: means [DT][ncp], {1/2 is^2, logc}[ncp]; then row staging
 
     const int n_moves = A.prm.n_moves;
     const bool per_move = A.prm.reserved == 0;
@@ -224,18 +237,54 @@ __global__ void __launch_bounds__(kTppBlock, tpp_min_blocks<DL>()) pcn_sweep_tpp
         return T;
     };
 
-    for (int64_t base = warp_id * kPerWarp; base < A.n; base += stride) {
+    // Row staging.  The resampling gather reads random 8 DT-byte rows and the dependent chain idx -> row
+    // costs two DRAM latencies that 8 warps per SM cannot hide (measured: 5.6 ms for ONE move at N = 2e7,
+    // 0.8 ms per further move).  Each warp therefore owns two shared-memory buffers of 32 / G rows: the rows
+    // of batch b+1 are fetched with cp.async (16-byte chunks, whole rows per instruction, no registers)
+    // while batch b moves, and the ancestor indices of batch b+2 are loaded at the same time.  The finished
+    // rows go back through the same buffer so that global stores are row-contiguous too.
+    constexpr int kChunks = DT / 2;                 // 16-byte chunks per row
+    constexpr int kRowStride = DT * 8 + 16;         // +16: rows land in different banks for the per-thread reads
+    constexpr int kStageBytes = kPerWarp * kRowStride;
+    constexpr int kCopyIters = (kPerWarp * kChunks) / 32;  // = DL / 2
+    unsigned char* stage0 = reinterpret_cast<unsigned char*>(s_dyn) + tpp_gmm_bytes(DT, n_comp) +
+                            (size_t)(threadIdx.x >> 5) * 2 * kStageBytes;
+    const int wl = threadIdx.x & 31;
+    auto src_of = [&](int64_t b) -> int64_t {  // ancestor row of this thread's particle in the batch at `b`
+        const int64_t ii = b + sub < A.n ? b + sub : A.n - 1;
+        return A.idx ? A.idx[ii] : ii;
+    };
+    auto fetch = [&](int buf, int64_t src_row) {  // all 32 lanes: copy the batch's rows into buffer `buf`
+        const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(stage0 + buf * kStageBytes);
+#pragma unroll
+        for (int it = 0; it < kCopyIters; ++it) {
+            const int e = it * 32 + wl, r = e / kChunks, c = e % kChunks;
+            const int64_t sr = __shfl_sync(0xffffffffu, src_row, r * G);
+            cp_async16(dst0 + r * kRowStride + c * 16, A.x + sr * DT + c * 2);
+        }
+        cp_async_commit();
+    };
+    int64_t base = warp_id * kPerWarp;
+    int64_t src = 0, src_next = 0;
+    if (base < A.n) {
+        src = src_of(base);
+        fetch(0, src);
+        src_next = src_of(base + stride);
+    }
+    for (int bi = 0; base < A.n; base += stride, ++bi) {
         const int64_t i_raw = base + sub;
         const bool active = i_raw < A.n;
         const int64_t i = active ? i_raw : A.n - 1;
-        const int64_t src = A.idx ? A.idx[i] : i;
-        const int64_t i_next = i_raw + stride;
-        const int64_t src_next = i_next < A.n ? (A.idx ? A.idx[i_next] : i_next) : src;
-        const double* row = A.x + src * DT + lane * DL;
+        unsigned char* my_rows = stage0 + (bi & 1) * kStageBytes;
+        const double* row = reinterpret_cast<const double*>(my_rows + sub * kRowStride) + lane * DL;
+        cp_async_wait_all();
+        __syncwarp();
+        if (base + stride < A.n) fetch((bi + 1) & 1, src_next);  // overlaps this batch's moves
+        const int64_t src_next2 = src_of(base + 2 * stride);
         double y[DL], yp[DL];
 #pragma unroll
         for (int k = 0; k < DL; k += 2) {
-            const double2 v = ldg2(row + k);
+            const double2 v = *reinterpret_cast<const double2*>(row + k);
             y[k] = v.x - C01(k).y;
             y[k + 1] = v.y - C01(k + 1).y;
         }
@@ -255,11 +304,6 @@ __global__ void __launch_bounds__(kTppBlock, tpp_min_blocks<DL>()) pcn_sweep_tpp
                 log_u = accept_log_u(aw, t);
             } else {
                 log_u = A.prm.d_log_u[(size_t)t * A.n + i];
-            }
-            if (t == 1) {  // the next particle's row, fetched towards L2 while this one moves
-                const double* nx = A.x + src_next * DT + lane * DL;
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
-                if constexpr (DL * 8 > 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 16));
             }
             double stot = 0.0, rtot = 0.0;
             double xprev = 0.0, xfirst = 0.0;
@@ -381,7 +425,7 @@ __global__ void __launch_bounds__(kTppBlock, tpp_min_blocks<DL>()) pcn_sweep_tpp
         if (!moved) {
 #pragma unroll
             for (int k = 0; k < DL; k += 2) {
-                const double2 v = ldg2(row + k);
+                const double2 v = *reinterpret_cast<const double2*>(row + k);
                 x[k] = v.x;
                 x[k + 1] = v.y;
             }
@@ -389,16 +433,29 @@ __global__ void __launch_bounds__(kTppBlock, tpp_min_blocks<DL>()) pcn_sweep_tpp
             lp = A.lp[src];
             lq = A.lq[src];
         }
-        if (active) {
-            double* dst = A.xo + i * DT + lane * DL;
+        // the finished rows go out through the staging buffer: whole rows per store instruction
+        {
+            double* mine = reinterpret_cast<double*>(my_rows + sub * kRowStride) + lane * DL;
 #pragma unroll
-            for (int k = 0; k < DL; k += 2) st_stream2(dst + k, x[k], x[k + 1]);
-            if (lane == 0) {
-                A.llo[i] = ll;
-                A.lpo[i] = lp;
-                A.lqo[i] = lq;
+            for (int k = 0; k < DL; k += 2) *reinterpret_cast<double2*>(mine + k) = make_double2(x[k], x[k + 1]);
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < kCopyIters; ++it) {
+                const int e = it * 32 + wl, r = e / kChunks, c = e % kChunks;
+                if (base + r < A.n) {
+                    const double2 v = *reinterpret_cast<const double2*>(my_rows + r * kRowStride + c * 16);
+                    st_stream2(A.xo + (base + r) * DT + c * 2, v.x, v.y);
+                }
             }
+            __syncwarp();  // the buffer is refilled by the fetch issued at the top of the next batch
         }
+        if (active && lane == 0) {
+            A.llo[i] = ll;
+            A.lpo[i] = lp;
+            A.lqo[i] = lq;
+        }
+        src = src_next;
+        src_next = src_next2;
     }
     if (!per_move) {
 #pragma unroll
@@ -422,10 +479,10 @@ inline bool tpp_shape(int dims, int like_kind, int& dl, int& g) {
     }
 }
 
+template <int DL, int G>
 inline size_t tpp_dyn_smem(const SweepArgs& A) {
-    if (A.like.kind != ASP_DENSITY_GMM) return 0;
-    const int ncp = (A.like.n_comp + kTppChunk - 1) / kTppChunk * kTppChunk;
-    return sizeof(double) * ((size_t)A.dims * ncp + 2 * (size_t)ncp);
+    const size_t stage = (size_t)(kTppBlock / 32) * 2 * (32 / G) * (DL * G * 8 + 16);
+    return tpp_gmm_bytes(A.dims, A.like.kind == ASP_DENSITY_GMM ? A.like.n_comp : 0) + stage;
 }
 
 template <int DL, int G, int LIKE, int PRIOR>
@@ -434,10 +491,15 @@ inline int launch_tpp_n(const SweepArgs& A, cudaStream_t s) {
     const int64_t need = (A.n + per_block - 1) / per_block;
     const int64_t cap = (int64_t)kNumSMs * tpp_min_blocks<DL>();
     const int grid = (int)(need < cap ? need : cap);
-    const size_t smem = tpp_dyn_smem(A);
-    if (A.prm.noise_mode == 0) pcn_sweep_tpp_kernel<DL, G, LIKE, PRIOR, true><<<grid, kTppBlock, smem, s>>>(A);
-    else pcn_sweep_tpp_kernel<DL, G, LIKE, PRIOR, false><<<grid, kTppBlock, smem, s>>>(A);
-    return ASP_OK;
+    const size_t smem = tpp_dyn_smem<DL, G>(A);
+    auto launch = [&](auto kernel) -> int {
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return ASP_ERR_CUDA;
+        kernel<<<grid, kTppBlock, smem, s>>>(A);
+        return ASP_OK;
+    };
+    if (A.prm.noise_mode == 0) return launch(pcn_sweep_tpp_kernel<DL, G, LIKE, PRIOR, true>);
+    return launch(pcn_sweep_tpp_kernel<DL, G, LIKE, PRIOR, false>);
 }
 
 template <int LIKE, int PRIOR>

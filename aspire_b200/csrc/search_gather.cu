@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(kBlock) build_guide_kernel(const double* __res
 // medium ones by the warp, ranges longer than 2^16 buckets (collapsed weights) are
 // deferred to a second, full-grid pass.
 constexpr int kLongRange = 1 << 16;
-constexpr int kGuideShift = 2;  // measured at N = 1e8: 6.23 (0), 5.94 (2), 7.12 (3), 9.12 ms (4) for CDF + search
+constexpr int kGuideShift = 0;  // n_cdf buckets; micro-benchmark at N = 1e8: 6.23 (0), 5.94 (2), 7.12 (3), 9.12 ms (4), but 2 was slower inside the tempering step
 struct GuideDeferred {
     unsigned int count;
     unsigned int pad;
