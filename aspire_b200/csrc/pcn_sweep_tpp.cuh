@@ -254,6 +254,10 @@ __global__ void __launch_bounds__(kTppBlock, tpp_min_blocks<DL>()) pcn_sweep_tpp
         const int64_t ii = b + sub < A.n ? b + sub : A.n - 1;
         return A.idx ? A.idx[ii] : ii;
     };
+    auto pid_of = [&](int64_t b) -> uint64_t {  // Philox counter (global output slot) of this thread's particle
+        const int64_t ii = b + sub < A.n ? b + sub : A.n - 1;
+        return (uint64_t)(A.prm.d_slot ? A.prm.d_slot[ii] : A.prm.index0 + ii);
+    };
     auto fetch = [&](int buf, int64_t src_row) {  // all 32 lanes: copy the batch's rows into buffer `buf`
         const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(stage0 + buf * kStageBytes);
 #pragma unroll
@@ -266,10 +270,12 @@ __global__ void __launch_bounds__(kTppBlock, tpp_min_blocks<DL>()) pcn_sweep_tpp
     };
     int64_t base = warp_id * kPerWarp;
     int64_t src = 0, src_next = 0;
+    uint64_t pidx_next = 0;
     if (base < A.n) {
         src = src_of(base);
         fetch(0, src);
         src_next = src_of(base + stride);
+        pidx_next = pid_of(base);
     }
     for (int bi = 0; base < A.n; base += stride, ++bi) {
         const int64_t i_raw = base + sub;
@@ -281,6 +287,8 @@ __global__ void __launch_bounds__(kTppBlock, tpp_min_blocks<DL>()) pcn_sweep_tpp
         __syncwarp();
         if (base + stride < A.n) fetch((bi + 1) & 1, src_next);  // overlaps this batch's moves
         const int64_t src_next2 = src_of(base + 2 * stride);
+        const uint64_t pidx = pidx_next;  // loaded one batch ahead, like the ancestor indices
+        pidx_next = pid_of(base + stride);
         double y[DL], yp[DL];
 #pragma unroll
         for (int k = 0; k < DL; k += 2) {
@@ -295,7 +303,6 @@ __global__ void __launch_bounds__(kTppBlock, tpp_min_blocks<DL>()) pcn_sweep_tpp
 #pragma unroll
         for (int k = 0; k < DL; ++k) y[k] *= ca;
         bool moved = false;
-        const uint64_t pidx = (uint64_t)(A.prm.d_slot ? A.prm.d_slot[i] : A.prm.index0 + i);
         uint4 aw = make_uint4(0, 0, 0, 0);
         for (int t = 0; t < n_moves; ++t) {
             double log_u;

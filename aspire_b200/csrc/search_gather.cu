@@ -33,16 +33,21 @@ __global__ void __launch_bounds__(kBlock) search_multinomial_kernel(const double
         idx[j] = upper_bound(cdf, n, ld_stream(u + j));
 }
 
-__global__ void __launch_bounds__(kBlock) search_systematic_kernel(const double* __restrict__ cdf, int64_t n,
-                                                                   double u0, int64_t j0, int64_t m, double m_total,
-                                                                   int64_t* __restrict__ idx) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += stride) {
-        // (j + u0) / m_total: one fp64 add, one IEEE division, no contraction
-        double uj = __ddiv_rn(__dadd_rn(__ll2double_rn(j0 + j), u0), m_total);
-        int64_t k = upper_bound(cdf, n, uj);
-        idx[j] = k < n - 1 ? k : n - 1;
-    }
+// Systematic resampling, u_j = fl(fl(j + u0) / M): the queries are sorted, so instead of one 27-level binary
+// search per slot the CDF is streamed once - entry k owns the slots j with cdf[k-1] <= u_j < cdf[k] and
+// writes idx[j] = k there (same construction as the guide table below, with the offset u0).  Identical
+// to upper_bound(cdf, u_j) by construction: the slot boundaries are fixed up with the same IEEE operations.
+__device__ __forceinline__ double systematic_u(int64_t j, double u0, double m_total) {
+    return __ddiv_rn(__dadd_rn(__ll2double_rn(j), u0), m_total);  // one fp64 add, one IEEE division, no contraction
+}
+__device__ __forceinline__ int64_t first_slot_geq(double c, double u0, int64_t M, double Md) {
+    // smallest j in [0, M] with u_j >= c  (M if none)
+    if (!(c > 0.0)) return 0;
+    double e = ceil(c * Md - u0);
+    int64_t j = e > (double)M ? M : (e < 0.0 ? 0 : (int64_t)e);
+    while (j > 0 && systematic_u(j - 1, u0, Md) >= c) --j;
+    while (j < M && systematic_u(j, u0, Md) < c) ++j;
+    return j;
 }
 
 // ---- guide-table search ------------------------------------------------------
@@ -117,6 +122,46 @@ __global__ void __launch_bounds__(kBlock) build_guide_stream_kernel(const double
             const int64_t hi = __shfl_sync(0xffffffffu, b_hi, src);
             const int64_t kk = __shfl_sync(0xffffffffu, k, src);
             for (int64_t b = lo + lane; b < hi; b += 32) guide[b] = (GT)kk;
+        }
+    }
+}
+
+// slots [j0, j0 + m) of a sweep over m_total slots; idx is indexed by j - j0
+__global__ void __launch_bounds__(kBlock) search_systematic_stream_kernel(const double* __restrict__ cdf, int64_t n,
+                                                                          double u0, int64_t j0, int64_t m,
+                                                                          int64_t m_total, int64_t* __restrict__ idx,
+                                                                          GuideDeferred* __restrict__ deferred) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const double Md = (double)m_total;
+    const int lane = threadIdx.x & 31;
+    const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t base = first - lane; base <= n; base += stride) {  // warp-uniform trip count; k = n: virtual tail
+        const int64_t k = base + lane;
+        int64_t lo = 0, hi = 0;
+        if (k <= n) {
+            lo = k > 0 ? first_slot_geq(__ldg(cdf + k - 1), u0, m_total, Md) : 0;
+            hi = k < n ? first_slot_geq(__ldg(cdf + k), u0, m_total, Md) : m_total;
+            lo = (lo < j0 ? j0 : lo) - j0;
+            hi = (hi > j0 + m ? j0 + m : hi) - j0;
+        }
+        const int64_t val = k < n - 1 ? k : n - 1;
+        const int64_t len = hi - lo;
+        if (len > 0 && len <= 16) {
+            for (int64_t j = lo; j < hi; ++j) idx[j] = val;
+        } else if (len > kLongRange) {
+            const unsigned int slot = atomicAdd(&deferred->count, 1u);
+            deferred->entry[slot][0] = lo;
+            deferred->entry[slot][1] = hi;
+            deferred->entry[slot][2] = val;
+        }
+        unsigned int medium = __ballot_sync(0xffffffffu, len > 16 && len <= kLongRange);
+        while (medium) {
+            const int src = __ffs(medium) - 1;
+            medium &= medium - 1;
+            const int64_t l = __shfl_sync(0xffffffffu, lo, src);
+            const int64_t h = __shfl_sync(0xffffffffu, hi, src);
+            const int64_t v = __shfl_sync(0xffffffffu, val, src);
+            for (int64_t j = l + lane; j < h; j += 32) idx[j] = v;
         }
     }
 }
@@ -236,14 +281,25 @@ int asp_search_multinomial_guided(const double* d_cdf, int64_t n_cdf, const doub
     return check_launch("asp_search_multinomial_guided");
 }
 
+size_t asp_search_systematic_workspace_bytes(int64_t m) {
+    if (m < 1) m = 1;
+    return 256 + sizeof(long long) * 3 * (size_t)(m / kLongRange + 4);
+}
+
 int asp_search_systematic(const double* d_cdf, int64_t n_cdf, double u0, int64_t j0, int64_t m, int64_t m_total,
-                          int64_t* d_idx, void* stream) {
+                          int64_t* d_idx, void* ws, void* stream) {
     ASP_DEVICE_OR_RETURN();
     ASP_REQUIRE(d_cdf && d_idx, "null pointer");
     ASP_REQUIRE(n_cdf > 0 && m > 0 && m_total > 0, "sizes must be positive");
     ASP_REQUIRE(u0 >= 0.0 && u0 < 1.0, "u0 must be in [0, 1)");
-    search_systematic_kernel<<<grid_for(m, 1), kBlock, 0, (cudaStream_t)stream>>>(d_cdf, n_cdf, u0, j0, m,
-                                                                                  (double)m_total, d_idx);
+    ASP_REQUIRE(ws, "null workspace");
+    ASP_REQUIRE(j0 >= 0 && j0 + m <= m_total, "slot window outside the sweep");
+    cudaStream_t s = (cudaStream_t)stream;
+    GuideDeferred* def = (GuideDeferred*)ws;  // at most m / 2^16 + 2 long ranges
+    guide_reset_kernel<<<1, 1, 0, s>>>(def);
+    search_systematic_stream_kernel<<<grid_for(n_cdf + 1, 1), kBlock, 0, s>>>(d_cdf, n_cdf, u0, j0, m, m_total, d_idx,
+                                                                             def);
+    build_guide_deferred_kernel<int64_t><<<kNumSMs * 4, kBlock, 0, s>>>(d_idx, def);
     return check_launch("asp_search_systematic");
 }
 

@@ -195,6 +195,7 @@ class ShardedSMC:
         stream_u = self.next_stream()
         capacity = int(max(n_local, n_total / comm.world) * self.headroom) + 1024
         slot, u = ops.select_uniforms(n_total, lo, hi, capacity, dev, seed=self.seed, stream_id=stream_u, u_all=u_all)
+        mark("select")
         idx = ops.search_multinomial(cdf, u)
         n_out = slot.numel()
         mark("resample")
@@ -310,7 +311,7 @@ def run_bench(args, rank, world, dev, metric, unit, workload_config, bytes_per_p
     x0 = ops.philox_normal(seed, 0, n_local, dims, dev, mean=prob["q"].mean, sigma=prob["q"].sigma, index0=start)
     shard0 = Shard(x0, prob["like"].log_prob(x0), prob["prior"].log_prob(x0), prob["q"].log_prob(x0))
     engine = ShardedSMC(comm, prob["like"], prob["prior"], prob["q"], seed=seed + 1, n_moves=moves, rho=0.5)
-    phases = ["beta_search", "cdf_local", "cdf", "resample", "moments", "pcn_sweep"]
+    phases = ["beta_search", "cdf_local", "cdf", "select", "resample", "moments", "pcn_sweep"]
     stream = torch.cuda.current_stream()
 
     def one_step(record=None):
@@ -355,6 +356,7 @@ def run_bench(args, rank, world, dev, metric, unit, workload_config, bytes_per_p
         for (_, e0), (name, e1) in zip(evs[:-1], evs[1:]):
             phase_ms[name] += e0.elapsed_time(e1) / len(records)
     pm = torch.tensor([phase_ms[k] for k in phases], dtype=torch.float64, device=dev)
+    per_rank = comm.all_gather(pm).cpu().tolist()  # [rank][phase]: imbalance shows up here
     comm.all_reduce_max(pm)
     phase_ms = {k: float(v) for k, v in zip(phases, pm)}
     e2e = None
@@ -382,7 +384,8 @@ def run_bench(args, rank, world, dev, metric, unit, workload_config, bytes_per_p
                          "note": "issue-bound kernel (Philox, Box-Muller, fp64); HBM fraction reported as the contract asks"},
             "step_roofline": {"achieved": step_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s per GPU",
                               "frac": step_ach / peaks["hbm_gbs"]},
-            "cpu_baseline": None, "phase_ms": phase_ms, "beta_after_step": rec.beta, "acceptance": rec.acceptance,
+            "cpu_baseline": None, "phase_ms": phase_ms,
+            "phase_ms_per_rank": [[round(v, 3) for v in row] for row in per_rank], "beta_after_step": rec.beta, "acceptance": rec.acceptance,
             "n_local_out": rec.n_local_out,
         }
         print(json.dumps(line))

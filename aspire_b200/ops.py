@@ -267,8 +267,10 @@ def search_systematic(cdf, u0: float, m: int, j0: int = 0, m_total: int | None =
     idx = torch.empty(m, dtype=torch.int64, device=cdf.device)
     if m == 0:
         return idx
-    check(_lib.load().asp_search_systematic(cdf.data_ptr(), cdf.numel(), float(u0), j0, m, m_total, idx.data_ptr(),
-                                            _stream()), "asp_search_systematic")
+    lib = _lib.load()
+    ws = _sized_ws("systematic", lib.asp_search_systematic_workspace_bytes(m), cdf.device)
+    check(lib.asp_search_systematic(cdf.data_ptr(), cdf.numel(), float(u0), j0, m, m_total, idx.data_ptr(),
+                                    ws.data_ptr(), _stream()), "asp_search_systematic")
     return idx
 
 

@@ -62,6 +62,28 @@ class ClockSampler(threading.Thread):
         self._halt = threading.Event()
 
     def run(self):
+        """NVML (a query takes ~1 ms, so a 100 ms timed region still gets ~20 samples); nvidia-smi as fallback."""
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+            while not self._halt.is_set():
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                try:
+                    r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                row = ["", str(sm), str(mx), ""] + ["Active" if r & bits[k] else "Not Active" for k in
+                                                   ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                                    "sw_power_cap")]
+                self.rows.append(row)
+                self._halt.wait(0.005)
+            return
+        except Exception:
+            pass
         while not self._halt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
@@ -71,6 +93,14 @@ class ClockSampler(threading.Thread):
             except Exception:
                 pass
             self._halt.wait(0.2)
+
+    def _physical_index(self) -> int:
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.gpu_index < len(ids) and ids[self.gpu_index].isdigit():
+                return int(ids[self.gpu_index])
+        return self.gpu_index
 
     def stop(self):
         self._halt.set()

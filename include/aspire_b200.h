@@ -193,8 +193,12 @@ int asp_search_multinomial(const double* d_cdf, int64_t n_cdf, const double* d_u
 size_t asp_search_workspace_bytes(int64_t n_cdf);
 int asp_search_multinomial_guided(const double* d_cdf, int64_t n_cdf, const double* d_u, int64_t m, int64_t* d_idx,
                                   void* ws, void* stream);
+/* Systematic resampling: d_idx[j - j0] = #{k : cdf[k] <= (j + u0) / m_total} (clamped to n_cdf - 1) for the
+ * slots j0 <= j < j0 + m of a sweep over m_total slots.  The queries are sorted, so the CDF is streamed
+ * once and every entry writes the slots it owns.  ws: asp_search_systematic_workspace_bytes(m). */
+size_t asp_search_systematic_workspace_bytes(int64_t m);
 int asp_search_systematic(const double* d_cdf, int64_t n_cdf, double u0, int64_t j0, int64_t m,
-                          int64_t m_total, int64_t* d_idx, void* stream);
+                          int64_t m_total, int64_t* d_idx, void* ws, void* stream);
 
 /* ---- row gather (K7) ----------------------------------------------------
  * x[idx], logL[idx], logP[idx], logq[idx] - src/aspire/samples.py:1279-1287.
