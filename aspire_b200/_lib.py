@@ -150,6 +150,11 @@ SIGNATURES = {
         C.c_int,
         [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, C.POINTER(PcnParams), _I32, _P, _P],
     ),
+    "asp_pcn_propose_eval_supported": (_I32, [_I32, _I32, _I32]),
+    "asp_pcn_propose_eval": (C.c_int, [_P, _I64, _I32, C.POINTER(Density), C.POINTER(Density), C.POINTER(PcnParams), _I32,
+                                       _P, _P, _P, _P, _P]),
+    "asp_pcn_accept_scalar": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, C.POINTER(PcnParams), _I32, _P,
+                                        _P]),
     "asp_flow_weights_bytes": (C.c_size_t, [_I32, _I32]),
     "asp_flow_logprob_bf16": (C.c_int, [C.POINTER(Flow), _P, _I64, _P, _P, _P]),
     "asp_flow_sample_bf16": (C.c_int, [C.POINTER(Flow), _P, _I64, _P, _P, _P]),
@@ -190,7 +195,7 @@ def last_error() -> str:
 KERNELS_PER_CALL = {"asp_importance_weights": 3, "asp_cdf_exact": 6, "asp_cdf_tile_stats": 2,
                     "asp_cdf_set_tile_stats": 2, "asp_cdf_info": 0, "asp_device_check": 0,
                     "asp_search_multinomial_guided": 4, "asp_select_uniforms": 3, "asp_search_systematic": 3,
-                    "asp_search_systematic_workspace_bytes": 0}
+                    "asp_search_systematic_workspace_bytes": 0, "asp_pcn_propose_eval_supported": 0}
 launch_count = 0
 
 

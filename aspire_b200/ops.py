@@ -365,6 +365,33 @@ def pcn_accept(x, log_l, log_p, log_q, x_prop, log_l_prop, log_p_prop, log_q_pro
                                      accepts.data_ptr(), _stream()), "asp_pcn_accept")
 
 
+def pcn_propose_eval_supported(dims: int, like, prior) -> bool:
+    return bool(_lib.load().asp_pcn_propose_eval_supported(int(dims), int(like.kind), int(prior.kind)))
+
+
+def pcn_propose_eval(x, like, prior, prm, move: int):
+    """One pass: proposal x' of move ``move`` + built-in log prior / log likelihood at x' + r(x') - r(x).
+    -> (x', log_l', log_p', dr)"""
+    x = _f64(x, "x")
+    n, dims = x.shape
+    xp = torch.empty_like(x)
+    ll2, lp2, dr = (torch.empty(n, dtype=torch.float64, device=x.device) for _ in range(3))
+    check(_lib.load().asp_pcn_propose_eval(x.data_ptr(), n, dims, C.byref(like.struct()), C.byref(prior.struct()),
+                                           C.byref(prm), move, xp.data_ptr(), ll2.data_ptr(), lp2.data_ptr(),
+                                           dr.data_ptr(), _stream()), "asp_pcn_propose_eval")
+    return xp, ll2, lp2, dr
+
+
+def pcn_accept_scalar(x, log_l, log_p, log_q, x_prop, log_l_prop, log_p_prop, log_q_prop, dr, prm, move: int, accepts):
+    """In-place accept/reject of move ``move`` from the scalars of ``pcn_propose_eval`` + the caller's log q(x')."""
+    ts = [_f64(t, "tensor") for t in (x, log_l, log_p, log_q, x_prop, log_l_prop, log_p_prop, log_q_prop, dr)]
+    for a, b in zip(ts[:4], (x, log_l, log_p, log_q)):
+        if a.data_ptr() != b.data_ptr():
+            raise AspireB200Error("pcn_accept_scalar updates in place: state tensors must be contiguous")
+    check(_lib.load().asp_pcn_accept_scalar(*(t.data_ptr() for t in ts), x.shape[0], x.shape[1], C.byref(prm), move,
+                                            accepts.data_ptr(), _stream()), "asp_pcn_accept_scalar")
+
+
 # ---- K9 / K10 ---------------------------------------------------------------
 def flow_logprob(flow_struct, x, want_z: bool = False):
     """Coupling-flow log_prob on tcgen05 (bf16 GEMMs, fp32 epilogue).  -> log_q [n] (, z [n, D])"""

@@ -426,7 +426,17 @@ class SMCSampler(Sampler):
                 x, ll, lp, lq = (t.clone() for t in (particles.x, particles.log_likelihood, particles.log_prior,
                                                      particles.log_q))
             accepts = torch.zeros(max(n_moves, 1), dtype=torch.int64, device=self.device)
-            for t in range(n_moves):
+            # built-in prior / likelihood with a proposal that only offers log_prob (a flow): one pass proposes
+            # and evaluates both densities, the flow adds log q(x'), a scalar kernel accepts (csrc/pcn_eval.cu)
+            semi = (isinstance(self._log_likelihood, Density) and isinstance(self._log_prior, Density)
+                    and self.rho < 1.0 and x.data_ptr() % 16 == 0
+                    and ops.pcn_propose_eval_supported(dims, self._log_likelihood, self._log_prior))
+            for t in range(n_moves if semi else 0):
+                xp, ll2, lp2, dr = ops.pcn_propose_eval(x, self._log_likelihood, self._log_prior, prm, t)
+                lq2 = torch.as_tensor(self.prior_flow.log_prob(xp), dtype=torch.float64, device=self.device).contiguous()
+                ops.pcn_accept_scalar(x, ll, lp, lq, xp, ll2, lp2, lq2, dr, prm, t, accepts)
+                self.n_likelihood_evaluations += n
+            for t in range(0 if semi else n_moves):
                 xp = ops.pcn_propose(x, prm, t)
                 prop = SMCSamples(xp, beta=beta, device=self.device, parameters=self.parameters)
                 lq2 = torch.as_tensor(self.prior_flow.log_prob(xp), dtype=torch.float64, device=self.device).contiguous()

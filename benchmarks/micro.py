@@ -5,6 +5,7 @@
     python benchmarks/micro.py resample    # C5: exact CDF + ancestor search, N = 1e4 .. 1e9
     python benchmarks/micro.py importance  # C2: importance reweighting, N = 1e6, D = 16
     python benchmarks/micro.py sweep       # K8: fused gather + 10 pCN moves per benchmark problem
+    python benchmarks/micro.py c4          # C4: mixture SMC step with the tcgen05 flow as proposal (unfused moves)
 
 Each prints JSON lines; times are CUDA events over `--iters` launches after 3 warm-ups, on inputs
 larger than L2 where the size allows (noted per line otherwise).
@@ -146,9 +147,50 @@ def sweep(args):
         np.savez(args.dump, **dump)
 
 
+def c4(args):
+    """C4: 64-D 8-component mixture, coupling-flow proposal evaluated on tcgen05 inside the loop.  One tempering step
+    = reweight + beta bisection + exact resample + `moves` pCN moves; the proposal density is the flow, so every move
+    is asp_pcn_propose -> flow log_prob (tcgen05) -> prior / likelihood kernels -> asp_pcn_accept."""
+    from aspire_b200.flows import CouplingFlow
+    from aspire_b200.history import SMCHistory
+    from aspire_b200.rng import PhiloxRNG
+    from aspire_b200.samplers import SMCSampler
+    from aspire_b200.samples import SMCSamples
+
+    dev = torch.device("cuda")
+    n, dims, moves = args.n or 10_000_000, 64, args.moves
+    prob = tg.gmm_problem(dims, device=dev)
+    flow = CouplingFlow(dims, device=dev, n_layers=3, rng=PhiloxRNG(3), seed=1)
+    flow.std = torch.full((dims,), 2.5, dtype=torch.float64, device=dev)  # broad proposal over the mixture
+    flow._struct = None
+    s = SMCSampler(prob["like"], prob["prior"], dims, flow, rng=PhiloxRNG(4))
+    assert not s.fused
+    s._configure_kernel(dict(n_steps=moves, rho=0.3, adapt_rho=False))
+    s.resampling, s.target_efficiency, s.target_efficiency_rate = "multinomial", 0.5, 1.0
+    s.adaptive, s.adaptive_min_beta_step, s.max_beta_step = True, False, 1.0
+    s.history = SMCHistory()
+    x0, lq0 = flow.sample_and_log_prob(n)
+    p0 = SMCSamples(x0, log_likelihood=prob["like"].log_prob(x0), log_prior=prob["prior"].log_prob(x0), log_q=lq0,
+                    beta=0.0, device=dev)
+    t_flow = timed(lambda: flow.log_prob(x0), 3)
+
+    def step():
+        p0.__dict__.pop("_slope_cache", None)
+        return s.tempering_step(p0, 0.0, float("nan"), 0.0, 1e-6)
+
+    ms = timed(step, max(2, args.iters // 3))
+    flow._check_error()
+    half, h = dims // 2, 64
+    flops = 3 * 2 * (half * h + h * h + h * dims) * n * moves
+    print(json.dumps({"bench": "c4_smc_step_flow_proposal", "config": "C4", "particles": n, "dims": dims, "moves": moves,
+                      "ms_per_step": ms, "particles_per_s": n / ms * 1e3, "ms_flow_logprob": t_flow,
+                      "flow_share": moves * t_flow / ms, "flow_tflops_in_step": flops / ms / 1e9,
+                      "beta": s.history.beta[-1], "acceptance": s.history.mcmc_acceptance[-1]}))
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["flow", "resample", "importance", "sweep"])
+    ap.add_argument("what", choices=["flow", "resample", "importance", "sweep", "c4"])
     ap.add_argument("--n", type=int, default=0)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--moves", type=int, default=10)
@@ -156,4 +198,4 @@ if __name__ == "__main__":
     ap.add_argument("--dump", default="")
     a = ap.parse_args()
     ops.device_check()
-    {"flow": flow, "resample": resample, "importance": importance, "sweep": sweep}[a.what](a)
+    {"flow": flow, "resample": resample, "importance": importance, "sweep": sweep, "c4": c4}[a.what](a)

@@ -256,6 +256,21 @@ int asp_pcn_accept(double* d_x, double* d_log_l, double* d_log_p, double* d_log_
                    int32_t dims, const asp_pcn_params_t* params, int32_t move, unsigned long long* d_accepts,
                    void* stream);
 
+/* Semi-fused move for a proposal density that is not a built-in (e.g. a flow evaluated by
+ * asp_flow_logprob_bf16): asp_pcn_propose_eval proposes x' for move `move` and evaluates the built-in
+ * prior / likelihood at x' plus the reference-measure term d_dr = r(x') - r(x) in ONE pass (x read once,
+ * x' written once); after the caller evaluated log q(x'), asp_pcn_accept_scalar decides from the scalars
+ * and copies the accepted rows.  Same step and noise stream as asp_pcn_sweep / asp_pcn_propose + asp_pcn_accept.
+ * asp_pcn_propose_eval_supported: 1 if (dims, kinds) is built (dims 4, 8, 16, 32, 64), else use the unfused pair. */
+int32_t asp_pcn_propose_eval_supported(int32_t dims, int32_t like_kind, int32_t prior_kind);
+int asp_pcn_propose_eval(const double* d_x, int64_t n, int32_t dims, const asp_density_t* like,
+                         const asp_density_t* prior, const asp_pcn_params_t* params, int32_t move, double* d_x_prop,
+                         double* d_log_l_prop, double* d_log_p_prop, double* d_dr, void* stream);
+int asp_pcn_accept_scalar(double* d_x, double* d_log_l, double* d_log_p, double* d_log_q, const double* d_x_prop,
+                          const double* d_log_l_prop, const double* d_log_p_prop, const double* d_log_q_prop,
+                          const double* d_dr, int64_t n, int32_t dims, const asp_pcn_params_t* params, int32_t move,
+                          unsigned long long* d_accepts, void* stream);
+
 /* ---- coupling-flow log_prob / sample on tcgen05 (K9/K10) ---------------------
  * ZukoFlow.log_prob / sample_and_log_prob, src/aspire/flows/torch/flows.py:327-387, with
  * the affine data transform of src/aspire/transforms.py:618-628 folded in.  Spec and

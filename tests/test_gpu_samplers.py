@@ -344,3 +344,48 @@ def _no_h5py():
         return False
     except ImportError:
         return True
+
+
+@pytest.mark.parametrize("name,dims", [("rosenbrock", 32), ("gmm", 64), ("gauss", 16), ("rosenbrock", 8)])
+def test_semi_fused_move_equals_unfused_and_fused(cuda, name, dims):
+    """asp_pcn_propose_eval + asp_pcn_accept_scalar (csrc/pcn_eval.cu) walk the same trajectory as
+    asp_pcn_propose / density kernels / asp_pcn_accept and as the fused sweep."""
+    import torch
+
+    from aspire_b200 import ops
+    from aspire_b200 import targets as tg
+
+    mk = dict(rosenbrock=tg.rosenbrock_problem, gmm=tg.gmm_problem, gauss=tg.gaussian_problem)[name]
+    pg = mk(dims)
+    n, moves, beta, rho = 5000, 4, 0.3, 0.35
+    x0 = ops.philox_normal(8, 0, n, dims, cuda, mean=pg["q"].mean, sigma=pg["q"].sigma)
+    logs0 = [pg[k].log_prob(x0) for k in ("like", "prior", "q")]
+    mom = ops.weighted_moments(x0)
+    mu, sigma = ops.moments_to_mu_sigma(mom, dims)
+    assert ops.pcn_propose_eval_supported(dims, pg["like"], pg["prior"])
+    results = []
+    for mode in ("semi", "unfused"):
+        x = x0.clone()
+        ll, lp, lq = (t.clone() for t in logs0)
+        prm = ops.make_pcn_params(beta, rho, mu, sigma, moves, seed=31, stream0=5, index0=17)
+        acc = torch.zeros(moves, dtype=torch.int64, device=cuda)
+        for t in range(moves):
+            if mode == "semi":
+                xp, ll2, lp2, dr = ops.pcn_propose_eval(x, pg["like"], pg["prior"], prm, t)
+                np.testing.assert_allclose(ll2.cpu().numpy(), pg["like"].log_prob(xp).cpu().numpy(), rtol=1e-12, atol=1e-11)
+                np.testing.assert_allclose(lp2.cpu().numpy(), pg["prior"].log_prob(xp).cpu().numpy(), rtol=1e-12, atol=1e-11)
+                ops.pcn_accept_scalar(x, ll, lp, lq, xp, ll2, lp2, pg["q"].log_prob(xp), dr, prm, t, acc)
+            else:
+                xp = ops.pcn_propose(x, prm, t)
+                ops.pcn_accept(x, ll, lp, lq, xp, pg["like"].log_prob(xp), pg["prior"].log_prob(xp),
+                               pg["q"].log_prob(xp), prm, t, acc)
+        results.append((x.cpu().numpy(), ll.cpu().numpy(), acc.cpu().numpy()))
+    prm = ops.make_pcn_params(beta, rho, mu, sigma, moves, seed=31, stream0=5, index0=17)
+    fused = ops.pcn_sweep(x0, *logs0, None, pg["like"], pg["prior"], pg["q"], prm)
+    (xs, ls, as_), (xu, lu, au) = results
+    np.testing.assert_array_equal(as_, au)
+    np.testing.assert_array_equal(as_, fused[4].cpu().numpy())
+    np.testing.assert_allclose(xs, xu, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(xs, fused[0].cpu().numpy(), rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(ls, fused[1].cpu().numpy(), rtol=1e-11, atol=1e-10)
+    assert 0 < as_.sum() < moves * n
