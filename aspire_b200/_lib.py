@@ -122,6 +122,9 @@ SIGNATURES = {
     "asp_beta_search_init": (C.c_int, [_P, _D, _D, _D, _D, _P, _P]),
     "asp_beta_search_pass": (C.c_int, [_P, _I64, _P, C.c_int, _P, _P]),
     "asp_beta_search_decide": (C.c_int, [_P, _P]),
+    "asp_beta_search_max_passes3": (C.c_int, [_D, _D]),
+    "asp_beta_search_pass3": (C.c_int, [_P, _I64, _P, _P, C.c_int, _P, _P]),
+    "asp_beta_search_decide3": (C.c_int, [_P, _P, _P]),
     "asp_smc_weights": (C.c_int, [_P, _I64, _D, _D, _D, _D, _P, _P, _P, _P, _P]),
     "asp_cdf_workspace_bytes": (C.c_size_t, [_I64]),
     "asp_cdf_tile_stats": (C.c_int, [_P, _I64, _P, _P]),
@@ -195,7 +198,7 @@ def last_error() -> str:
 KERNELS_PER_CALL = {"asp_importance_weights": 3, "asp_cdf_exact": 6, "asp_cdf_tile_stats": 2,
                     "asp_cdf_set_tile_stats": 2, "asp_cdf_info": 0, "asp_device_check": 0,
                     "asp_search_multinomial_guided": 4, "asp_select_uniforms": 3, "asp_search_systematic": 3,
-                    "asp_search_systematic_workspace_bytes": 0, "asp_pcn_propose_eval_supported": 0}
+                    "asp_search_systematic_workspace_bytes": 0, "asp_pcn_propose_eval_supported": 0, "asp_beta_search_max_passes3": 0}
 launch_count = 0
 
 

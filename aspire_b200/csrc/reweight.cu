@@ -201,6 +201,91 @@ __global__ void __launch_bounds__(kBlock) beta_pass_kernel(const double* __restr
 }
 
 // ---------------------------------------------------------------------------
+// Three bisection levels per pass.  The seven betas a 3-level bisection of [beta_min, beta_max] can visit
+// are beta_min + k h, h = (beta_max - beta_min) / 8, so their weights are E r^k with
+// E = exp((beta_min - beta_prev)(d - d_max)),  r = exp(h (d - d_max)):  two exps and seven multiplies per
+// particle instead of three dependent passes (each one exp).  The decisions are the reference's
+// (smc/base.py:177-185: beta_try = 0.5 (max + min), ESS/N >= target), replayed on the seven (S1, S2) pairs.
+// ---------------------------------------------------------------------------
+constexpr int kBetaLevels = 3;
+constexpr int kBetaCand = (1 << kBetaLevels) - 1;  // 7
+
+__device__ __forceinline__ void beta_decide3(asp_beta_state_t* st, const double* sums) {
+    if (st->phase != 1) return;
+    double lo = st->beta_min, hi = st->beta_max;
+    int k_lo = 0, k_hi = 1 << kBetaLevels;  // grid indices of lo / hi
+    for (int level = 0; level < kBetaLevels; ++level) {
+        if (!(hi - lo > st->tol)) break;
+        const double mid = 0.5 * (hi + lo);  // the reference's beta_try
+        const int k = (k_lo + k_hi) >> 1;
+        const double s1 = sums[2 * (k - 1)], s2 = sums[2 * (k - 1) + 1];
+        const double eff = (s1 * s1 / s2) / st->n_total;
+        if (eff >= st->target_eff) {
+            lo = mid;
+            k_lo = k;
+            st->s1_min = s1;
+            st->s2_min = s2;
+            st->min_valid = 1;
+        } else {
+            hi = mid;
+            k_hi = k;
+        }
+        st->s1 = s1;
+        st->s2 = s2;
+        st->n_evals += 1;
+    }
+    st->beta_min = lo;
+    st->beta_max = hi;
+    if (hi - lo > st->tol) st->beta_try = 0.5 * (hi + lo);
+    else st->phase = 2;
+}
+
+__global__ void beta_decide3_kernel(asp_beta_state_t* st, const double* sums) { beta_decide3(st, sums); }
+
+__global__ void __launch_bounds__(kBlock) beta_pass3_kernel(const double* __restrict__ d, int64_t n,
+                                                            asp_beta_state_t* st, double* __restrict__ sums,
+                                                            int fused_decide, ReduceWs* ws) {
+    __shared__ double smem[2 * kBetaCand * 32];
+    if (st->phase != 1) return;  // uniform across the grid
+    const double d_max = st->d_max;
+    const double db0 = st->beta_min - st->beta_prev;
+    const double h = (st->beta_max - st->beta_min) * 0.125;
+    double v[2 * kBetaCand];
+    int ops[2 * kBetaCand];
+#pragma unroll
+    for (int k = 0; k < 2 * kBetaCand; ++k) {
+        v[k] = 0.0;
+        ops[k] = OP_SUM;
+    }
+    auto accumulate = [&](double x) {
+        const double t = x - d_max;  // <= 0: every factor below is in [0, 1]
+        const double e0 = exp(db0 * t), r = exp(h * t);
+        double e = e0;
+#pragma unroll
+        for (int k = 0; k < kBetaCand; ++k) {
+            e *= r;
+            v[2 * k] += e;
+            v[2 * k + 1] = fma(e, e, v[2 * k + 1]);
+        }
+    };
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + (kUnroll - 1) * stride < n; i += kUnroll * stride) {
+        double x[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) x[u] = ld_stream(d + i + u * stride);
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) accumulate(x[u]);
+    }
+    for (; i < n; i += stride) accumulate(d[i]);
+    grid_reduce<2 * kBetaCand>(v, ops, ws, smem, [&](double(&r)[2 * kBetaCand]) {
+#pragma unroll
+        for (int k = 0; k < 2 * kBetaCand; ++k) sums[k] = r[k];
+        if (fused_decide) beta_decide3(st, sums);
+    });
+}
+
+// ---------------------------------------------------------------------------
 // resampling weights, evidence-variance sum, exact-scan tile statistics
 // one block handles one ASP_CDF_TILE (=2048) tile per iteration
 // ---------------------------------------------------------------------------
@@ -369,6 +454,12 @@ int asp_beta_search_max_passes(double beta_prev, double tol) {
     return k + 2;
 }
 
+/* passes of asp_beta_search_pass3 after the single beta = 1 pass: three bisection levels each */
+int asp_beta_search_max_passes3(double beta_prev, double tol) {
+    const int levels = asp_beta_search_max_passes(beta_prev, tol) - 1;
+    return (levels + kBetaLevels - 1) / kBetaLevels;
+}
+
 int asp_beta_search_init(asp_beta_state_t* d_state, double beta_prev, double target_eff, double tol, double n_total,
                          const double* d_stats, void* stream) {
     ASP_DEVICE_OR_RETURN();
@@ -385,6 +476,23 @@ int asp_beta_search_pass(const double* d_d, int64_t n, asp_beta_state_t* d_state
     beta_pass_kernel<<<grid_for(n, kUnroll), kBlock, 0, (cudaStream_t)stream>>>(d_d, n, d_state, fused_decide,
                                                                                 (ReduceWs*)ws);
     return check_launch("asp_beta_search_pass");
+}
+
+int asp_beta_search_pass3(const double* d_d, int64_t n, asp_beta_state_t* d_state, double* d_sums, int fused_decide,
+                          void* ws, void* stream) {
+    ASP_DEVICE_OR_RETURN();
+    ASP_REQUIRE(d_d && d_state && d_sums && ws, "null pointer");
+    ASP_REQUIRE(n > 0, "n must be positive");
+    beta_pass3_kernel<<<grid_for(n, kUnroll), kBlock, 0, (cudaStream_t)stream>>>(d_d, n, d_state, d_sums, fused_decide,
+                                                                                 (ReduceWs*)ws);
+    return check_launch("asp_beta_search_pass3");
+}
+
+int asp_beta_search_decide3(asp_beta_state_t* d_state, const double* d_sums, void* stream) {
+    ASP_DEVICE_OR_RETURN();
+    ASP_REQUIRE(d_state && d_sums, "null pointer");
+    beta_decide3_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(d_state, d_sums);
+    return check_launch("asp_beta_search_decide3");
 }
 
 int asp_beta_search_decide(asp_beta_state_t* d_state, void* stream) {

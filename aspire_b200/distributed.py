@@ -152,9 +152,9 @@ class ShardedSMC:
         total = carry_out[:1].clone()
         comm.broadcast(total, g - 1)
         cdf = ops.cdf_write(p, total)
-        th = float(total)
-        lo = float(carry[2]) / th if r > 0 else 0.0          # == global cdf just before this slice (IEEE division)
-        hi = 1.0 if r == g - 1 else float(cdf[-1])
+        th, c_in, c_last = torch.stack([total[0], carry[2], cdf[-1]]).tolist()   # one device -> host read
+        lo = c_in / th if r > 0 else 0.0                     # == global cdf just before this slice (IEEE division)
+        hi = 1.0 if r == g - 1 else c_last
         return cdf, lo, hi, host
 
     # -- one tempering step ---------------------------------------------------------
@@ -333,10 +333,15 @@ def run_bench(args, rank, world, dev, metric, unit, workload_config, bytes_per_p
         one_step()
     torch.cuda.synchronize()
     comm.barrier()
-    clocks = ClockSampler(dev.index)
-    clocks.start()
+    clocks = ClockSampler(dev.index) if rank == 0 else None  # one sampler thread per box, not per rank
+    if clocks:
+        clocks.start()
     records = []
     launches0 = _lib.launch_count
+    import gc
+
+    gc.collect()
+    gc.disable()  # a cyclic-GC pause on one rank stalls every rank at the next collective
     torch.cuda.synchronize()
     comm.barrier()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -346,8 +351,9 @@ def run_bench(args, rank, world, dev, metric, unit, workload_config, bytes_per_p
     b.record(stream)
     torch.cuda.synchronize()
     comm.barrier()
+    gc.enable()
     launches = _lib.launch_count - launches0
-    clock_info = clocks.stop()
+    clock_info = clocks.stop() if clocks else None
     ms = torch.tensor([a.elapsed_time(b) / args.steps], dtype=torch.float64, device=dev)
     comm.all_reduce_max(ms)                                  # max over ranks, device-timed
     ms_per_step = float(ms[0])

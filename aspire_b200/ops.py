@@ -120,9 +120,11 @@ _STATE_WORDS = C.sizeof(_lib.BetaState) // 8
 
 
 def beta_search(d, stats, beta_prev: float, target_eff: float, tol: float, n_total: int | None = None,
-                allreduce=None) -> _lib.BetaState:
+                allreduce=None, multi_level: bool = True) -> _lib.BetaState:
     """Device-driven bisection of ``determine_beta`` (smc/base.py:166-186).
 
+    ``multi_level`` (default) resolves three bisection levels per pass over ``d`` (``asp_beta_search_pass3``),
+    with the same decisions and the same beta as one level per pass.
     Launches a fixed number of passes with no host round trip; ``allreduce``
     (multi-GPU) is called on the two-element sums tensor between a pass and its
     decision.  Returns the final state (one device->host read)."""
@@ -135,13 +137,30 @@ def beta_search(d, stats, beta_prev: float, target_eff: float, tol: float, n_tot
     st = _stream()
     check(lib.asp_beta_search_init(state.data_ptr(), beta_prev, target_eff, tol, n_total, stats.data_ptr(), st),
           "asp_beta_search_init")
-    for _ in range(lib.asp_beta_search_max_passes(beta_prev, tol)):
+    sums = torch.zeros(14, dtype=torch.float64, device=d.device)
+
+    def single_pass():
         if allreduce is None:
             check(lib.asp_beta_search_pass(d.data_ptr(), n, state.data_ptr(), 1, ws, st), "asp_beta_search_pass")
         else:
             check(lib.asp_beta_search_pass(d.data_ptr(), n, state.data_ptr(), 0, ws, st), "asp_beta_search_pass")
             allreduce(state[7:9])  # s1, s2
             check(lib.asp_beta_search_decide(state.data_ptr(), st), "asp_beta_search_decide")
+
+    if not multi_level:
+        for _ in range(lib.asp_beta_search_max_passes(beta_prev, tol)):
+            single_pass()
+    else:
+        single_pass()  # ESS at beta = 1 (smc/base.py:170-175), then three bisection levels per pass
+        for _ in range(lib.asp_beta_search_max_passes3(beta_prev, tol)):
+            if allreduce is None:
+                check(lib.asp_beta_search_pass3(d.data_ptr(), n, state.data_ptr(), sums.data_ptr(), 1, ws, st),
+                      "asp_beta_search_pass3")
+            else:
+                check(lib.asp_beta_search_pass3(d.data_ptr(), n, state.data_ptr(), sums.data_ptr(), 0, ws, st),
+                      "asp_beta_search_pass3")
+                allreduce(sums)
+                check(lib.asp_beta_search_decide3(state.data_ptr(), sums.data_ptr(), st), "asp_beta_search_decide3")
     host = state.cpu().numpy().tobytes()
     out = _lib.BetaState.from_buffer_copy(host)
     if out.phase != 2:

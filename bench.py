@@ -80,7 +80,7 @@ class ClockSampler(threading.Thread):
                                                    ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
                                                     "sw_power_cap")]
                 self.rows.append(row)
-                self._halt.wait(0.005)
+                self._halt.wait(0.01)
             return
         except Exception:
             pass
@@ -266,6 +266,10 @@ def run_gpu(args):
     clocks.start()
     records = []
     launches0 = _lib.launch_count
+    import gc
+
+    gc.collect()
+    gc.disable()  # no cyclic-GC pause inside the timed region
     torch.cuda.synchronize()
     t_start = torch.cuda.Event(enable_timing=True)
     t_end = torch.cuda.Event(enable_timing=True)
@@ -274,6 +278,7 @@ def run_gpu(args):
         new, beta = one_step(records)
     t_end.record(stream)
     torch.cuda.synchronize()
+    gc.enable()
     launches = _lib.launch_count - launches0
     clock_info = clocks.stop()
     total_ms = t_start.elapsed_time(t_end)

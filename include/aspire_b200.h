@@ -140,6 +140,15 @@ int asp_beta_search_init(asp_beta_state_t* d_state, double beta_prev, double tar
 int asp_beta_search_pass(const double* d_d, int64_t n, asp_beta_state_t* d_state, int fused_decide, void* ws,
                          void* stream);
 int asp_beta_search_decide(asp_beta_state_t* d_state, void* stream);
+/* Three bisection levels per pass over d: the seven candidate betas of a 3-level bisection are equally
+ * spaced, so their weights are E r^k (two exps + seven multiplies per particle).  d_sums[14] receives
+ * {S1_k, S2_k}, k = 1..7 (all-reduce these across ranks, then asp_beta_search_decide3); decisions and the
+ * resulting beta are those of the one-level-per-pass search.  Run the beta = 1 evaluation first with one
+ * asp_beta_search_pass, then asp_beta_search_max_passes3 passes of these. */
+int asp_beta_search_max_passes3(double beta_prev, double tol);
+int asp_beta_search_pass3(const double* d_d, int64_t n, asp_beta_state_t* d_state, double* d_sums, int fused_decide,
+                          void* ws, void* stream);
+int asp_beta_search_decide3(asp_beta_state_t* d_state, const double* d_sums, void* stream);
 
 /* ---- resampling weights + evidence bookkeeping (K4/K5 front end) --------
  * p_i = exp(dbeta d_i - c - log S1) (== exp(lw - lse(lw)), src/aspire/samples.py:1277),
