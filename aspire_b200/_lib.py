@@ -83,6 +83,9 @@ class PcnParams(C.Structure):
         ("d_xi", C.c_void_p),
         ("d_log_u", C.c_void_p),
         ("d_slot", C.c_void_p),
+        ("nu", C.c_double),
+        ("d_scale", C.c_void_p),
+        ("d_gamma", C.c_void_p),
     ]
 
 
@@ -153,6 +156,7 @@ SIGNATURES = {
         C.c_int,
         [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, C.POINTER(PcnParams), _I32, _P, _P],
     ),
+    "asp_tpcn_scales": (C.c_int, [_P, _I64, _I32, C.POINTER(PcnParams), _I32, _P, _P]),
     "asp_pcn_propose_eval_supported": (_I32, [_I32, _I32, _I32]),
     "asp_pcn_propose_eval": (C.c_int, [_P, _I64, _I32, C.POINTER(Density), C.POINTER(Density), C.POINTER(PcnParams), _I32,
                                        _P, _P, _P, _P, _P]),

@@ -51,7 +51,10 @@ __global__ void __launch_bounds__(kBlock) pcn_propose_kernel(const double* __res
             row_load(prm.d_xi + (size_t)move * n * dims, i, dims, lane, vec_xi, xi);
         }
 #pragma unroll
-        for (int k = 0; k < kDPL; ++k) xp[k] = mu[k] + (ca * (x[k] - mu[k]) + rs[k] * xi[k]);
+        const double sc = prm.d_scale ? prm.d_scale[i] : 1.0;  // tpCN: sqrt(s_i)
+#pragma unroll
+        for (int k = 0; k < kDPL; ++k)
+            xp[k] = mu[k] + (ca * (x[k] - mu[k]) + (prm.d_scale ? rs[k] * sc : rs[k]) * xi[k]);
         row_store(xout, i, dims, lane, vec, xp);
     }
 }
@@ -99,7 +102,10 @@ __global__ void __launch_bounds__(kBlock) pcn_accept_kernel(double* __restrict__
         } else {
             log_u = prm.d_log_u[(size_t)move * n + i];
         }
-        const bool acc = log_u < (nw - cur) + (rx2 - rx);
+        // reference-measure term: Gaussian 1/2 (r2' - r2), or Student-t (nu + D)/2 [log1p(r2'/nu) - log1p(r2/nu)]
+        const double dref = prm.nu > 0.0 ? 0.5 * (prm.nu + dims) * (log1p(2.0 * rx2 / prm.nu) - log1p(2.0 * rx / prm.nu))
+                                         : rx2 - rx;
+        const bool acc = log_u < (nw - cur) + dref;
         // every lane of the group has finished reading row i before any lane overwrites it
         __syncwarp();
         if (acc && active) {
@@ -115,6 +121,60 @@ __global__ void __launch_bounds__(kBlock) pcn_accept_kernel(double* __restrict__
     }
     __syncthreads();
     if (threadIdx.x == 0 && s_acc) atomicAdd(&accepts[move], (unsigned long long)s_acc);
+}
+
+// ---- tpCN proposal scales: sqrt((nu + r2(x)) / (2 g)), g ~ Gamma((D + nu)/2, 1) ----
+constexpr uint32_t kGammaBlock0 = 0xFFFFFF00u;
+
+// Marsaglia & Tsang (2000), fp32, counter-based (spec: oracle/pcn.py::gamma_mt_f32)
+__device__ __forceinline__ double gamma_mt(uint64_t seed, uint32_t stream, uint64_t index, float a) {
+    const float d = a - (1.0f / 3.0f);
+    const float c = 1.0f / sqrtf(9.0f * d);
+    for (uint32_t it = 0; it < 64; ++it) {
+        const uint4 r = philox4x32_10((uint32_t)index, (uint32_t)(index >> 32), stream, kGammaBlock0 + it,
+                                      (uint32_t)seed, (uint32_t)(seed >> 32));
+        float z, z1;
+        box_muller_f32(r.x, r.y, z, z1);
+        const float u = u01_f32(r.z);
+        const float t = 1.0f + c * z;
+        const float v = t * t * t;
+        if (t > 0.0f && sfu_log(u) < 0.5f * z * z + d - d * v + d * sfu_log(fmaxf(v, 1e-30f))) return (double)(d * v);
+    }
+    return (double)d;
+}
+
+template <int G>
+__global__ void __launch_bounds__(kBlock) tpcn_scales_kernel(const double* __restrict__ x, int64_t n, int dims,
+                                                             const asp_pcn_params_t prm, int move,
+                                                             double* __restrict__ scale) {
+    const int lane = threadIdx.x % G;
+    double mu[kDPL], isig[kDPL];
+#pragma unroll
+    for (int k = 0; k < kDPL; ++k) {
+        const int j = lane * kDPL + k;
+        mu[k] = j < dims ? __ldg(prm.d_mu + j) : 0.0;
+        isig[k] = j < dims ? 1.0 / __ldg(prm.d_sigma + j) : 0.0;
+    }
+    const bool vec = (dims % kDPL == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    const int64_t groups = ((int64_t)gridDim.x * blockDim.x) / G;
+    const int64_t g0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int64_t warp_first = ((int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31)) / G;
+    const float a = (float)(0.5 * (prm.nu + dims));
+    for (int64_t base = warp_first; base < n; base += groups) {  // warp-uniform trip count
+        const int64_t i_raw = base + (g0 - warp_first);
+        const bool active = i_raw < n;
+        const int64_t i = active ? i_raw : n - 1;
+        double xc[kDPL];
+        row_load(x, i, dims, lane, vec, xc);
+        const double r2 = 2.0 * ref_quad<G>(xc, mu, isig);
+        if (active && lane == 0) {
+            const double g = prm.noise_mode == 0
+                                 ? gamma_mt(prm.seed, prm.stream0 + (uint32_t)move,
+                                            (uint64_t)(prm.d_slot ? prm.d_slot[i] : prm.index0 + i), a)
+                                 : prm.d_gamma[(size_t)move * n + i];
+            scale[i] = sqrt((prm.nu + r2) / (2.0 * g));
+        }
+    }
 }
 
 // ---- K1: standalone log-density ----
@@ -300,6 +360,7 @@ int asp_pcn_sweep(const double* d_x, const double* d_log_l, const double* d_log_
     ASP_REQUIRE(params->d_mu && params->d_sigma, "reference measure missing");
     ASP_REQUIRE(params->noise_mode == 0 || (params->d_xi && params->d_log_u), "noise arrays missing");
     ASP_REQUIRE(d_x != d_x_out || !d_idx, "in-place sweep cannot gather");
+    ASP_REQUIRE(!(params->nu > 0.0), "the fused sweep is pCN only: tpCN (nu > 0) runs through asp_tpcn_scales + the unfused pair");
     int rc;
     if ((rc = check_density(like, dims, "likelihood"))) return rc;
     if ((rc = check_density(prior, dims, "prior"))) return rc;
@@ -339,6 +400,21 @@ int asp_pcn_sweep(const double* d_x, const double* d_log_l, const double* d_log_
     }
     if (rc) { set_error("asp_pcn_sweep: unsupported density combination"); return rc; }
     return check_launch("asp_pcn_sweep");
+}
+
+int asp_tpcn_scales(const double* d_x, int64_t n, int32_t dims, const asp_pcn_params_t* params, int32_t move,
+                    double* d_scale, void* stream) {
+    ASP_DEVICE_OR_RETURN();
+    ASP_REQUIRE(d_x && params && d_scale, "null pointer");
+    ASP_REQUIRE(n > 0 && dims > 0 && dims <= 32 * kDPL, "bad sizes");
+    ASP_REQUIRE(params->nu > 0.0, "nu must be positive");
+    ASP_REQUIRE(params->d_mu && params->d_sigma, "reference measure missing");
+    ASP_REQUIRE(params->noise_mode == 0 || params->d_gamma, "gamma variates missing");
+    const int g = group_size_for(dims);
+    const int grid = grid_for(n * g, 1);
+    ASP_DISPATCH_G(g, (tpcn_scales_kernel<G><<<grid, kBlock, 0, (cudaStream_t)stream>>>(d_x, n, dims, *params, move,
+                                                                                       d_scale)));
+    return check_launch("asp_tpcn_scales");
 }
 
 int asp_pcn_propose(const double* d_x, int64_t n, int32_t dims, const asp_pcn_params_t* params, int32_t move,

@@ -247,6 +247,7 @@ int asp_pcn_propose_eval(const double* d_x, int64_t n, int32_t dims, const asp_d
     ASP_REQUIRE(params->d_mu && params->d_sigma, "reference measure missing");
     ASP_REQUIRE(params->rho > 0.0 && params->rho <= 1.0, "rho must be in (0, 1]");
     ASP_REQUIRE(params->noise_mode == 0 || params->d_xi, "noise array missing");
+    ASP_REQUIRE(!(params->nu > 0.0), "asp_pcn_propose_eval is pCN only (tpCN: asp_tpcn_scales + the unfused pair)");
     ASP_REQUIRE(like->kind != ASP_DENSITY_GMM || (like->p0 && like->p1 && like->p2 && like->n_comp >= 1 &&
                                                   like->n_comp <= 32), "bad mixture parameters");
     ASP_REQUIRE(((reinterpret_cast<uintptr_t>(d_x) | reinterpret_cast<uintptr_t>(d_x_prop) |

@@ -331,7 +331,7 @@ def moments_to_mu_sigma(m: torch.Tensor, dims: int):
 
 
 def make_pcn_params(beta, rho, mu, sigma, n_moves, seed=0, stream0=0, index0=0, xi=None, log_u=None, slot=None,
-                    total_accepts_only=False):
+                    total_accepts_only=False, nu: float = 0.0, gamma=None):
     mu, sigma = _f64(mu, "mu"), _f64(sigma, "sigma")
     prm = _lib.PcnParams()
     prm.beta, prm.rho = float(beta), float(rho)
@@ -345,7 +345,10 @@ def make_pcn_params(beta, rho, mu, sigma, n_moves, seed=0, stream0=0, index0=0, 
     prm.d_xi = None if xi is None else _f64(xi, "xi").data_ptr()
     prm.d_log_u = None if log_u is None else _f64(log_u, "log_u").data_ptr()
     prm.d_slot = None if slot is None else _i64(slot, "slot").data_ptr()
-    prm._keep = (mu, sigma, xi, log_u, slot)  # keep the tensors alive
+    prm.nu = float(nu)  # > 0: tpCN (Student-t reference measure), unfused moves only
+    prm.d_scale = None
+    prm.d_gamma = None if gamma is None else _f64(gamma, "gamma").data_ptr()
+    prm._keep = (mu, sigma, xi, log_u, slot, gamma)  # keep the tensors alive
     return prm
 
 
@@ -364,6 +367,18 @@ def pcn_sweep(x, log_l, log_p, log_q, idx, like, prior, q, prm, out=None):
                                     C.byref(prm), out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
                                     out[3].data_ptr(), accepts.data_ptr(), _stream()), "asp_pcn_sweep")
     return (*out, accepts[:1] if prm.reserved else accepts[:prm.n_moves])
+
+
+def tpcn_scales(x, prm, move: int) -> torch.Tensor:
+    """tpCN: per-particle proposal scale sqrt(s_i) of move ``move`` (``oracle/pcn.py::tpcn_scale``); the
+    result is attached to ``prm`` (``d_scale``) for the following ``pcn_propose``."""
+    x = _f64(x, "x")
+    sc = torch.empty(x.shape[0], dtype=torch.float64, device=x.device)
+    check(_lib.load().asp_tpcn_scales(x.data_ptr(), x.shape[0], x.shape[1], C.byref(prm), move, sc.data_ptr(), _stream()),
+          "asp_tpcn_scales")
+    prm.d_scale = sc.data_ptr()
+    prm._scale = sc  # keep alive
+    return sc
 
 
 def pcn_propose(x, prm, move: int) -> torch.Tensor:

@@ -371,9 +371,11 @@ class SMCSampler(Sampler):
         kw.setdefault("rho", 0.5)
         kw.setdefault("adapt_rho", True)
         kw.setdefault("moment_particles", 1 << 22)
-        if kw["step_fn"] != "pcn":
-            raise NotImplementedError(
-                f"step_fn={kw['step_fn']!r}: only the pCN step is built (tpCN is scope row 8f-2 of SURVEY.md)")
+        if kw["step_fn"] not in ("pcn", "tpcn"):
+            raise ValueError(f"step_fn={kw['step_fn']!r}: expected 'pcn' or 'tpcn'")
+        # 'pcn' (default here) runs the fused sweep; 'tpcn' (the reference's default, smc/minipcn.py:48) fits a
+        # Student-t reference measure by EM and runs unfused moves (asp_tpcn_scales + propose / accept)
+        self.step_fn = kw["step_fn"]
         self.sampler_kwargs = kw
         self.rho = float(kw["rho"])
 
@@ -401,17 +403,25 @@ class SMCSampler(Sampler):
             mom = ops.weighted_moments(particles.x[:m_use])
         mu, sigma = ops.moments_to_mu_sigma(mom, dims)
         sigma = torch.clamp_min(sigma, 1e-150)
+        tpcn = getattr(self, "step_fn", "pcn") == "tpcn"
+        nu = 0.0
+        if tpcn:  # Student-t reference measure t_nu(mu, diag sigma^2) fitted to (a sample of) the ensemble
+            rows = particles.x[:min(m_use, 1 << 20)] if idx is None else particles.x[idx[:min(m_use, 1 << 20)]]
+            mu, sigma, nu = fit_student_t_diag(rows, mu, sigma)
+            self.history.__dict__.setdefault("tpcn_nu", []).append(nu)
         if mark:
             mark("moments")
         if self.rng.is_host:  # parity mode: noise drawn on the host in a fixed order, then uploaded
             xi = torch.from_numpy(self.rng.rng.standard_normal((n_moves, n, dims))).to(self.device)
             log_u = torch.from_numpy(np.log(1.0 - self.rng.rng.random((n_moves, n)))).to(self.device)
-            prm = ops.make_pcn_params(beta, self.rho, mu, sigma, n_moves, xi=xi, log_u=log_u)
+            gam = (torch.from_numpy(self.rng.rng.gamma(0.5 * (dims + nu), 1.0, (n_moves, n))).to(self.device)
+                   if tpcn else None)
+            prm = ops.make_pcn_params(beta, self.rho, mu, sigma, n_moves, xi=xi, log_u=log_u, nu=nu, gamma=gam)
         else:
             prm = ops.make_pcn_params(beta, self.rho, mu, sigma, n_moves, seed=self.rng.seed,
                                       stream0=self.rng.next_stream(n_moves), index0=getattr(self, "index0", 0),
-                                      total_accepts_only=True)
-        if self.fused:
+                                      total_accepts_only=not tpcn, nu=nu)
+        if self.fused and not tpcn:
             x, ll, lp, lq, accepts = ops.pcn_sweep(particles.x, particles.log_likelihood, particles.log_prior,
                                                    particles.log_q, idx, self._log_likelihood, self._log_prior,
                                                    self.prior_flow.density, prm, out=out)
@@ -428,7 +438,7 @@ class SMCSampler(Sampler):
             accepts = torch.zeros(max(n_moves, 1), dtype=torch.int64, device=self.device)
             # built-in prior / likelihood with a proposal that only offers log_prob (a flow): one pass proposes
             # and evaluates both densities, the flow adds log q(x'), a scalar kernel accepts (csrc/pcn_eval.cu)
-            semi = (isinstance(self._log_likelihood, Density) and isinstance(self._log_prior, Density)
+            semi = (not tpcn and isinstance(self._log_likelihood, Density) and isinstance(self._log_prior, Density)
                     and self.rho < 1.0 and x.data_ptr() % 16 == 0
                     and ops.pcn_propose_eval_supported(dims, self._log_likelihood, self._log_prior))
             for t in range(n_moves if semi else 0):
@@ -437,6 +447,8 @@ class SMCSampler(Sampler):
                 ops.pcn_accept_scalar(x, ll, lp, lq, xp, ll2, lp2, lq2, dr, prm, t, accepts)
                 self.n_likelihood_evaluations += n
             for t in range(0 if semi else n_moves):
+                if tpcn:
+                    ops.tpcn_scales(x, prm, t)  # sqrt(s_i) of this move, attached to prm
                 xp = ops.pcn_propose(x, prm, t)
                 prop = SMCSamples(xp, beta=beta, device=self.device, parameters=self.parameters)
                 lq2 = torch.as_tensor(self.prior_flow.log_prob(xp), dtype=torch.float64, device=self.device).contiguous()
@@ -457,6 +469,41 @@ class SMCSampler(Sampler):
         if bool(torch.isnan(lq).any()):
             raise ValueError("Log proposal contains NaN values")  # smc/minipcn.py:133-134
         return out
+
+
+def fit_student_t_diag(x: torch.Tensor, mu0: torch.Tensor, sigma0: torch.Tensor, n_iter: int = 30, nu0: float = 10.0,
+                       nu_min: float = 1.0, nu_max: float = 1e6):
+    """EM fit of t_nu(mu, diag sigma^2) on the device rows ``x`` (spec: ``oracle/pcn.py::fit_student_t_diag``);
+    the reductions run on the GPU, the scalar nu equation is solved on the host.  -> (mu, sigma, nu)"""
+    from scipy.special import digamma
+
+    n, d = x.shape
+    mu, sigma, nu = mu0.clone(), sigma0.clone(), float(nu0)
+    for _ in range(n_iter):
+        z = (x - mu) / sigma
+        r2 = (z * z).sum(dim=1)
+        w = (nu + d) / (nu + r2)
+        mu = (w[:, None] * x).sum(dim=0) / w.sum()
+        sigma = torch.sqrt((w[:, None] * (x - mu) ** 2).sum(dim=0) / n)
+        const = 1.0 + float((torch.log(w) - w).mean()) + float(digamma(0.5 * (nu + d))) - math.log(0.5 * (nu + d))
+
+        def f(v):
+            return -float(digamma(0.5 * v)) + math.log(0.5 * v) + const
+
+        lo, hi = nu_min, nu_max
+        if f(hi) > 0:
+            nu = hi
+        elif f(lo) < 0:
+            nu = lo
+        else:
+            for _ in range(60):
+                mid = math.sqrt(lo * hi)
+                if f(mid) > 0:
+                    lo = mid
+                else:
+                    hi = mid
+            nu = math.sqrt(lo * hi)
+    return mu.contiguous(), torch.clamp_min(sigma, 1e-150).contiguous(), float(nu)
 
 
 class MiniPCNSMC(SMCSampler):

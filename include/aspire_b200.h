@@ -243,6 +243,12 @@ typedef struct asp_pcn_params {
     const double* d_log_u;/* [n_moves, n] log-uniforms   (noise_mode 1)         */
     const int64_t* d_slot;/* optional per-particle Philox counter (global output
                              slot); NULL: index0 + i                            */
+    /* tpCN (Student-t preconditioned CN, the reference's default step_fn): unfused moves only */
+    double nu;            /* 0: pCN (Gaussian reference); > 0: degrees of freedom of the
+                             Student-t reference t_nu(mu, diag sigma^2)          */
+    const double* d_scale;/* [n] per-particle proposal scale sqrt(s_i) of the current
+                             move (written by asp_tpcn_scales); NULL: 1          */
+    const double* d_gamma;/* [n_moves, n] Gamma((dims + nu)/2, 1) variates (noise_mode 1) */
 } asp_pcn_params_t;
 
 /* Fused sweep: particle i starts from row d_idx[i] of the inputs (d_idx NULL
@@ -258,6 +264,12 @@ int asp_pcn_sweep(const double* d_x, const double* d_log_l, const double* d_log_
 /* Unfused halves for user-supplied Python callables: propose x' for move
  * `move`, then (after the caller evaluated the three logs at x') accept/reject
  * in place. */
+/* tpCN: sqrt(s_i) with s_i = (nu + r2(x_i)) / (2 g_i), g_i ~ Gamma((dims + nu)/2, 1) drawn in-kernel
+ * (Marsaglia-Tsang on Philox, noise_mode 0) or taken from params->d_gamma (noise_mode 1).  Step spec:
+ * oracle/pcn.py::tpcn_sweep.  Pass the result as params->d_scale to asp_pcn_propose; asp_pcn_accept then
+ * uses the Student-t reference term when params->nu > 0. */
+int asp_tpcn_scales(const double* d_x, int64_t n, int32_t dims, const asp_pcn_params_t* params, int32_t move,
+                    double* d_scale, void* stream);
 int asp_pcn_propose(const double* d_x, int64_t n, int32_t dims, const asp_pcn_params_t* params, int32_t move,
                     double* d_x_prop, void* stream);
 int asp_pcn_accept(double* d_x, double* d_log_l, double* d_log_p, double* d_log_q, const double* d_x_prop,

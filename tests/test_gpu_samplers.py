@@ -263,8 +263,8 @@ def test_sampler_argument_errors(cuda):
         s.sample(100, target_efficiency=1.5)                # :96-98
     with pytest.raises(ValueError):
         s.sample(100, max_beta_step=1.0)                    # :364-366
-    with pytest.raises(NotImplementedError):
-        s.sample(100, sampler_kwargs=dict(step_fn="tpcn"))  # scope row 8f-2
+    with pytest.raises(ValueError):
+        s.sample(100, sampler_kwargs=dict(step_fn="hmc"))   # only 'pcn' and 'tpcn' exist
     # fixed schedule (adaptive=False) runs exactly n_steps trips
     s.sample(500, adaptive=False, n_steps=4, sampler_kwargs=dict(n_steps=2), store_sample_history=False)
     assert s.history.beta == [0.25, 0.5, 0.75, 1.0]
@@ -389,3 +389,37 @@ def test_semi_fused_move_equals_unfused_and_fused(cuda, name, dims):
     np.testing.assert_allclose(xs, fused[0].cpu().numpy(), rtol=1e-12, atol=1e-12)
     np.testing.assert_allclose(ls, fused[1].cpu().numpy(), rtol=1e-11, atol=1e-10)
     assert 0 < as_.sum() < moves * n
+
+
+def test_smc_with_tpcn_step(cuda):
+    """step_fn='tpcn' (the reference's default kernel): EM fit of the Student-t reference on the device matches
+    the oracle's, and the sampler recovers the analytic posterior and evidence of the quickstart problem."""
+    import torch
+
+    from aspire_b200 import ops
+    from aspire_b200 import targets as tg
+    from aspire_b200.flows import DiagGaussianFlow
+    from aspire_b200.rng import PhiloxRNG
+    from aspire_b200.samplers import MiniPCNSMC
+    from aspire_b200.samplers.smc import fit_student_t_diag
+    from oracle import pcn as opcn
+
+    rng = np.random.default_rng(2)
+    xs = 0.3 + np.array([0.5, 1.0, 2.0]) * rng.standard_t(4.0, size=(60000, 3))
+    xt = torch.as_tensor(xs, device=cuda)
+    mu, sg, nu = fit_student_t_diag(xt, xt.mean(dim=0), xt.std(dim=0, unbiased=False))
+    mu_r, sg_r, nu_r = opcn.fit_student_t_diag(xs)
+    np.testing.assert_allclose(mu.cpu().numpy(), mu_r, rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(sg.cpu().numpy(), sg_r, rtol=1e-9)
+    assert nu == pytest.approx(nu_r, rel=1e-6) and 3.0 < nu < 5.5
+
+    dims = 4
+    prob = tg.quickstart_problem(dims)
+    flow = DiagGaussianFlow(dims, device=cuda, mean=np.zeros(dims), sigma=np.full(dims, 1.5), rng=PhiloxRNG(21))
+    s = MiniPCNSMC(prob["like"], prob["prior"], dims, flow, rng=PhiloxRNG(22))
+    out = s.sample(60000, sampler_kwargs=dict(n_steps=8, step_fn="tpcn"), store_sample_history=False)
+    x = out.x.cpu().numpy()
+    assert np.abs(x.mean(axis=0)).max() < 0.02
+    np.testing.assert_allclose(x.var(axis=0), 0.5, rtol=0.05)
+    assert out.log_evidence == pytest.approx(2.0 * math.log(math.pi), abs=0.05)  # C1: logZ = (D/2) ln pi
+    assert len(s.history.tpcn_nu) == len(s.history.beta) and all(v >= 1.0 for v in s.history.tpcn_nu)
