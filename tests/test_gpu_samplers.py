@@ -405,7 +405,7 @@ def test_smc_with_tpcn_step(cuda):
     from oracle import pcn as opcn
 
     rng = np.random.default_rng(2)
-    xs = 0.3 + np.array([0.5, 1.0, 2.0]) * rng.standard_t(4.0, size=(60000, 3))
+    xs = 0.3 + np.array([0.5, 1.0, 2.0]) * rng.standard_normal((60000, 3)) / np.sqrt(rng.chisquare(4.0, 60000) / 4.0)[:, None]
     xt = torch.as_tensor(xs, device=cuda)
     mu, sg, nu = fit_student_t_diag(xt, xt.mean(dim=0), xt.std(dim=0, unbiased=False))
     mu_r, sg_r, nu_r = opcn.fit_student_t_diag(xs)

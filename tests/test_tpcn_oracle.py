@@ -34,7 +34,8 @@ def test_gamma_sampler_and_em_fit():
     np.testing.assert_array_equal(a, pcn.gamma_mt_f32(5, 3, np.arange(0, 100), 7.5)[50:60])
     rng = np.random.default_rng(1)
     scale = np.array([0.5, 1.0, 2.0, 1.0, 0.7, 3.0])
-    x = 1.5 + scale * rng.standard_t(5.0, size=(100000, 6))
+    # multivariate t: one chi-square per row shared by all dimensions
+    x = 1.5 + scale * rng.standard_normal((100000, 6)) / np.sqrt(rng.chisquare(5.0, 100000) / 5.0)[:, None]
     mu, sigma, nu = pcn.fit_student_t_diag(x)
     np.testing.assert_allclose(mu, 1.5, atol=0.03)
     np.testing.assert_allclose(sigma, scale, rtol=0.03)
