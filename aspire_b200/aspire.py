@@ -76,6 +76,14 @@ class Aspire:
     def sampler(self):
         return self._sampler
 
+    def config_dict(self, **kwargs) -> dict:
+        """Subset of ``Aspire.config_dict`` (aspire.py:820-860) that concerns this path."""
+        cfg = dict(dims=self.dims, parameters=self.parameters, device=str(self.device), eps=self.eps,
+                   flow_backend=self.flow_backend, flow_kwargs=dict(self.flow_kwargs))
+        if self._sampler is not None:
+            cfg["sampler_config"] = self._sampler.config_dict(**kwargs)
+        return cfg
+
     @property
     def n_likelihood_evaluations(self):
         return None if self._sampler is None else self._sampler.n_likelihood_evaluations
@@ -107,7 +115,14 @@ class Aspire:
             return ImportanceSampler
         if sampler_type in ("smc", "minipcn_smc", "minipcn"):
             return MiniPCNSMC
-        raise ValueError(f"Unknown sampler type: {sampler_type}. aspire_b200 builds 'importance' and 'smc'.")
+        # other names resolve through the same entry-point group as the reference (aspire.py:293-304)
+        from importlib.metadata import entry_points
+
+        eps = {ep.name.lower(): ep for ep in entry_points(group="aspire.samplers")}
+        if sampler_type.lower() in eps:
+            return eps[sampler_type.lower()].load()
+        raise ValueError(f"Unknown sampler type: {sampler_type}. aspire_b200 builds 'importance' and 'smc'; "
+                         f"entry points in 'aspire.samplers': {sorted(eps)}")
 
     def init_sampler(self, sampler_type: str, preconditioning=None, preconditioning_kwargs=None, **kwargs):
         if preconditioning not in (None, "default", "identity"):

@@ -242,7 +242,7 @@ __device__ __forceinline__ void beta_decide3(asp_beta_state_t* st, const double*
 
 __global__ void beta_decide3_kernel(asp_beta_state_t* st, const double* sums) { beta_decide3(st, sums); }
 
-__global__ void __launch_bounds__(kBlock) beta_pass3_kernel(const double* __restrict__ d, int64_t n,
+__global__ void __launch_bounds__(kBlock, 2) beta_pass3_kernel(const double* __restrict__ d, int64_t n,
                                                             asp_beta_state_t* st, double* __restrict__ sums,
                                                             int fused_decide, ReduceWs* ws) {
     __shared__ double smem[2 * kBetaCand * 32];

@@ -363,6 +363,8 @@ def run_bench(args, rank, world, dev, metric, unit, workload_config, bytes_per_p
             phase_ms[name] += e0.elapsed_time(e1) / len(records)
     pm = torch.tensor([phase_ms[k] for k in phases], dtype=torch.float64, device=dev)
     per_rank = comm.all_gather(pm).cpu().tolist()  # [rank][phase]: imbalance shows up here
+    sm = torch.tensor([evs[0][1].elapsed_time(evs[-1][1]) for evs in records], dtype=torch.float64, device=dev)
+    step_ms_per_rank = comm.all_gather(sm).cpu().tolist()  # [rank][step]: a straggling step shows up here
     comm.all_reduce_max(pm)
     phase_ms = {k: float(v) for k, v in zip(phases, pm)}
     e2e = None
@@ -391,7 +393,8 @@ def run_bench(args, rank, world, dev, metric, unit, workload_config, bytes_per_p
             "step_roofline": {"achieved": step_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s per GPU",
                               "frac": step_ach / peaks["hbm_gbs"]},
             "cpu_baseline": None, "phase_ms": phase_ms,
-            "phase_ms_per_rank": [[round(v, 3) for v in row] for row in per_rank], "beta_after_step": rec.beta, "acceptance": rec.acceptance,
+            "phase_ms_per_rank": [[round(v, 3) for v in row] for row in per_rank],
+            "step_ms_per_rank": [[round(v, 2) for v in row] for row in step_ms_per_rank], "beta_after_step": rec.beta, "acceptance": rec.acceptance,
             "n_local_out": rec.n_local_out,
         }
         print(json.dumps(line))
