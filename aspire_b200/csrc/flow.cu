@@ -267,22 +267,30 @@ __device__ __forceinline__ bool coupling_layer(float (&z)[D], float& ladj, int l
     phase ^= 1;
     tc_fence_after();
     // ---- epilogue 3: columns [0, HALF) = shift, [HALF, D) = raw log-scale ----
+    auto update = [&](int j, float sh_acc, float raw_acc) {
+        const float shift = sh_acc + b1[128 + j];
+        const float r = raw_acc + b1[128 + HALF + j];
+        const float log_s = __fdividef(r, 1.0f + fabsf(r) * (1.0f / kFlowLimit));
+        ladj += log_s;
+        // z_b is the half NOT fed to the conditioner
+        float& zb = odd ? z[j] : z[HALF + j];
+        zb = INVERSE ? (zb - shift) * __expf(-log_s) : fmaf(zb, __expf(log_s), shift);
+    };
+    if constexpr (HALF >= 16) {
 #pragma unroll
-    for (int c = 0; c < HALF / 16; ++c) {
-        float sh[16], raw[16];
-        tmem_ld16(lane_taddr + c * 16, sh);
-        tmem_ld16(lane_taddr + HALF + c * 16, raw);
+        for (int c = 0; c < HALF / 16; ++c) {
+            float sh[16], raw[16];
+            tmem_ld16(lane_taddr + c * 16, sh);
+            tmem_ld16(lane_taddr + HALF + c * 16, raw);
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const int j = c * 16 + k;
-            const float shift = sh[k] + b1[128 + j];
-            const float r = raw[k] + b1[128 + HALF + j];
-            const float log_s = __fdividef(r, 1.0f + fabsf(r) * (1.0f / kFlowLimit));
-            ladj += log_s;
-            // z_b is the half NOT fed to the conditioner
-            float& zb = odd ? z[j] : z[HALF + j];
-            zb = INVERSE ? (zb - shift) * __expf(-log_s) : fmaf(zb, __expf(log_s), shift);
+            for (int k = 0; k < 16; ++k) update(c * 16 + k, sh[k], raw[k]);
         }
+    } else {  // D = 16: both halves sit in one 16-column load
+        static_assert(HALF == 8, "flow kernel: D must be 16, 32 or 64");
+        float v[16];
+        tmem_ld16(lane_taddr, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) update(k, v[k], v[8 + k]);
     }
     return ok;
 }
@@ -417,6 +425,7 @@ extern "C" {
 
 size_t asp_flow_weights_bytes(int32_t dims, int32_t n_layers) {
     switch (dims) {
+        case 16: return (size_t)n_layers * FlowSizes<16>::kLayer;
         case 32: return (size_t)n_layers * FlowSizes<32>::kLayer;
         case 64: return (size_t)n_layers * FlowSizes<64>::kLayer;
         default: return 0;
@@ -439,9 +448,10 @@ static int flow_dispatch(const asp_flow_t* f, const double* d_in, int64_t n, dou
     A.log_det0 = f->log_det0; A.n_layers = f->n_layers; A.error = f->d_error;
     cudaStream_t s = (cudaStream_t)stream;
     switch (f->dims) {
+        case 16: return inverse ? launch_flow<16, true>(A, s) : launch_flow<16, false>(A, s);
         case 32: return inverse ? launch_flow<32, true>(A, s) : launch_flow<32, false>(A, s);
         case 64: return inverse ? launch_flow<64, true>(A, s) : launch_flow<64, false>(A, s);
-        default: set_error("asp_flow: dims must be 32 or 64"); return ASP_ERR_ARG;
+        default: set_error("asp_flow: dims must be 16, 32 or 64"); return ASP_ERR_ARG;
     }
 }
 

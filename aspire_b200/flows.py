@@ -122,8 +122,8 @@ class CouplingFlow(Flow):
     def __init__(self, dims: int, device=None, data_transform=None, dtype=None, n_layers: int = 3, rng=None,
                  seed: int = 0):
         super().__init__(dims, device, data_transform, dtype)
-        if dims not in (32, 64):
-            raise ValueError("CouplingFlow kernels are built for dims in {32, 64}")
+        if dims not in (16, 32, 64):
+            raise ValueError("CouplingFlow kernels are built for dims in {16, 32, 64}")
         self.n_layers = int(n_layers)
         self.rng = as_uniform_source(rng)
         g = torch.Generator().manual_seed(seed)

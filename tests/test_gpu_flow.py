@@ -28,7 +28,7 @@ def _flow(dims, n_layers, cuda, seed=0):
     return f, p
 
 
-@pytest.mark.parametrize("dims,n_layers,n", [(64, 3, 5000), (64, 1, 128), (64, 4, 77), (32, 3, 4097), (32, 2, 1)])
+@pytest.mark.parametrize("dims,n_layers,n", [(64, 3, 5000), (64, 1, 128), (64, 4, 77), (32, 3, 4097), (32, 2, 1), (16, 3, 3001), (16, 2, 130)])
 def test_flow_logprob_matches_spec(cuda, dims, n_layers, n):
     f, p = _flow(dims, n_layers, cuda)
     rng = np.random.default_rng(n)
@@ -48,7 +48,7 @@ def test_flow_logprob_matches_spec(cuda, dims, n_layers, n):
     np.testing.assert_array_equal(f.log_prob(_t(x, cuda)).cpu().numpy(), logq)  # deterministic
 
 
-@pytest.mark.parametrize("dims", [32, 64])
+@pytest.mark.parametrize("dims", [16, 32, 64])
 def test_flow_sample_inverts_logprob(cuda, dims):
     from aspire_b200 import ops
 
