@@ -10,6 +10,7 @@ in-kernel.  Any other object with the same methods works through the unfused pat
 
 from __future__ import annotations
 
+import logging
 import math
 
 import numpy as np
@@ -19,6 +20,8 @@ from . import ops
 from .history import FlowHistory
 from .rng import as_uniform_source
 from .targets import GaussianDensity
+
+logger = logging.getLogger(__name__)
 
 
 class Flow:
@@ -211,29 +214,67 @@ class CouplingFlow(Flow):
             ladj = ladj + log_s.sum(dim=1)
         return -0.5 * (z * z).sum(dim=1) - 0.5 * self.dims * math.log(2 * math.pi) + ladj
 
-    def fit(self, samples, n_epochs: int = 50, lr: float = 1e-3, batch_size: int = 500, **kwargs) -> FlowHistory:
-        """Maximum-likelihood fit (Adam), mirroring ``ZukoFlow.fit`` (flows/torch/flows.py:170-325) in outline."""
+    def fit(self, samples, n_epochs: int = 100, lr: float = 1e-3, batch_size: int = 500,
+            validation_fraction: float = 0.2, clip_grad: float | None = None, lr_annealing: bool = False,
+            patience: int | None = None, **kwargs) -> FlowHistory:
+        """Maximum-likelihood fit with the reference's training protocol (``ZukoFlow.fit``,
+        flows/torch/flows.py:170-325): affine data transform from the samples (mean, unbiased std -
+        ``transforms.py:618-621``), random permutation, train / validation split, Adam, optional gradient
+        clipping, cosine annealing and early stopping, best-validation weights restored at the end.
+        The optimiser is torch autograd over the kernel's own weight tensors (scaffolding: SURVEY 8f-1)."""
         x = samples.x if hasattr(samples, "x") else samples
-        x = torch.as_tensor(x, dtype=torch.float64, device=self.device)
+        x = torch.as_tensor(x, dtype=torch.float64, device=self.device).clone()
+        if bool(torch.isnan(x).any()):
+            bad = torch.isnan(x).any(dim=0).nonzero(as_tuple=True)[0].tolist()
+            raise ValueError(f"Training data contains NaN values in dimensions: {bad}")
+        if not bool(torch.isfinite(x).all()):
+            bad = (~torch.isfinite(x)).any(dim=0).nonzero(as_tuple=True)[0].tolist()
+            raise ValueError(f"Training data contains infinite values in dimensions: {bad}")
         self.mean = x.mean(dim=0)
-        self.std = x.std(dim=0, unbiased=False).clamp_min(1e-12)
+        self.std = x.std(dim=0).clamp_min(1e-12)
+        n = x.shape[0]
+        g = torch.Generator(device="cpu").manual_seed(int(kwargs.get("seed", 0)))
+        x32 = x[torch.randperm(n, generator=g).to(self.device)].float()
+        n_val = int(validation_fraction * n)
+        x_train, x_val = (x32[:-n_val], x32[-n_val:]) if n_val > 0 else (x32, x32[:0])
+        logger.info(f"Training on {x_train.shape[0]} samples, validating on {x_val.shape[0]} samples.")
         params = [p.requires_grad_(True) for layer in self.layers for p in layer.values()]
         opt = torch.optim.Adam(params, lr=lr)
+        sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, n_epochs) if lr_annealing else None
         hist = FlowHistory()
-        x32 = x.float()
-        for _ in range(n_epochs):
-            perm = torch.randperm(x32.shape[0], device=self.device)
-            tot = 0.0
-            for i in range(0, x32.shape[0], batch_size):
-                xb = x32[perm[i:i + batch_size]]
-                loss = -self._torch_forward(xb, self.layers).mean()
+        best_val, best_state, best_epoch = float("inf"), None, 0
+        for epoch in range(n_epochs):
+            perm = torch.randperm(x_train.shape[0], generator=g).to(self.device)
+            tot, nb = 0.0, 0
+            for i in range(0, x_train.shape[0], batch_size):
+                loss = -self._torch_forward(x_train[perm[i:i + batch_size]], self.layers).mean()
                 opt.zero_grad()
                 loss.backward()
+                if clip_grad is not None:
+                    torch.nn.utils.clip_grad_norm_(params, clip_grad)
                 opt.step()
-                tot += float(loss.detach()) * xb.shape[0]
-            hist.training_loss.append(tot / x32.shape[0])
-        for layer in self.layers:
-            for k in layer:
-                layer[k] = layer[k].detach()
+                tot += float(loss.detach())
+                nb += 1
+            if sched is not None:
+                sched.step()
+            hist.training_loss.append(tot / max(nb, 1))
+            val, nv = 0.0, 0
+            with torch.no_grad():
+                for i in range(0, x_val.shape[0], batch_size):
+                    val += float(-self._torch_forward(x_val[i:i + batch_size], self.layers).mean())
+                    nv += 1
+            avg_val = val / nv if nv else hist.training_loss[-1]
+            hist.validation_loss.append(avg_val)
+            if avg_val < best_val:
+                best_val, best_epoch = avg_val, epoch
+                best_state = [{k: v.detach().clone() for k, v in layer.items()} for layer in self.layers]
+            if patience is not None and epoch - best_epoch >= patience:
+                logger.info(f"Early stopping triggered after {patience} epochs")
+                break
+        if best_state is not None:
+            self.layers = best_state
+            logger.info(f"Loaded best model from epoch {best_epoch} with val loss {best_val:.4f}")
+        else:
+            self.layers = [{k: v.detach() for k, v in layer.items()} for layer in self.layers]
         self._struct = None
         return hist
