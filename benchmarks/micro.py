@@ -5,6 +5,7 @@
     python benchmarks/micro.py resample    # C5: exact CDF + ancestor search, N = 1e4 .. 1e9
     python benchmarks/micro.py importance  # C2: importance reweighting, N = 1e6, D = 16
     python benchmarks/micro.py sweep       # K8: fused gather + 10 pCN moves per benchmark problem
+    python benchmarks/micro.py full        # whole sample_posterior(sampler="smc") run through the drop-in API
     python benchmarks/micro.py c4          # C4: mixture SMC step with the tcgen05 flow as proposal (unfused moves)
 
 Each prints JSON lines; times are CUDA events over `--iters` launches after 3 warm-ups, on inputs
@@ -213,9 +214,38 @@ def c4(args):
                       "beta": s.history.beta[-1], "acceptance": s.history.mcmc_acceptance[-1]}))
 
 
+def full(args):
+    """A whole ``Aspire.sample_posterior(sampler="smc")`` run (all tempering steps to beta = 1) through the
+    drop-in API: 32-D Rosenbrock, N particles, 10 pCN moves per step, adaptive beta at efficiency 0.5."""
+    import time
+
+    from aspire_b200.aspire import Aspire
+    from aspire_b200.flows import DiagGaussianFlow
+    from aspire_b200.rng import PhiloxRNG
+
+    dev = torch.device("cuda")
+    n, dims = args.n or 10_000_000, 32
+    prob = tg.rosenbrock_problem(dims, device=dev)
+    flow = DiagGaussianFlow(dims, device=dev, mean=prob["q"].mean_np, sigma=prob["q"].sigma_np, rng=PhiloxRNG(1))
+    a = Aspire(log_likelihood=prob["like"], log_prior=prob["prior"], dims=dims, flow=flow, device="cuda")
+    for rep in range(2):  # the first run warms the allocator and the kernels
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out, hist = a.sample_posterior(n, sampler="smc", return_history=True, rng=PhiloxRNG(2 + rep),
+                                       sampler_kwargs=dict(n_steps=args.moves), store_sample_history=False)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    steps = len(hist.beta)
+    print(json.dumps({"bench": "smc_full_run", "particles": n, "dims": dims, "moves": args.moves, "tempering_steps": steps,
+                      "seconds": dt, "ms_per_step": dt / steps * 1e3, "particle_steps_per_s": n * steps / dt,
+                      "log_evidence": float(out.log_evidence), "log_evidence_error": float(out.log_evidence_error),
+                      "mean_acceptance": float(sum(hist.mcmc_acceptance) / steps),
+                      "likelihood_evaluations": a.n_likelihood_evaluations}))
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["flow", "resample", "importance", "sweep", "c4"])
+    ap.add_argument("what", choices=["flow", "resample", "importance", "sweep", "c4", "full"])
     ap.add_argument("--n", type=int, default=0)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--moves", type=int, default=10)
@@ -223,4 +253,4 @@ if __name__ == "__main__":
     ap.add_argument("--dump", default="")
     a = ap.parse_args()
     ops.device_check()
-    {"flow": flow, "resample": resample, "importance": importance, "sweep": sweep, "c4": c4}[a.what](a)
+    {"flow": flow, "resample": resample, "importance": importance, "sweep": sweep, "c4": c4, "full": full}[a.what](a)
