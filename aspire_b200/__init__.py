@@ -9,3 +9,17 @@ mutation sweep and built-in benchmark log-densities.  See DESIGN.md.
 from ._lib import AspireB200Error  # noqa: F401
 
 __version__ = "0.1.0"
+
+
+def __getattr__(name):
+    """``from aspire_b200 import Aspire, Samples`` like ``from aspire import Aspire, Samples`` (lazy: torch
+    is only imported when the classes are asked for)."""
+    if name == "Aspire":
+        from .aspire import Aspire
+
+        return Aspire
+    if name in ("Samples", "SMCSamples"):
+        from . import samples
+
+        return getattr(samples, name)
+    raise AttributeError(f"module 'aspire_b200' has no attribute {name!r}")

@@ -423,3 +423,17 @@ def test_smc_with_tpcn_step(cuda):
     np.testing.assert_allclose(x.var(axis=0), 0.5, rtol=0.05)
     assert out.log_evidence == pytest.approx(2.0 * math.log(math.pi), abs=0.05)  # C1: logZ = (D/2) ln pi
     assert len(s.history.tpcn_nu) == len(s.history.beta) and all(v >= 1.0 for v in s.history.tpcn_nu)
+
+
+def test_readme_quickstart_example_runs(cuda, capsys):
+    """examples/quickstart.py = the reference README quickstart (README.md:42-77) with torch callables."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("quickstart", os.path.join(os.path.dirname(__file__), "..", "examples",
+                                                                          "quickstart.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.main()
+    out = capsys.readouterr().out
+    z = float(out.split("log evidence")[1].split()[0])
+    assert abs(z - 2 * math.log(math.pi)) < 0.5      # 500 particles: a loose statistical check
