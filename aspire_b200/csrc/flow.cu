@@ -184,12 +184,15 @@ __device__ __forceinline__ void issue_gemm(uint32_t tmem, const unsigned char* a
     umma_commit(bar);
 }
 
+// barrier over the 128 threads of one warpgroup (named barriers 1..; 0 is __syncthreads)
+__device__ __forceinline__ void wg_sync(int wg) { asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory"); }
+
 // One coupling layer for this thread's particle; ODD selects which half conditions which
 // (compile time, so z[] keeps static indices and stays in registers).
 template <int D, bool INVERSE, bool ODD>
 __device__ __forceinline__ bool coupling_layer(float (&z)[D], float& ladj, int layer, const unsigned char* s_w,
-                                               unsigned char* s_a, const float* s_bias, uint64_t* s_bar, uint32_t tmem,
-                                               uint32_t lane_taddr, uint32_t& phase, int tid) {
+                                               unsigned char* s_a, const float* s_bias, uint64_t* mma_bar, uint32_t tmem,
+                                               uint32_t lane_taddr, uint32_t& phase, int tid, int wg) {
     using S = FlowSizes<D>;
     constexpr int HALF = S::kHalf;
     constexpr bool odd = ODD;
@@ -212,12 +215,12 @@ __device__ __forceinline__ bool coupling_layer(float (&z)[D], float& ladj, int l
     }
     fence_proxy_async_smem();
     tc_fence_before();
-    __syncthreads();
+    wg_sync(wg);
     if (tid == 0) {
         tc_fence_after();
-        issue_gemm<S::kKA, kFlowH>(tmem, s_a, w1, &s_bar[1]);
+        issue_gemm<S::kKA, kFlowH>(tmem, s_a, w1, mma_bar);
     }
-    ok &= mbar_wait(&s_bar[1], phase);
+    ok &= mbar_wait(mma_bar, phase);
     phase ^= 1;
     tc_fence_after();
     // ---- epilogue 1 -> A = bf16(relu(acc + b1)); GEMM 2 ----
@@ -235,12 +238,12 @@ __device__ __forceinline__ bool coupling_layer(float (&z)[D], float& ladj, int l
     }
     fence_proxy_async_smem();
     tc_fence_before();
-    __syncthreads();
+    wg_sync(wg);
     if (tid == 0) {
         tc_fence_after();
-        issue_gemm<kFlowH, kFlowH>(tmem, s_a, w2, &s_bar[1]);
+        issue_gemm<kFlowH, kFlowH>(tmem, s_a, w2, mma_bar);
     }
-    ok &= mbar_wait(&s_bar[1], phase);
+    ok &= mbar_wait(mma_bar, phase);
     phase ^= 1;
     tc_fence_after();
     // ---- epilogue 2 -> A = bf16(relu(acc + b2)); GEMM 3 (N = D) ----
@@ -258,12 +261,12 @@ __device__ __forceinline__ bool coupling_layer(float (&z)[D], float& ladj, int l
     }
     fence_proxy_async_smem();
     tc_fence_before();
-    __syncthreads();
+    wg_sync(wg);
     if (tid == 0) {
         tc_fence_after();
-        issue_gemm<kFlowH, D>(tmem, s_a, w3, &s_bar[1]);
+        issue_gemm<kFlowH, D>(tmem, s_a, w3, mma_bar);
     }
-    ok &= mbar_wait(&s_bar[1], phase);
+    ok &= mbar_wait(mma_bar, phase);
     phase ^= 1;
     tc_fence_after();
     // ---- epilogue 3: columns [0, HALF) = shift, [HALF, D) = raw log-scale ----
@@ -295,37 +298,49 @@ __device__ __forceinline__ bool coupling_layer(float (&z)[D], float& ladj, int l
     return ok;
 }
 
+// The tile chain MMA -> wait -> epilogue is serial for the 128 threads that own a tile, so throughput comes from
+// tiles in flight per SM.  D = 64: the weights blob (61 KB) allows two CTAs per SM, so one CTA runs kFlowWG = 3
+// independent warpgroups (own A tile, own 64 TMEM columns, own MMA barrier) over one copy of the weights;
+// D = 32 / 16: three / four single-warpgroup CTAs fit.
+template <int D>
+constexpr int flow_wg() { return D >= 64 ? 3 : 1; }
+template <int D>
+constexpr int flow_ctas_per_sm() { return D >= 64 ? 1 : (D >= 32 ? 3 : 4); }
+
 template <int D, bool INVERSE>
-__global__ void __launch_bounds__(kFlowThreads, 2) flow_kernel(const FlowArgs A) {
+__global__ void __launch_bounds__(kFlowThreads * flow_wg<D>(), flow_ctas_per_sm<D>()) flow_kernel(const FlowArgs A) {
     using S = FlowSizes<D>;
     constexpr int HALF = S::kHalf;
+    constexpr int NWG = flow_wg<D>();
+    constexpr int kTmemAll = NWG == 1 ? 64 : (NWG == 2 ? 128 : 256);  // power of two >= 64 NWG
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* s_w = smem;                                             // weights blob
-    unsigned char* s_a = smem + kFlowMaxLayers * 0 + A.n_layers * S::kLayer;  // A tile (16 KB)
-    float* s_bias = reinterpret_cast<float*>(s_a + kFlowM * kFlowH * 2);
+    unsigned char* s_a_all = smem + A.n_layers * S::kLayer;                // NWG A tiles (16 KB each)
+    float* s_bias = reinterpret_cast<float*>(s_a_all + NWG * kFlowM * kFlowH * 2);
     double* s_mean = reinterpret_cast<double*>(s_bias + A.n_layers * 3 * 64);
     double* s_scale = s_mean + D;
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_scale + D);           // [0]: weights TMA, [1]: MMA
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_scale + D);           // [0]: weights TMA, [1 + wg]: MMA
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 1 + NWG);
 
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int wg = threadIdx.x / kFlowThreads, tid = threadIdx.x % kFlowThreads, warp = tid >> 5;
+    unsigned char* s_a = s_a_all + wg * (kFlowM * kFlowH * 2);
     const int wbytes = A.n_layers * S::kLayer;
-    if (tid == 0) {
+    if (threadIdx.x == 0) {
         mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
+        for (int w = 0; w < NWG; ++w) mbar_init(&s_bar[1 + w], 1);
         fence_mbar_init();
     }
-    if (warp == 0) tmem_alloc(s_tmem, S::kTmemCols);
-    for (int i = tid; i < A.n_layers * 3 * 64; i += kFlowThreads) s_bias[i] = A.bias[i];
-    for (int i = tid; i < D; i += kFlowThreads) {
+    if (threadIdx.x < 32) tmem_alloc(s_tmem, kTmemAll);
+    for (int i = threadIdx.x; i < A.n_layers * 3 * 64; i += blockDim.x) s_bias[i] = A.bias[i];
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {
         s_mean[i] = A.mean[i];
         s_scale[i] = A.inv_std[i];
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *s_tmem;
-    if (tid == 0) {  // weights: one TMA bulk copy per layer blob, all on one mbarrier
+    const uint32_t tmem = *s_tmem + (uint32_t)(wg * S::kTmemCols);  // this warpgroup's accumulator columns
+    if (threadIdx.x == 0) {  // weights: one TMA bulk copy per layer blob, all on one mbarrier
         mbar_expect_tx(&s_bar[0], (uint32_t)wbytes);
         for (int l = 0; l < A.n_layers; ++l)
             tma_bulk_load(s_w + l * S::kLayer, reinterpret_cast<const unsigned char*>(A.weights) + (size_t)l * S::kLayer,
@@ -333,10 +348,11 @@ __global__ void __launch_bounds__(kFlowThreads, 2) flow_kernel(const FlowArgs A)
     }
     bool ok = mbar_wait(&s_bar[0], 0);
     uint32_t phase = 0;
-    const uint32_t lane_taddr = tmem + ((uint32_t)(warp * 32) << 16);
+    uint64_t* mma_bar = &s_bar[1 + wg];
+    const uint32_t lane_taddr = tmem + ((uint32_t)(warp * 32) << 16);  // warp % 4 selects the 32-lane TMEM slab
 
     const int64_t n_tiles = (A.n + kFlowM - 1) / kFlowM;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int64_t tile = (int64_t)blockIdx.x * NWG + wg; tile < n_tiles; tile += (int64_t)gridDim.x * NWG) {
         const int64_t row = tile * kFlowM + tid;
         const bool live = row < A.n;
         float z[D];
@@ -363,9 +379,11 @@ __global__ void __launch_bounds__(kFlowThreads, 2) flow_kernel(const FlowArgs A)
         for (int li = 0; li < A.n_layers; ++li) {
             const int layer = INVERSE ? A.n_layers - 1 - li : li;
             if (layer & 1)
-                ok &= coupling_layer<D, INVERSE, true>(z, ladj, layer, s_w, s_a, s_bias, s_bar, tmem, lane_taddr, phase, tid);
+                ok &= coupling_layer<D, INVERSE, true>(z, ladj, layer, s_w, s_a, s_bias, mma_bar, tmem, lane_taddr, phase,
+                                                       tid, wg);
             else
-                ok &= coupling_layer<D, INVERSE, false>(z, ladj, layer, s_w, s_a, s_bias, s_bar, tmem, lane_taddr, phase, tid);
+                ok &= coupling_layer<D, INVERSE, false>(z, ladj, layer, s_w, s_a, s_bias, mma_bar, tmem, lane_taddr, phase,
+                                                        tid, wg);
         }
         // ---- outputs ----
         if (live) {
@@ -394,13 +412,14 @@ __global__ void __launch_bounds__(kFlowThreads, 2) flow_kernel(const FlowArgs A)
     if (!ok && tid == 0) atomicOr(A.error, 1u);
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, S::kTmemCols);
+    if (threadIdx.x < 32) tmem_dealloc(*s_tmem, kTmemAll);
 }
 
 template <int D>
 static size_t flow_smem_bytes(int n_layers) {
     using S = FlowSizes<D>;
-    return (size_t)n_layers * S::kLayer + kFlowM * kFlowH * 2 + (size_t)n_layers * 3 * 64 * 4 + 2 * D * 8 + 2 * 8 + 16 + 128;
+    return (size_t)n_layers * S::kLayer + (size_t)flow_wg<D>() * kFlowM * kFlowH * 2 + (size_t)n_layers * 3 * 64 * 4 +
+           2 * D * 8 + (1 + flow_wg<D>()) * 8 + 16 + 128;
 }
 
 template <int D, bool INV>
@@ -412,8 +431,11 @@ static int launch_flow(const FlowArgs& A, cudaStream_t s) {
         return ASP_ERR_CUDA;
     }
     const int64_t n_tiles = (A.n + kFlowM - 1) / kFlowM;
-    const int grid = (int)(n_tiles < 2 * kNumSMs ? n_tiles : 2 * kNumSMs);
-    flow_kernel<D, INV><<<grid, kFlowThreads, smem, s>>>(A);
+    constexpr int NWG = flow_wg<D>();
+    constexpr int64_t cap = (int64_t)flow_ctas_per_sm<D>() * kNumSMs;
+    const int64_t need = (n_tiles + NWG - 1) / NWG;
+    const int grid = (int)(need < cap ? need : cap);
+    flow_kernel<D, INV><<<grid, kFlowThreads * NWG, smem, s>>>(A);
     return check_launch("asp_flow");
 }
 
