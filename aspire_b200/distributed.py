@@ -229,6 +229,20 @@ class ShardedSMC:
         return Shard(x, ll, lp, lq, slot), rec
 
 
+def run_tempering(engine: "ShardedSMC", shard: "Shard", beta: float = 0.0, max_steps: int = 10_000):
+    """The tempering loop (reference ``smc/base.py:401-454``) over sharded particles: ``ShardedSMC.step`` until
+    beta reaches 1.  Every rank takes the same decisions (they all see the all-reduced sums), so no rank can
+    leave the loop early.  -> (final shard, [StepRecord], log evidence, log evidence error)"""
+    records = []
+    while beta < 1.0 and len(records) < max_steps:
+        shard, rec = engine.step(shard, beta)
+        beta = rec.beta
+        records.append(rec)
+    log_z = float(sum(r.log_norm_ratio for r in records))
+    err = math.sqrt(float(sum(r.log_norm_ratio_var for r in records)))
+    return shard, records, log_z, err
+
+
 def _host_buffer_leg(args, comm, engine, shard0, n_total, dev, unit):
     """The sharded step with HOST buffers: every rank uploads its slice from pinned host memory over its own
     PCIe link, runs ``ShardedSMC.step`` and downloads its offspring; device-timed, max over ranks."""
