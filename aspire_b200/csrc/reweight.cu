@@ -259,7 +259,8 @@ __global__ void __launch_bounds__(kBlock, 2) beta_pass3_kernel(const double* __r
     }
     auto accumulate = [&](double x) {
         const double t = x - d_max;  // <= 0: every factor below is in [0, 1]
-        const double e0 = exp(db0 * t), r = exp(h * t);
+        // db0 == 0 on the first passes: 0 * (-inf) would be NaN for a particle of zero weight (d = -inf)
+        const double e0 = db0 > 0.0 ? exp(db0 * t) : 1.0, r = exp(h * t);
         double e = e0;
 #pragma unroll
         for (int k = 0; k < kBetaCand; ++k) {
