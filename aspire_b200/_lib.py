@@ -45,6 +45,15 @@ class Density(C.Structure):
     ]
 
 
+MAX_PEERS = 8
+PEER_BOX_BYTES = 2 * MAX_PEERS * 16 * 8 + 64
+
+
+class PeerDesc(C.Structure):
+    """``asp_peer_t``: the ranks' mailboxes as addressable from this device."""
+    _fields_ = [("box", C.c_void_p * MAX_PEERS), ("rank", C.c_int32), ("world", C.c_int32)]
+
+
 class BetaState(C.Structure):
     _fields_ = [
         ("beta_prev", C.c_double),
@@ -128,6 +137,7 @@ SIGNATURES = {
     "asp_beta_search_max_passes3": (C.c_int, [_D, _D]),
     "asp_beta_search_pass3": (C.c_int, [_P, _I64, _P, _P, C.c_int, _P, _P]),
     "asp_beta_search_decide3": (C.c_int, [_P, _P, _P]),
+    "asp_beta_search_pass_p2p": (C.c_int, [_P, _I64, _P, C.c_int, _P, _P, _P, _P]),
     "asp_smc_weights": (C.c_int, [_P, _I64, _D, _D, _D, _D, _P, _P, _P, _P, _P]),
     "asp_cdf_workspace_bytes": (C.c_size_t, [_I64]),
     "asp_cdf_tile_stats": (C.c_int, [_P, _I64, _P, _P]),

@@ -113,6 +113,57 @@ __global__ void __launch_bounds__(kBlock) ess_sums_kernel(const double* __restri
 }
 
 // ---------------------------------------------------------------------------
+// All-reduce (sum) of a few doubles across the GPUs of one box INSIDE the reducing kernel, over peer memory
+// (NVLink loads / stores into mailboxes the ranks exchanged by CUDA IPC): the last block of every rank's
+// pass publishes its partial sums to every mailbox, waits for the others and adds them in rank order, so all
+// ranks hold bit-identical totals and take the same bisection decisions - no NCCL call, no extra launch, no
+// host round trip between a pass and its decision.  Mailbox layout: [parity][writer rank][16 doubles],
+// value 15 = epoch flag; two parities because a rank may start pass e+1 while a slow peer still reads pass e
+// (it cannot reach e+2 before every peer has finished reading e).  The epoch is a device-side counter kept
+// behind the rank's own mailbox and advanced by the kernel itself, so passes that return early (search
+// already converged - the same passes on every rank, their states being bit-identical) do not consume epochs.
+// ---------------------------------------------------------------------------
+constexpr int kBoxStride = 16;
+template <int NV>
+__device__ __forceinline__ bool p2p_allreduce_sum(double (&v)[NV], const asp_peer_t& P) {
+    static_assert(NV < kBoxStride, "mailbox slot too small");
+    double* counter = P.box[P.rank] + 2 * ASP_MAX_PEERS * kBoxStride;
+    const double flag = *counter + 1.0;
+    *counter = flag;
+    const size_t par = (size_t)((long long)flag & 1) * ASP_MAX_PEERS * kBoxStride;
+    for (int p = 0; p < P.world; ++p) {
+        volatile double* slot = P.box[p] + par + (size_t)P.rank * kBoxStride;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) slot[k] = v[k];
+    }
+    __threadfence_system();
+    for (int p = 0; p < P.world; ++p) P.box[p][par + (size_t)P.rank * kBoxStride + 15] = flag;
+    __threadfence_system();
+    bool ok = true;
+    double acc[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) acc[k] = 0.0;
+    for (int w = 0; w < P.world; ++w) {
+        volatile double* slot = P.box[P.rank] + par + (size_t)w * kBoxStride;
+        unsigned long long t0 = 0, t1;
+        while (slot[15] != flag) {  // bounded: a peer that has not arrived within 5 s is reported, never waited for
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (!t0) t0 = t1;
+            if (t1 - t0 > 5000000000ull) {
+                ok = false;
+                break;
+            }
+        }
+        __threadfence_system();
+#pragma unroll
+        for (int k = 0; k < NV; ++k) acc[k] += slot[k];
+    }
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = acc[k];
+    return ok;
+}
+
+// ---------------------------------------------------------------------------
 // device-driven bisection
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void beta_decide(asp_beta_state_t* st) {
@@ -168,7 +219,8 @@ __global__ void beta_init_kernel(asp_beta_state_t* st, double beta_prev, double 
 __global__ void beta_decide_kernel(asp_beta_state_t* st) { beta_decide(st); }
 
 __global__ void __launch_bounds__(kBlock) beta_pass_kernel(const double* __restrict__ d, int64_t n,
-                                                           asp_beta_state_t* st, int fused_decide, ReduceWs* ws) {
+                                                           asp_beta_state_t* st, int fused_decide, ReduceWs* ws,
+                                                           const asp_peer_t P) {
     __shared__ double smem[2 * 32];
     if (st->phase == 2) return;  // uniform across the grid: phase only changes in the last block's epilogue
     const double db = st->beta_try - st->beta_prev;
@@ -194,6 +246,7 @@ __global__ void __launch_bounds__(kBlock) beta_pass_kernel(const double* __restr
     }
     const int ops[2] = {OP_SUM, OP_SUM};
     grid_reduce<2>(v, ops, ws, smem, [&](double(&r)[2]) {
+        if (P.world > 1 && !p2p_allreduce_sum<2>(r, P)) st->reserved = -1;
         st->s1 = r[0];
         st->s2 = r[1];
         if (fused_decide) beta_decide(st);
@@ -244,7 +297,7 @@ __global__ void beta_decide3_kernel(asp_beta_state_t* st, const double* sums) { 
 
 __global__ void __launch_bounds__(kBlock, 2) beta_pass3_kernel(const double* __restrict__ d, int64_t n,
                                                             asp_beta_state_t* st, double* __restrict__ sums,
-                                                            int fused_decide, ReduceWs* ws) {
+                                                            int fused_decide, ReduceWs* ws, const asp_peer_t P) {
     __shared__ double smem[2 * kBetaCand * 32];
     if (st->phase != 1) return;  // uniform across the grid
     const double d_max = st->d_max;
@@ -280,6 +333,7 @@ __global__ void __launch_bounds__(kBlock, 2) beta_pass3_kernel(const double* __r
     }
     for (; i < n; i += stride) accumulate(d[i]);
     grid_reduce<2 * kBetaCand>(v, ops, ws, smem, [&](double(&r)[2 * kBetaCand]) {
+        if (P.world > 1 && !p2p_allreduce_sum<2 * kBetaCand>(r, P)) st->reserved = -1;
 #pragma unroll
         for (int k = 0; k < 2 * kBetaCand; ++k) sums[k] = r[k];
         if (fused_decide) beta_decide3(st, sums);
@@ -474,9 +528,33 @@ int asp_beta_search_pass(const double* d_d, int64_t n, asp_beta_state_t* d_state
     ASP_DEVICE_OR_RETURN();
     ASP_REQUIRE(d_d && d_state && ws, "null pointer");
     ASP_REQUIRE(n > 0, "n must be positive");
+    asp_peer_t none = {};
     beta_pass_kernel<<<grid_for(n, kUnroll), kBlock, 0, (cudaStream_t)stream>>>(d_d, n, d_state, fused_decide,
-                                                                                (ReduceWs*)ws);
+                                                                                (ReduceWs*)ws, none);
     return check_launch("asp_beta_search_pass");
+}
+
+static int check_peer(const asp_peer_t* peer) {
+    ASP_REQUIRE(peer && peer->world >= 2 && peer->world <= ASP_MAX_PEERS && peer->rank >= 0 && peer->rank < peer->world,
+                "bad peer descriptor");
+    for (int r = 0; r < peer->world; ++r) ASP_REQUIRE(peer->box[r], "null mailbox pointer");
+    return ASP_OK;
+}
+
+int asp_beta_search_pass_p2p(const double* d_d, int64_t n, asp_beta_state_t* d_state, int levels3, double* d_sums,
+                             const asp_peer_t* peer, void* ws, void* stream) {
+    ASP_DEVICE_OR_RETURN();
+    ASP_REQUIRE(d_d && d_state && ws && (d_sums || !levels3), "null pointer");
+    ASP_REQUIRE(n > 0, "n must be positive");
+    int rc = check_peer(peer);
+    if (rc) return rc;
+    if (levels3)
+        beta_pass3_kernel<<<grid_for(n, kUnroll), kBlock, 0, (cudaStream_t)stream>>>(d_d, n, d_state, d_sums, 1,
+                                                                                     (ReduceWs*)ws, *peer);
+    else
+        beta_pass_kernel<<<grid_for(n, kUnroll), kBlock, 0, (cudaStream_t)stream>>>(d_d, n, d_state, 1, (ReduceWs*)ws,
+                                                                                    *peer);
+    return check_launch("asp_beta_search_pass_p2p");
 }
 
 int asp_beta_search_pass3(const double* d_d, int64_t n, asp_beta_state_t* d_state, double* d_sums, int fused_decide,
@@ -484,8 +562,9 @@ int asp_beta_search_pass3(const double* d_d, int64_t n, asp_beta_state_t* d_stat
     ASP_DEVICE_OR_RETURN();
     ASP_REQUIRE(d_d && d_state && d_sums && ws, "null pointer");
     ASP_REQUIRE(n > 0, "n must be positive");
+    asp_peer_t none = {};
     beta_pass3_kernel<<<grid_for(n, kUnroll), kBlock, 0, (cudaStream_t)stream>>>(d_d, n, d_state, d_sums, fused_decide,
-                                                                                 (ReduceWs*)ws);
+                                                                                 (ReduceWs*)ws, none);
     return check_launch("asp_beta_search_pass3");
 }
 

@@ -69,6 +69,61 @@ class Comm:
         self.dist.barrier(group=self.group)
 
 
+class PeerMailboxes:
+    """Mailboxes of the in-kernel all-reduce (``asp_beta_search_pass_p2p``): every rank owns
+    ``ASP_PEER_BOX_BYTES`` of zeroed device memory that all the other ranks of the box can store into over
+    NVLink.  Mapped with torch's symmetric memory (CUDA VMM handles exchanged through the group's store; plain
+    CUDA IPC handles of a caching-allocator block were tried and fault without explicit peer enabling, so they
+    are not used).  ``create`` returns None - and the caller keeps NCCL - unless EVERY rank mapped every
+    mailbox.  ``ASPIRE_B200_P2P=0`` forces NCCL.  No reference site (single process)."""
+
+    def __init__(self, desc, keep, how):
+        self.desc, self._keep, self.how = desc, keep, how
+
+    @staticmethod
+    def _map_symmetric(comm: "Comm", device, n):
+        import torch.distributed._symmetric_memory as symm
+        box = symm.empty(n, dtype=torch.float64, device=device)
+        box.zero_()
+        torch.cuda.synchronize(device)
+        hdl = symm.rendezvous(box, comm.group if comm.group is not None else comm.dist.group.WORLD)
+        ptrs = [int(p) + int(getattr(hdl, "offset", 0)) for p in hdl.buffer_ptrs]
+        if len(ptrs) != comm.world or not all(ptrs) or ptrs[comm.rank] != box.data_ptr():
+            raise RuntimeError("symmetric memory: unexpected buffer pointers")
+        return ptrs, (box, hdl), "symmetric memory"
+
+    @classmethod
+    def _map(cls, comm: "Comm", device):
+        from . import _lib
+        return cls._map_symmetric(comm, device, _lib.PEER_BOX_BYTES // 8)
+
+    @classmethod
+    def create(cls, comm: "Comm", device):
+        import os
+        from . import _lib
+        device = torch.device(device)
+        ok, mapped = 0.0, None
+        if (device.type == "cuda" and 2 <= comm.world <= _lib.MAX_PEERS and comm.world <= torch.cuda.device_count()
+                and os.environ.get("ASPIRE_B200_P2P", "1") != "0"):
+            try:
+                mapped = cls._map(comm, device)
+                ok = 1.0
+            except Exception:  # noqa: BLE001
+                ok = 0.0
+        flag = torch.tensor([-ok], dtype=torch.float64, device=device)
+        comm.all_reduce_max(flag)  # every rank or none
+        if float(flag[0]) != -1.0:
+            return None
+        ptrs, keep, how = mapped
+        desc = _lib.PeerDesc()
+        for r, ptr in enumerate(ptrs):
+            desc.box[r] = ptr
+        desc.rank, desc.world = comm.rank, comm.world
+        torch.cuda.synchronize(device)
+        comm.dist.barrier(group=comm.group)
+        return cls(desc, keep, how)
+
+
 @dataclass
 class Shard:
     """This rank's particles: rows + logs + the global output slot of every row
@@ -115,6 +170,7 @@ class ShardedSMC:
         self.headroom = headroom
         self.moment_particles = int(moment_particles)
         self._stream = 0
+        self._peer = False  # mailboxes of the in-kernel all-reduce: False = not tried yet, None = NCCL
 
     def next_stream(self, count=1):
         s = self._stream
@@ -171,8 +227,11 @@ class ShardedSMC:
         n_total = int(round(float(counts[0])))
         if st[2] > 0 or st[3] > 0:
             raise ValueError(f"Log weights contain NaN values for beta={beta_prev}")
+        if self._peer is False:
+            self._peer = PeerMailboxes.create(comm, dev) if dev.type == "cuda" and comm.world > 1 else None
         state = ops.beta_search(d, stats, beta_prev, self.target_efficiency, self.beta_tolerance, n_total=n_total,
-                                allreduce=comm.all_reduce_sum)
+                                allreduce=comm.all_reduce_sum,
+                                **({} if self._peer is None else {"peer": self._peer.desc}))
         mark("beta_search")
         beta = min(max(state.beta_min, beta_prev), 1.0)
         if beta == beta_prev:
@@ -397,7 +456,9 @@ def run_bench(args, rank, world, dev, metric, unit, workload_config, bytes_per_p
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {**workload_config(args, n_total), "parallelism": f"particle-sharded x{world}, owner-computes "
-                       "resampling, scalar NCCL collectives only"},
+                       "resampling, scalar collectives only",
+                       "beta_search_allreduce": ("inside the pass kernel over NVLink peer memory (" + engine._peer.how + ")"
+                                                 if engine._peer else "NCCL")},
             "clocks": clock_info, "gpu_launches": launches,
             "e2e": e2e,
             "roofline": {"kernel": "pcn_sweep_tpp_kernel<32,1,rosenbrock,gaussian> (per GPU)", "bound": "hbm", "achieved": ach,

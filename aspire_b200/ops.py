@@ -120,14 +120,16 @@ _STATE_WORDS = C.sizeof(_lib.BetaState) // 8
 
 
 def beta_search(d, stats, beta_prev: float, target_eff: float, tol: float, n_total: int | None = None,
-                allreduce=None, multi_level: bool = True) -> _lib.BetaState:
+                allreduce=None, multi_level: bool = True, peer=None) -> _lib.BetaState:
     """Device-driven bisection of ``determine_beta`` (smc/base.py:166-186).
 
     ``multi_level`` (default) resolves three bisection levels per pass over ``d`` (``asp_beta_search_pass3``),
     with the same decisions and the same beta as one level per pass.
     Launches a fixed number of passes with no host round trip; ``allreduce``
     (multi-GPU) is called on the two-element sums tensor between a pass and its
-    decision.  Returns the final state (one device->host read)."""
+    decision.  ``peer`` (a ``_lib.PeerDesc``, multi-GPU) replaces that with the all-reduce done inside the pass
+    kernel over NVLink peer memory (``asp_beta_search_pass_p2p``): one launch per pass and no NCCL call.
+    Returns the final state (one device->host read)."""
     lib = _lib.load()
     d, stats = _f64(d, "d"), _f64(stats, "stats")
     n = d.numel()
@@ -139,8 +141,13 @@ def beta_search(d, stats, beta_prev: float, target_eff: float, tol: float, n_tot
           "asp_beta_search_init")
     sums = torch.zeros(14, dtype=torch.float64, device=d.device)
 
+    peer_ref = None if peer is None else C.byref(peer)
+
     def single_pass():
-        if allreduce is None:
+        if peer is not None:
+            check(lib.asp_beta_search_pass_p2p(d.data_ptr(), n, state.data_ptr(), 0, None, peer_ref, ws, st),
+                  "asp_beta_search_pass_p2p")
+        elif allreduce is None:
             check(lib.asp_beta_search_pass(d.data_ptr(), n, state.data_ptr(), 1, ws, st), "asp_beta_search_pass")
         else:
             check(lib.asp_beta_search_pass(d.data_ptr(), n, state.data_ptr(), 0, ws, st), "asp_beta_search_pass")
@@ -153,7 +160,10 @@ def beta_search(d, stats, beta_prev: float, target_eff: float, tol: float, n_tot
     else:
         single_pass()  # ESS at beta = 1 (smc/base.py:170-175), then three bisection levels per pass
         for _ in range(lib.asp_beta_search_max_passes3(beta_prev, tol)):
-            if allreduce is None:
+            if peer is not None:
+                check(lib.asp_beta_search_pass_p2p(d.data_ptr(), n, state.data_ptr(), 1, sums.data_ptr(), peer_ref, ws,
+                                                   st), "asp_beta_search_pass_p2p")
+            elif allreduce is None:
                 check(lib.asp_beta_search_pass3(d.data_ptr(), n, state.data_ptr(), sums.data_ptr(), 1, ws, st),
                       "asp_beta_search_pass3")
             else:
@@ -163,6 +173,8 @@ def beta_search(d, stats, beta_prev: float, target_eff: float, tol: float, n_tot
                 check(lib.asp_beta_search_decide3(state.data_ptr(), sums.data_ptr(), st), "asp_beta_search_decide3")
     host = state.cpu().numpy().tobytes()
     out = _lib.BetaState.from_buffer_copy(host)
+    if out.reserved == -1:
+        raise AspireB200Error("beta bisection: a peer GPU did not reach the in-kernel all-reduce within 5 s")
     if out.phase != 2:
         raise AspireB200Error("beta bisection did not converge within the planned number of passes")
     return out

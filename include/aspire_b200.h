@@ -145,6 +145,19 @@ int asp_beta_search_decide(asp_beta_state_t* d_state, void* stream);
  * {S1_k, S2_k}, k = 1..7 (all-reduce these across ranks, then asp_beta_search_decide3); decisions and the
  * resulting beta are those of the one-level-per-pass search.  Run the beta = 1 evaluation first with one
  * asp_beta_search_pass, then asp_beta_search_max_passes3 passes of these. */
+/* Multi-GPU: the all-reduce of the pass sums done INSIDE the pass kernel over peer memory (no NCCL call, no
+ * separate decide launch).  box[r] is rank r's mailbox (ASP_PEER_BOX_BYTES of zero-initialised device memory,
+ * exchanged between the processes with CUDA IPC) as addressable from this device; every rank must make the
+ * same sequence of calls.  levels3 = 0: the single-beta pass, 1: three levels.
+ * A peer that never arrives is reported in asp_beta_state_t.reserved = -1 after a bounded wait. */
+#define ASP_MAX_PEERS 8
+#define ASP_PEER_BOX_BYTES (2 * ASP_MAX_PEERS * 16 * 8 + 64)
+typedef struct asp_peer {
+    double* box[ASP_MAX_PEERS];
+    int32_t rank, world;
+} asp_peer_t;
+int asp_beta_search_pass_p2p(const double* d_d, int64_t n, asp_beta_state_t* d_state, int levels3, double* d_sums,
+                             const asp_peer_t* peer, void* ws, void* stream);
 int asp_beta_search_max_passes3(double beta_prev, double tol);
 int asp_beta_search_pass3(const double* d_d, int64_t n, asp_beta_state_t* d_state, double* d_sums, int fused_decide,
                           void* ws, void* stream);

@@ -33,6 +33,31 @@ def main():
     shard = Shard(x0, prob["like"].log_prob(x0), prob["prior"].log_prob(x0), prob["q"].log_prob(x0))
     eng = ShardedSMC(comm, prob["like"], prob["prior"], prob["q"], seed=seed + 1, n_moves=moves, rho=0.5)
     new, rec = eng.step(shard, 0.0)
+    # the bisection with its all-reduce inside the pass kernel (NVLink peer memory) against the NCCL route:
+    # the same state, bit for bit, on every rank
+    d, stats_local = ops.reweight(shard.log_l, shard.log_p, shard.log_q)
+    stats = eng.global_stats(stats_local)
+    via_nccl = ops.beta_search(d, stats, 0.0, 0.5, 1e-6, n_total=n_total, allreduce=comm.all_reduce_sum)
+    p2p_note = "in-kernel all-reduce: not available (NCCL route used)"
+    if eng._peer is not None:
+        def timed(fn, reps=10):
+            torch.cuda.synchronize()
+            dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                out = fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return out, e0.elapsed_time(e1) / reps
+        via_p2p, ms_p2p = timed(lambda: ops.beta_search(d, stats, 0.0, 0.5, 1e-6, n_total=n_total,
+                                                        peer=eng._peer.desc))
+        _, ms_nccl = timed(lambda: ops.beta_search(d, stats, 0.0, 0.5, 1e-6, n_total=n_total,
+                                                   allreduce=comm.all_reduce_sum))
+        assert bytes(via_p2p) == bytes(via_nccl), (via_p2p.beta_min, via_nccl.beta_min)
+        p2p_note = f"in-kernel all-reduce over {eng._peer.how}: {ms_p2p:.3f} ms per search, NCCL {ms_nccl:.3f} ms"
+    if r == 0:
+        print(p2p_note)
     # gather (slot, x, logL) on rank 0
     cnt = torch.tensor([len(new)], dtype=torch.int64, device=dev)
     counts = comm.all_gather(cnt).reshape(-1).tolist()
