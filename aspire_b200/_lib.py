@@ -46,7 +46,7 @@ class Density(C.Structure):
 
 
 MAX_PEERS = 8
-PEER_BOX_BYTES = 2 * MAX_PEERS * 16 * 8 + 64
+PEER_BOX_BYTES = 2 * MAX_PEERS * 16 * 8 + 64 + 128
 
 
 class PeerDesc(C.Structure):
@@ -146,6 +146,8 @@ SIGNATURES = {
     "asp_cdf_aggregate": (C.c_int, [_P, _I64, _P, _P]),
     "asp_cdf_resolve": (C.c_int, [_P, _I64, _P, _P, _P, _P, _P]),
     "asp_cdf_write": (C.c_int, [_P, _I64, _P, C.c_int, _P, _P, _P]),
+    "asp_cdf_resolve_p2p": (C.c_int, [_P, _I64, _P, _P, _P, _P, _P]),
+    "asp_cdf_write_p2p": (C.c_int, [_P, _I64, C.c_int, _P, _P, _P, _P, _P]),
     "asp_cdf_exact": (C.c_int, [_P, _I64, C.c_int, _P, _P, _P]),
     "asp_cdf_info": (C.c_int, [_P, C.POINTER(C.c_int64), _P]),
     "asp_search_multinomial": (C.c_int, [_P, _I64, _P, _I64, _P, _P]),

@@ -28,6 +28,24 @@ constexpr long long kSatMax = 1LL << 60;
 
 enum { ERR_PLAN = 1, ERR_CROSSED = 2, ERR_BAD_WEIGHT = 4 };
 
+// Multi-GPU carry chain over NVLink peer memory (asp_cdf_resolve_p2p / asp_cdf_write_p2p): the chain region of
+// a rank's mailbox (include/aspire_b200.h, asp_peer_t) holds, per epoch parity, {running sum handed over by rank
+// r-1, its epoch flag, exact total written by the last rank, its epoch flag}; the epoch counter follows.
+constexpr int kChainBase = 2 * ASP_MAX_PEERS * 16 + 8;
+constexpr int kChainCounter = kChainBase + 8;
+
+// waits (bounded: 5 s of %globaltimer) until *flag == epoch; false = the writer never arrived
+__device__ __forceinline__ bool chain_wait(volatile double* flag, double epoch) {
+    unsigned long long t0 = 0, t1;
+    while (*flag != epoch) {
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (!t0) t0 = t1;
+        if (t1 - t0 > 5000000000ull) return false;
+    }
+    __threadfence_system();
+    return true;
+}
+
 struct Pair {
     long long d0, d1;  // increment if incoming mantissa is even / odd
 };
@@ -288,9 +306,11 @@ __global__ void __launch_bounds__(kBlock) cdf_aggregate_kernel(const double* __r
 __global__ void __launch_bounds__(kResolveThreads) cdf_resolve_kernel(
     const double* __restrict__ p, int64_t n, const double* __restrict__ carry, const int* __restrict__ tile_e,
     const Pair* __restrict__ agg, const int* __restrict__ dirty, double* __restrict__ tile_start,
-    double* __restrict__ cdf, double* __restrict__ carry_out, CdfHeader* hdr) {
+    double* __restrict__ cdf, double* __restrict__ carry_out, CdfHeader* hdr, const asp_peer_t P,
+    double* __restrict__ chain_out) {
     __shared__ Pair smem[32];
     __shared__ double s_s;
+    __shared__ double s_epoch;
     __shared__ int s_j;
     __shared__ long long s_phases;
     __shared__ unsigned int s_err;
@@ -301,6 +321,17 @@ __global__ void __launch_bounds__(kResolveThreads) cdf_resolve_kernel(
         s_s = carry ? carry[2] : 0.0;
         s_phases = 0;
         s_err = 0;
+        if (P.world > 1) {  // the running sum at the end of rank r-1's slice arrives in this rank's mailbox
+            double* counter = P.box[P.rank] + kChainCounter;
+            s_epoch = *counter + 1.0;
+            *counter = s_epoch;
+            s_s = 0.0;
+            if (P.rank > 0) {
+                volatile double* m = P.box[P.rank] + kChainBase + ((long long)s_epoch & 1) * 4;
+                s_s = chain_wait(m + 1, s_epoch) ? m[0] : nan("");  // NaN poisons the CDF: the host raises
+            }
+            if (chain_out) chain_out[0] = s_s;
+        }
     }
     __syncthreads();
     int64_t prev = 0;
@@ -387,6 +418,19 @@ __global__ void __launch_bounds__(kResolveThreads) cdf_resolve_kernel(
             carry_out[0] = s_s;
             carry_out[1] = hdr->total[1];
         }
+        if (P.world > 1) {
+            const int par = (int)((long long)s_epoch & 1) * 4;
+            if (P.rank < P.world - 1) {  // hand the running sum to the next rank
+                volatile double* m = P.box[P.rank + 1] + kChainBase + par;
+                m[0] = s_s;
+                __threadfence_system();
+                m[1] = s_epoch;
+            } else {  // the last rank holds the exact total: every rank normalises by it
+                for (int q = 0; q < P.world; ++q) (P.box[q] + kChainBase + par)[2] = s_s;
+                __threadfence_system();
+                for (int q = 0; q < P.world; ++q) ((volatile double*)(P.box[q] + kChainBase + par))[3] = s_epoch;
+            }
+        }
     }
 }
 
@@ -397,10 +441,21 @@ __global__ void __launch_bounds__(kBlock) cdf_write_kernel(const double* __restr
                                                            const double* __restrict__ total_ptr, int normalise,
                                                            const int* __restrict__ tile_e,
                                                            const double* __restrict__ tile_start,
-                                                           double* __restrict__ cdf) {
+                                                           double* __restrict__ cdf, const asp_peer_t P,
+                                                           double* __restrict__ chain_out) {
     __shared__ Pair smem[32];
+    __shared__ double s_total;
     const int64_t n_tiles = (n + kTile - 1) / kTile;
-    const double total = normalise ? total_ptr[0] : 1.0;
+    if (P.world > 1) {  // the total comes from the last rank's resolve stage, through this rank's mailbox
+        if (threadIdx.x == 0) {
+            const double epoch = P.box[P.rank][kChainCounter];  // advanced by this rank's resolve stage
+            volatile double* m = P.box[P.rank] + kChainBase + ((long long)epoch & 1) * 4;
+            s_total = chain_wait(m + 3, epoch) ? m[2] : nan("");
+            if (blockIdx.x == 0 && chain_out) chain_out[1] = s_total;
+        }
+        __syncthreads();
+    }
+    const double total = P.world > 1 ? (normalise ? s_total : 1.0) : (normalise ? total_ptr[0] : 1.0);
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int e = tile_e[tile];
         const int64_t base = tile * kTile;
@@ -530,8 +585,44 @@ int asp_cdf_resolve(const double* d_p, int64_t n, const double* d_carry, double*
     char* b = (char*)ws;
     cdf_resolve_kernel<<<1, kResolveThreads, 0, (cudaStream_t)stream>>>(
         d_p, n, d_carry, (int*)(b + L.off_e), (Pair*)(b + L.off_agg), (int*)(b + L.off_dirty),
-        (double*)(b + L.off_start), d_cdf, d_carry_out, (CdfHeader*)b);
+        (double*)(b + L.off_start), d_cdf, d_carry_out, (CdfHeader*)b, asp_peer_t{}, nullptr);
     return check_launch("asp_cdf_resolve");
+}
+
+static int check_chain_peer(const asp_peer_t* peer) {
+    ASP_REQUIRE(peer && peer->world >= 2 && peer->world <= ASP_MAX_PEERS && peer->rank >= 0 && peer->rank < peer->world,
+                "bad peer descriptor");
+    for (int r = 0; r < peer->world; ++r) ASP_REQUIRE(peer->box[r], "null mailbox pointer");
+    return ASP_OK;
+}
+
+int asp_cdf_resolve_p2p(const double* d_p, int64_t n, double* d_cdf, double* d_chain_out, const asp_peer_t* peer,
+                        void* ws, void* stream) {
+    ASP_DEVICE_OR_RETURN();
+    ASP_REQUIRE(d_p && d_cdf && ws && d_chain_out, "null pointer");
+    ASP_REQUIRE(n > 0, "n must be positive");
+    int rc = check_chain_peer(peer);
+    if (rc) return rc;
+    CdfLayout L = cdf_layout(n);
+    char* b = (char*)ws;
+    cdf_resolve_kernel<<<1, kResolveThreads, 0, (cudaStream_t)stream>>>(
+        d_p, n, nullptr, (int*)(b + L.off_e), (Pair*)(b + L.off_agg), (int*)(b + L.off_dirty),
+        (double*)(b + L.off_start), d_cdf, nullptr, (CdfHeader*)b, *peer, d_chain_out);
+    return check_launch("asp_cdf_resolve_p2p");
+}
+
+int asp_cdf_write_p2p(const double* d_p, int64_t n, int normalise, double* d_cdf, double* d_chain_out,
+                      const asp_peer_t* peer, void* ws, void* stream) {
+    ASP_DEVICE_OR_RETURN();
+    ASP_REQUIRE(d_p && d_cdf && ws && d_chain_out, "null pointer");
+    ASP_REQUIRE(n > 0, "n must be positive");
+    int rc = check_chain_peer(peer);
+    if (rc) return rc;
+    CdfLayout L = cdf_layout(n);
+    char* b = (char*)ws;
+    cdf_write_kernel<<<tile_grid(L.n_tiles), kBlock, 0, (cudaStream_t)stream>>>(
+        d_p, n, nullptr, normalise, (int*)(b + L.off_e), (double*)(b + L.off_start), d_cdf, *peer, d_chain_out);
+    return check_launch("asp_cdf_write_p2p");
 }
 
 int asp_cdf_write(const double* d_p, int64_t n, const double* d_total, int normalise, double* d_cdf, void* ws,
@@ -543,7 +634,7 @@ int asp_cdf_write(const double* d_p, int64_t n, const double* d_total, int norma
     char* b = (char*)ws;
     const double* total = d_total ? d_total : ((CdfHeader*)b)->total;
     cdf_write_kernel<<<tile_grid(L.n_tiles), kBlock, 0, (cudaStream_t)stream>>>(
-        d_p, n, total, normalise, (int*)(b + L.off_e), (double*)(b + L.off_start), d_cdf);
+        d_p, n, total, normalise, (int*)(b + L.off_e), (double*)(b + L.off_start), d_cdf, asp_peer_t{}, nullptr);
     return check_launch("asp_cdf_write");
 }
 

@@ -264,6 +264,20 @@ def cdf_write(p, total, normalise: bool = True) -> torch.Tensor:
     return cdf
 
 
+def cdf_resolve_write_p2p(p, peer, normalise: bool = True):
+    """Stages 4 + 5 with the carry chain and the total crossing the ranks through NVLink peer memory
+    (``asp_cdf_resolve_p2p`` / ``asp_cdf_write_p2p``) instead of send / recv / broadcast.
+    -> (cdf slice, device [running sum before this slice, exact total])."""
+    ws, cdf = _cdf_ctx.pop(p.data_ptr())
+    lib, ref = _lib.load(), C.byref(peer)
+    chain = torch.empty(2, dtype=torch.float64, device=p.device)
+    check(lib.asp_cdf_resolve_p2p(p.data_ptr(), p.numel(), cdf.data_ptr(), chain.data_ptr(), ref, ws.data_ptr(),
+                                  _stream()), "asp_cdf_resolve_p2p")
+    check(lib.asp_cdf_write_p2p(p.data_ptr(), p.numel(), int(normalise), cdf.data_ptr(), chain.data_ptr(), ref,
+                                ws.data_ptr(), _stream()), "asp_cdf_write_p2p")
+    return cdf, chain
+
+
 def cdf_info(ws) -> dict:
     info = (C.c_int64 * 4)()
     check(_lib.load().asp_cdf_info(ws.data_ptr(), info, _stream()), "asp_cdf_info")

@@ -151,7 +151,7 @@ int asp_beta_search_decide(asp_beta_state_t* d_state, void* stream);
  * same sequence of calls.  levels3 = 0: the single-beta pass, 1: three levels.
  * A peer that never arrives is reported in asp_beta_state_t.reserved = -1 after a bounded wait. */
 #define ASP_MAX_PEERS 8
-#define ASP_PEER_BOX_BYTES (2 * ASP_MAX_PEERS * 16 * 8 + 64)
+#define ASP_PEER_BOX_BYTES (2 * ASP_MAX_PEERS * 16 * 8 + 64 + 128)
 typedef struct asp_peer {
     double* box[ASP_MAX_PEERS];
     int32_t rank, world;
@@ -195,6 +195,16 @@ int asp_cdf_plan(int64_t n, const double* d_carry, void* ws, void* stream);
 int asp_cdf_aggregate(const double* d_p, int64_t n, void* ws, void* stream);
 int asp_cdf_resolve(const double* d_p, int64_t n, const double* d_carry, double* d_cdf, double* d_carry_out,
                     void* ws, void* stream);
+/* Multi-GPU carry chain over peer memory instead of send / recv / broadcast (mailboxes: asp_peer_t above).
+ * Rank r's resolve stage waits for the exact running sum at the end of rank r-1's slice to land in its mailbox,
+ * resolves its slice and stores its own running sum into rank r+1's mailbox; the last rank stores the exact
+ * total into every mailbox, where each rank's write stage picks it up.  Every rank calls resolve then write on
+ * one stream, once per CDF.  d_chain_out[2] = {running sum before this slice, exact total}; a rank that waited
+ * more than 5 s gets NaN there (and in its cdf) instead of hanging. */
+int asp_cdf_resolve_p2p(const double* d_p, int64_t n, double* d_cdf, double* d_chain_out, const asp_peer_t* peer,
+                        void* ws, void* stream);
+int asp_cdf_write_p2p(const double* d_p, int64_t n, int normalise, double* d_cdf, double* d_chain_out,
+                      const asp_peer_t* peer, void* ws, void* stream);
 int asp_cdf_write(const double* d_p, int64_t n, const double* d_total, int normalise, double* d_cdf, void* ws,
                   void* stream);
 int asp_cdf_exact(const double* d_p, int64_t n, int normalise, double* d_cdf, void* ws, void* stream);

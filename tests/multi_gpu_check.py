@@ -56,6 +56,21 @@ def main():
                                                    allreduce=comm.all_reduce_sum))
         assert bytes(via_p2p) == bytes(via_nccl), (via_p2p.beta_min, via_nccl.beta_min)
         p2p_note = f"in-kernel all-reduce over {eng._peer.how}: {ms_p2p:.3f} ms per search, NCCL {ms_nccl:.3f} ms"
+    if eng._peer is not None:
+        # the exact-CDF carry chain through the mailboxes against send / recv / broadcast: same slice, bit for bit
+        dbeta = via_nccl.beta_min
+        pw, result, tiles = ops.smc_weights(d, dbeta, dbeta * float(stats[1]), via_nccl.s1_min, n_total=n_total)
+        info = torch.stack([result[1], tiles[1::2].max(), result[0], result[0] * 0 + len(shard)]).contiguous()
+        cdf_a, lo_a, hi_a, _ = eng.global_cdf(pw, tiles, info, n_total)
+        keep, eng._peer = eng._peer, None
+        cdf_b, lo_b, hi_b, _ = eng.global_cdf(pw, tiles, info, n_total)
+        eng._peer = keep
+        assert torch.equal(cdf_a, cdf_b) and (lo_a, hi_a) == (lo_b, hi_b), (lo_a, lo_b, hi_a, hi_b)
+        _, ms_a = timed(lambda: eng.global_cdf(pw, tiles, info, n_total))
+        eng._peer = None
+        _, ms_b = timed(lambda: eng.global_cdf(pw, tiles, info, n_total))
+        eng._peer = keep
+        p2p_note += f"; CDF chain over peer memory == NCCL chain ({ms_a:.3f} ms vs {ms_b:.3f} ms)"
     if r == 0:
         print(p2p_note)
     # gather (slot, x, logL) on rank 0
