@@ -54,6 +54,16 @@ class PeerDesc(C.Structure):
     _fields_ = [("box", C.c_void_p * MAX_PEERS), ("rank", C.c_int32), ("world", C.c_int32)]
 
 
+class TransformDesc(C.Structure):
+    """``asp_transform_t`` (include/aspire_b200.h)."""
+    _fields_ = [("dims", C.c_int32), ("bounded", C.c_int32), ("affine", C.c_int32), ("reserved", C.c_int32),
+                ("eps", C.c_double), ("d_kind", C.c_void_p), ("d_lower", C.c_void_p), ("d_upper", C.c_void_p),
+                ("d_mean", C.c_void_p), ("d_std", C.c_void_p)]
+
+
+BOUNDED_NONE, BOUNDED_LOGIT, BOUNDED_PROBIT = 0, 1, 2
+
+
 class BetaState(C.Structure):
     _fields_ = [
         ("beta_prev", C.c_double),
@@ -146,6 +156,8 @@ SIGNATURES = {
     "asp_cdf_aggregate": (C.c_int, [_P, _I64, _P, _P]),
     "asp_cdf_resolve": (C.c_int, [_P, _I64, _P, _P, _P, _P, _P]),
     "asp_cdf_write": (C.c_int, [_P, _I64, _P, C.c_int, _P, _P, _P]),
+    "asp_transform_forward": (C.c_int, [_P, _P, _I64, _P, _P, _P]),
+    "asp_transform_inverse": (C.c_int, [_P, _P, _I64, _P, _P, _P]),
     "asp_cdf_resolve_p2p": (C.c_int, [_P, _I64, _P, _P, _P, _P, _P]),
     "asp_cdf_write_p2p": (C.c_int, [_P, _I64, C.c_int, _P, _P, _P, _P, _P]),
     "asp_cdf_exact": (C.c_int, [_P, _I64, C.c_int, _P, _P, _P]),

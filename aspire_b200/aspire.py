@@ -5,7 +5,8 @@
 Only the dispatch that sits on the SMC / importance hot path is mirrored
 (``get_sampler_class`` :272-305, ``init_sampler`` :307-381, ``sample_posterior``
 :383-570, ``sample_flow`` :891-907); checkpointing, HDF5 config and the
-bounded-parameter preconditioning transforms are out of scope.
+flow-based preconditioning is out of scope; bounded / periodic / affine transforms are
+``aspire_b200.transforms``.
 """
 
 from __future__ import annotations
@@ -47,8 +48,12 @@ class Aspire:
         dtype: Any | str | None = None,
         **kwargs,
     ) -> None:
-        if periodic_parameters or prior_bounds:
-            raise NotImplementedError("periodic / bounded parameter transforms are scope row 8f-4 (SURVEY.md)")
+        if (periodic_parameters or prior_bounds) and parameters is None:
+            raise ValueError("prior_bounds / periodic_parameters are keyed by parameter name: pass `parameters`")
+        self.periodic_parameters = list(periodic_parameters or [])
+        self.prior_bounds = prior_bounds
+        self.bounded_to_unbounded = bounded_to_unbounded
+        self.bounded_transform = bounded_transform
         if flow_matching:
             raise NotImplementedError("flow matching is out of scope")
         self.log_likelihood = log_likelihood
@@ -97,6 +102,17 @@ class Aspire:
                 raise ValueError(f"Unknown flow class {flow_class!r}; available: {sorted(_FLOW_CLASSES)}")
             flow_class = _FLOW_CLASSES[flow_class]
         self._flow = flow_class(dims=self.dims, device=self.device, dtype=self.dtype, **kw)
+        if self.prior_bounds is not None and self.bounded_to_unbounded:
+            # aspire.py:182-191: the flow is defined on the unbounded image of the bounded parameters (the built
+            # flows standardise their input themselves, so the transform carries no affine stage)
+            from .flows import TransformedFlow
+            from .transforms import FlowTransform
+
+            t = FlowTransform(parameters=self.parameters, prior_bounds=self.prior_bounds, bounded_to_unbounded=True,
+                              bounded_transform=self.bounded_transform, affine_transform=False, device=self.device,
+                              eps=self.eps)
+            if not t.is_identity:
+                self._flow = TransformedFlow(self._flow, t)
 
     def fit(self, samples, **kwargs):
         """``Aspire.fit`` (aspire.py:208-270): build the flow if needed and fit it to ``samples``."""
@@ -125,9 +141,32 @@ class Aspire:
                          f"entry points in 'aspire.samplers': {sorted(eps)}")
 
     def init_sampler(self, sampler_type: str, preconditioning=None, preconditioning_kwargs=None, **kwargs):
-        if preconditioning not in (None, "default", "identity"):
-            raise NotImplementedError("preconditioning transforms are scope row 8f-4 (SURVEY.md)")
+        """aspire.py:307-381: ``preconditioning`` None / "none" -> no transform; "default" / "standard" -> a
+        ``CompositeTransform`` over the prior bounds and periodic parameters (by default without the bounded and
+        affine stages, :338-341); "flow" is not built (row 8f-1)."""
         cls = self.get_sampler_class(sampler_type)
+        if sampler_type != "importance" and preconditioning is None:
+            preconditioning = "default"
+        preconditioning = preconditioning.lower() if preconditioning else None
+        transform = None
+        if preconditioning in ("standard", "default"):
+            kw = dict(preconditioning_kwargs or {})
+            kw.setdefault("affine_transform", False)
+            kw.setdefault("bounded_to_unbounded", False)
+            kw.setdefault("bounded_transform", "logit")
+            if self.parameters is not None and (self.prior_bounds is not None or kw["affine_transform"]):
+                from .transforms import CompositeTransform
+
+                transform = CompositeTransform(parameters=self.parameters, prior_bounds=self.prior_bounds,
+                                               periodic_parameters=self.periodic_parameters, device=self.device, **kw)
+                if transform.is_identity:
+                    transform = None
+        elif preconditioning == "flow":
+            raise NotImplementedError("flow preconditioning needs the device flow fit (scope row 8f-1, SURVEY.md)")
+        elif preconditioning not in (None, "none", "identity"):
+            raise ValueError(f"Unknown preconditioning: {preconditioning}")
+        if transform is not None:
+            kwargs["preconditioning_transform"] = transform
         return cls(log_likelihood=self.log_likelihood, log_prior=self.log_prior, dims=self.dims,
                    prior_flow=self._flow, xp=self.xp, dtype=self.dtype, parameters=self.parameters, **kwargs)
 

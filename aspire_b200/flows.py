@@ -48,6 +48,31 @@ class Flow:
         raise NotImplementedError
 
 
+class TransformedFlow(Flow):
+    """A flow that lives in the space of a data transform (``flows/torch/flows.py:327-387``: ``rescale`` /
+    ``inverse_rescale``): ``log_prob(x) = inner.log_prob(T(x)) + log|det J_T(x)|``; samples are drawn in the
+    transformed space and mapped back, their log density corrected by the Jacobian of the way back.  Used when
+    prior bounds are given, so that the proposal has no mass outside them (``aspire.py:175-205``)."""
+
+    def __init__(self, inner: Flow, data_transform):
+        super().__init__(inner.dims, inner.device, data_transform, None)
+        self.inner = inner
+
+    def fit(self, samples, **kwargs) -> FlowHistory:
+        x = samples.x if hasattr(samples, "x") else samples
+        x = torch.as_tensor(x, dtype=torch.float64, device=self.device).contiguous()
+        return self.inner.fit(self.data_transform.fit(x), **kwargs)
+
+    def log_prob(self, x):
+        z, log_j = self.data_transform.forward(torch.as_tensor(x, dtype=torch.float64, device=self.device))
+        return torch.as_tensor(self.inner.log_prob(z), dtype=torch.float64, device=self.device) + log_j
+
+    def sample_and_log_prob(self, n_samples):
+        z, log_q = self.inner.sample_and_log_prob(n_samples)
+        x, log_j = self.data_transform.inverse(z)
+        return x, torch.as_tensor(log_q, dtype=torch.float64, device=self.device) - log_j
+
+
 class DiagGaussianFlow(Flow):
     """q(x) = N(mean, diag(sigma^2)); ``fit`` matches moments (population std)."""
 

@@ -524,3 +524,38 @@ def pcg64_uniform(state: int, inc: int, n: int, device, offset: int = 0) -> torc
         check(_lib.load().asp_pcg64_uniform((state >> 64) & m64, state & m64, (inc >> 64) & m64, inc & m64, int(offset),
                                             n, out.data_ptr(), _stream()), "asp_pcg64_uniform")
     return out
+
+
+# ---- preconditioning transforms (scope row 8f-4) ----------------------------
+def transform_apply(x, kind, lower, upper, bounded: int, eps: float, mean=None, std=None, inverse: bool = False,
+                    want_log_j: bool = True):
+    """``CompositeTransform.forward`` / ``inverse`` (transforms.py:271-316) in one pass over the rows of ``x``.
+    ``kind`` int32 [D] (0 untouched, 1 periodic, 2 bounded) or None; ``mean`` / ``std`` select the affine stage.
+    -> (transformed rows [N, D], log |det J| [N] or None)"""
+    x = _f64(x, "x")
+    if x.dim() != 2:
+        raise AspireB200Error("x must be [N, D]")
+    n, dims = x.shape
+    t = _lib.TransformDesc()
+    t.dims, t.bounded, t.affine, t.eps = dims, int(bounded), int(mean is not None), float(eps)
+    keep = []
+    if kind is not None:
+        if kind.dtype != torch.int32 or not kind.is_cuda or kind.numel() != dims:
+            raise AspireB200Error("kind must be a CUDA int32 tensor of length D")
+        lower, upper = _f64(lower, "lower"), _f64(upper, "upper")
+        if lower.numel() != dims or upper.numel() != dims:
+            raise AspireB200Error("lower / upper must have length D")
+        keep += [kind, lower, upper]
+        t.d_kind, t.d_lower, t.d_upper = kind.data_ptr(), lower.data_ptr(), upper.data_ptr()
+    if mean is not None:
+        mean, std = _f64(mean, "mean"), _f64(std, "std")
+        if mean.numel() != dims or std.numel() != dims:
+            raise AspireB200Error("mean / std must have length D")
+        keep += [mean, std]
+        t.d_mean, t.d_std = mean.data_ptr(), std.data_ptr()
+    out = torch.empty_like(x)
+    log_j = torch.empty(n, dtype=torch.float64, device=x.device) if want_log_j else None
+    fn = _lib.load().asp_transform_inverse if inverse else _lib.load().asp_transform_forward
+    check(fn(C.byref(t), x.data_ptr(), n, out.data_ptr(), _ptr(log_j), _stream()),
+          "asp_transform_inverse" if inverse else "asp_transform_forward")
+    return out, log_j

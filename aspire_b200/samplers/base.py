@@ -52,12 +52,15 @@ class Sampler:
         self.parameters = parameters
         self.history = None
         self.n_likelihood_evaluations = 0
-        if preconditioning_transform is not None and not getattr(preconditioning_transform, "is_identity", False):
-            raise NotImplementedError(
-                "aspire_b200 samplers run in the original parameter space; preconditioning / bounded-parameter "
-                "transforms are a later scope row (SURVEY 8f-4)")
-        self.preconditioning_transform = None
+        # samplers/base.py:63-66; None / an identity transform keep the fused kernels of the samplers
+        self.preconditioning_transform = preconditioning_transform
         self.device = torch.device(getattr(prior_flow, "device", None) or "cuda")
+
+    def fit_preconditioning_transform(self, x):
+        """samplers/base.py:68-75."""
+        if self.preconditioning_transform is None:
+            return x
+        return self.preconditioning_transform.fit(torch.as_tensor(x, dtype=torch.float64, device=self.device))
 
     def log_likelihood(self, samples) -> torch.Tensor:
         """Counts evaluations like the reference (samplers/base.py:81-87)."""

@@ -389,9 +389,83 @@ class SMCSampler(Sampler):
         return torch.where(torch.isnan(lp), torch.full_like(lp, -math.inf), lp)
 
     # ---- mutation (smc/minipcn.py:69-135) --------------------------------------
+    def _pcn_params(self, beta, mu, sigma, n_moves, n, nu, tpcn):
+        """Noise of one mutation: host draws in a fixed order (parity mode) or Philox streams."""
+        dims = self.dims
+        if self.rng.is_host:
+            xi = torch.from_numpy(self.rng.rng.standard_normal((n_moves, n, dims))).to(self.device)
+            log_u = torch.from_numpy(np.log(1.0 - self.rng.rng.random((n_moves, n)))).to(self.device)
+            gam = (torch.from_numpy(self.rng.rng.gamma(0.5 * (dims + nu), 1.0, (n_moves, n))).to(self.device)
+                   if tpcn else None)
+            return ops.make_pcn_params(beta, self.rho, mu, sigma, n_moves, xi=xi, log_u=log_u, nu=nu, gamma=gam)
+        return ops.make_pcn_params(beta, self.rho, mu, sigma, n_moves, seed=self.rng.seed,
+                                   stream0=self.rng.next_stream(n_moves), index0=getattr(self, "index0", 0),
+                                   total_accepts_only=False, nu=nu)
+
+    def _mutate_preconditioned(self, particles: SMCSamples, beta: float, n_moves: int, idx, mark) -> SMCSamples:
+        """Mutation in the space of the preconditioning transform (smc/minipcn.py:102-131): z = T.fit(x), pCN / tpCN
+        moves on z against ``log_prob(z) = log_p_t(T^-1(z)) + log|det J|`` (smc/base.py:507-519), x = T^-1(z_last),
+        the three logs recomputed at x.  The Jacobian is folded into the log prior and log proposal handed to the
+        accept kernel: (1-b)(lq + J) + b(ll + lp + J) = (1-b) lq + b(ll + lp) + J."""
+        T = self.preconditioning_transform
+        n = len(particles) if idx is None else idx.numel()
+        dims = self.dims
+        if idx is not None:
+            x, ll, lp, lq = ops.gather_rows(particles.x, idx, particles.log_likelihood, particles.log_prior,
+                                            particles.log_q)
+        else:
+            x, ll, lp, lq = (t.clone() for t in (particles.x, particles.log_likelihood, particles.log_prior,
+                                                 particles.log_q))
+        z = T.fit(x).contiguous()
+        _, lj = T.inverse(z)
+        lpj, lqj = (lp + lj).contiguous(), (lq + lj).contiguous()
+        m_use = min(n, int(self.sampler_kwargs.get("moment_particles", 1 << 22)))
+        mu, sigma = ops.moments_to_mu_sigma(ops.weighted_moments(z[:m_use]), dims)
+        sigma = torch.clamp_min(sigma, 1e-150)
+        tpcn = getattr(self, "step_fn", "pcn") == "tpcn"
+        nu = 0.0
+        if tpcn:
+            mu, sigma, nu = fit_student_t_diag(z[:min(m_use, 1 << 20)], mu, sigma)
+            self.history.__dict__.setdefault("tpcn_nu", []).append(nu)
+        if mark:
+            mark("moments")
+        prm = self._pcn_params(beta, mu, sigma, n_moves, n, nu, tpcn)
+        accepts = torch.zeros(max(n_moves, 1), dtype=torch.int64, device=self.device)
+        for t in range(n_moves):
+            if tpcn:
+                ops.tpcn_scales(z, prm, t)
+            zp = ops.pcn_propose(z, prm, t)
+            xp, lj2 = T.inverse(zp)
+            prop = SMCSamples(xp, beta=beta, device=self.device, parameters=self.parameters)
+            lq2 = torch.as_tensor(self.prior_flow.log_prob(xp), dtype=torch.float64, device=self.device).contiguous()
+            prop.log_q = lq2
+            lp2 = self.log_prior(prop)
+            prop.log_prior = lp2
+            ll2 = self.log_likelihood(prop)
+            ops.pcn_accept(z, ll, lpj, lqj, zp, ll2, (lp2 + lj2).contiguous(), (lq2 + lj2).contiguous(), prm, t, accepts)
+        if mark:
+            mark("pcn_sweep")
+        acc = float(accepts[:n_moves].sum()) / max(n_moves * n, 1)
+        self.history.mcmc_acceptance.append(acc)
+        self.history.rho.append(self.rho)
+        if self.sampler_kwargs.get("adapt_rho", True):
+            target = self.sampler_kwargs["target_acceptance_rate"]
+            self.rho = float(min(max(self.rho * math.exp(acc - target), 1e-3), 1.0))
+        x = T.inverse(z)[0]
+        out = SMCSamples(x, beta=beta, parameters=self.parameters, device=self.device)
+        out.log_q = torch.as_tensor(self.prior_flow.log_prob(out.x), dtype=torch.float64, device=self.device).contiguous()
+        out.log_prior = self.log_prior(out)
+        out.log_likelihood = self.log_likelihood(out)
+        if bool(torch.isnan(out.log_q).any()):
+            raise ValueError("Log proposal contains NaN values")  # smc/minipcn.py:133-134
+        return out
+
     def mutate(self, particles: SMCSamples, beta: float, n_steps: int | None = None, idx=None, out=None,
                mark=None) -> SMCSamples:
         n_moves = int(n_steps or self.sampler_kwargs["n_steps"])
+        T = self.preconditioning_transform
+        if T is not None and not getattr(T, "is_identity", False):
+            return self._mutate_preconditioned(particles, beta, n_moves, idx, mark)
         n = len(particles) if idx is None else idx.numel()
         dims = self.dims
         # reference measure of the pCN proposal: moments of the (resampled) ensemble; beyond

@@ -370,6 +370,32 @@ int asp_philox_normal(uint64_t seed, uint32_t stream_id, int64_t index0, int64_t
 int asp_pcg64_uniform(uint64_t state_hi, uint64_t state_lo, uint64_t inc_hi, uint64_t inc_lo, int64_t offset,
                       int64_t n, double* d_out, void* stream);
 
+/* ---- preconditioning / bounded-parameter transforms (scope row 8f-4) ------
+ * CompositeTransform.forward / inverse, src/aspire/transforms.py:271-316: per dimension a periodic wrap
+ * (:425-431) or a bounded -> unbounded map (logit :591-601 with utils.py:196-245, or probit :548-565; the
+ * unit-interval value is clamped to [eps, 1 - eps]), then an affine standardisation of every dimension
+ * (:624-634).  forward applies periodic, bounded, affine; inverse undoes them in the opposite order.  One pass:
+ * d_out[n, dims] and d_log_j[n] = log |det J| of the applied direction (d_log_j may be NULL).  d_kind[dims]:
+ * 0 untouched, 1 periodic, 2 bounded (NULL = all untouched); lower / upper are read for kinds 1 and 2; mean /
+ * std (fitted by the caller: CompositeTransform.fit, :250-269) when affine != 0.  dims <= 256. */
+enum asp_bounded_kind { ASP_BOUNDED_NONE = 0, ASP_BOUNDED_LOGIT = 1, ASP_BOUNDED_PROBIT = 2 };
+typedef struct asp_transform {
+    int32_t dims;
+    int32_t bounded; /* asp_bounded_kind used by the dimensions of kind 2 */
+    int32_t affine;
+    int32_t reserved;
+    double eps;
+    const int32_t* d_kind;  /* device */
+    const double* d_lower;  /* device */
+    const double* d_upper;  /* device */
+    const double* d_mean;   /* device */
+    const double* d_std;    /* device */
+} asp_transform_t;
+int asp_transform_forward(const asp_transform_t* t, const double* d_x, int64_t n, double* d_y, double* d_log_j,
+                          void* stream);
+int asp_transform_inverse(const asp_transform_t* t, const double* d_y, int64_t n, double* d_x, double* d_log_j,
+                          void* stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

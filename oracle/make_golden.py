@@ -147,6 +147,56 @@ def loop_case(name, problem, n, seed, n_moves=4, rho=0.5):
     print(f"loop_{name}: {len(h.beta)} steps, logZ={float(out.log_evidence):.4f} +/- {float(out.log_evidence_error):.4f}")
 
 
+def transforms_case(name, d, periodic, bounded, bounded_transform, affine, n, seed):
+    """``CompositeTransform`` of the reference itself (numpy namespace, ``src/aspire/transforms.py:142-358``):
+    fit / forward / inverse on seeded points that include values on and beyond the bounds (clamped by eps) and
+    several periods away."""
+    ref_shim.import_reference()
+    import array_api_compat.numpy as xp
+    from aspire.transforms import CompositeTransform
+
+    from . import transforms as ot
+
+    rng = np.random.default_rng(seed)
+    params = [f"x{j}" for j in range(d)]
+    bounds = {}
+    for j, p in enumerate(params):
+        if j in periodic:
+            bounds[p] = [0.0, 2 * np.pi] if j % 2 == 0 else [-1.5, 2.5]
+        elif j in bounded:
+            bounds[p] = [0.0, 1.0] if j % 3 == 0 else [-2.0 - j, 3.0 + 0.5 * j]
+        else:
+            bounds[p] = [-np.inf, np.inf]
+    t = CompositeTransform(parameters=params, periodic_parameters=[params[j] for j in periodic], prior_bounds=bounds,
+                           bounded_to_unbounded=True, bounded_transform=bounded_transform, affine_transform=affine,
+                           xp=xp, dtype="float64")
+    x = rng.normal(size=(n, d)) * 2.0
+    for j, p in enumerate(params):
+        lo, hi = bounds[p]
+        if j in bounded:
+            x[:, j] = rng.uniform(lo, hi, n)
+            x[0, j], x[1, j] = lo, hi                       # on the bounds
+            x[2, j], x[3, j] = lo - 0.25, hi + 0.25         # outside: clamped to eps / 1 - eps
+            x[4, j] = lo + 1e-9 * (hi - lo)
+        elif j in periodic:
+            x[:, j] = rng.uniform(lo - 3 * (hi - lo), hi + 3 * (hi - lo), n)
+            x[0, j], x[1, j] = lo, hi
+    z_fit = np.asarray(t.fit(x.copy()))
+    y, lj = t.forward(x.copy())
+    z_in = rng.normal(size=(n, d)) * 1.5
+    z_in[0] = 40.0   # sigmoid saturates: clamp on the way back
+    z_in[1] = -40.0
+    x_inv, lj_inv = t.inverse(z_in.copy())
+    desc = ot.from_composite_args(params, [params[j] for j in periodic], bounds, True, bounded_transform, affine)
+    out = dict(kind=desc["kind"], lower=desc["lower"], upper=desc["upper"],
+               bounded=np.array(desc["bounded"] or ""), eps=desc["eps"], affine=affine, x=x, z_fit=z_fit,
+               y=np.asarray(y), log_j=np.asarray(lj), z_in=z_in, x_inv=np.asarray(x_inv), log_j_inv=np.asarray(lj_inv))
+    if affine:
+        out["mean"], out["std"] = np.asarray(t._affine_transform._mean), np.asarray(t._affine_transform._std)
+    np.savez_compressed(os.path.join(OUT, f"transforms_{name}.npz"), **out)
+    print(f"transforms_{name}: d={d} n={n} |log_j| max {np.abs(lj).max():.3f}")
+
+
 def main():
     logging.disable(logging.CRITICAL)
     os.makedirs(OUT, exist_ok=True)
@@ -159,6 +209,17 @@ def main():
     importance_case("quick4", problems.quickstart_problem(4), 2000, 22)
     loop_case("quick4", problems.quickstart_problem(4), 500, 31)
     loop_case("rosen4", problems.rosenbrock_problem(4), 1500, 32, n_moves=6)
+    transforms_main()
+
+
+def transforms_main():
+    logging.disable(logging.CRITICAL)
+    os.makedirs(OUT, exist_ok=True)
+    transforms_case("logit4", 4, periodic=[1], bounded=[0, 3], bounded_transform="logit", affine=True, n=64, seed=41)
+    transforms_case("probit3", 3, periodic=[], bounded=[0, 1, 2], bounded_transform="probit", affine=False, n=48, seed=42)
+    transforms_case("mixed32", 32, periodic=[10, 11, 12, 13], bounded=list(range(10)), bounded_transform="logit",
+                    affine=True, n=257, seed=43)
+    transforms_case("affine5", 5, periodic=[], bounded=[], bounded_transform="logit", affine=True, n=33, seed=44)
 
 
 if __name__ == "__main__":
