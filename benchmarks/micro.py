@@ -7,6 +7,7 @@
     python benchmarks/micro.py sweep       # K8: fused gather + 10 pCN moves per benchmark problem
     python benchmarks/micro.py full        # whole sample_posterior(sampler="smc") run through the drop-in API
     python benchmarks/micro.py c4          # C4: mixture SMC step with the tcgen05 flow as proposal (unfused moves)
+    python benchmarks/micro.py transform   # 8f-4: preconditioning transforms, N = 2e7, D = 32 (HBM-bound pass)
 
 Each prints JSON lines; times are CUDA events over `--iters` launches after 3 warm-ups, on inputs
 larger than L2 where the size allows (noted per line otherwise).
@@ -243,9 +244,44 @@ def full(args):
                       "likelihood_evaluations": a.n_likelihood_evaluations}))
 
 
+def transform(args):
+    """Preconditioning transforms (scope row 8f-4): forward and inverse pass over N x 32 rows, for an all-logit, an
+    all-probit, a periodic + affine and a mixed description.  Algorithmic bytes: 8 D read + 8 D + 8 written."""
+    import math
+
+    from aspire_b200 import transforms as T
+
+    dev = torch.device("cuda")
+    n, d = args.n or 20_000_000, 32
+    params = [f"x{j}" for j in range(d)]
+    z = ops.philox_normal(1, 0, n, d, dev)
+    cases = {
+        "logit": dict(bounds={p: [0.0, 1.0] for p in params}, periodic=[], bounded="logit", affine=False),
+        "probit": dict(bounds={p: [0.0, 1.0] for p in params}, periodic=[], bounded="probit", affine=False),
+        "periodic+affine": dict(bounds={p: [0.0, 2 * math.pi] for p in params}, periodic=params, bounded="logit",
+                                affine=True),
+        "mixed": dict(bounds={p: ([0.0, 1.0] if j < 12 else [0.0, 2 * math.pi] if j < 16 else [-math.inf, math.inf])
+                              for j, p in enumerate(params)}, periodic=params[12:16], bounded="logit", affine=True),
+    }
+    nbytes = n * (16 * d + 8)
+    for name, c in cases.items():
+        t = T.CompositeTransform(params, periodic_parameters=c["periodic"], prior_bounds=c["bounds"],
+                                 bounded_transform=c["bounded"], affine_transform=c["affine"], device=dev)
+        if c["affine"]:
+            t.fit(ops.philox_uniform(2, 0, 4096 * d, dev).reshape(4096, d).contiguous())
+        x = t.inverse(z)[0]
+        for direction, fn in (("inverse", lambda: t.inverse(z)), ("forward", lambda: t.forward(x))):
+            ms = timed(fn, args.iters)
+            print(json.dumps({"bench": "transform", "case": name, "direction": direction, "rows": n, "dims": d, "ms": ms,
+                              "rows_per_s": n / ms * 1e3, "algorithmic_gbs": nbytes / ms / 1e6,
+                              "frac_of_hbm_peak": nbytes / ms / 1e6 / PEAKS["hbm_gbs"],
+                              "note": "includes the allocation of the two outputs by the caching allocator"}))
+        del x
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["flow", "resample", "importance", "sweep", "c4", "full"])
+    ap.add_argument("what", choices=["flow", "resample", "importance", "sweep", "c4", "full", "transform"])
     ap.add_argument("--n", type=int, default=0)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--moves", type=int, default=10)
@@ -253,4 +289,4 @@ if __name__ == "__main__":
     ap.add_argument("--dump", default="")
     a = ap.parse_args()
     ops.device_check()
-    {"flow": flow, "resample": resample, "importance": importance, "sweep": sweep, "c4": c4, "full": full}[a.what](a)
+    {"flow": flow, "resample": resample, "importance": importance, "sweep": sweep, "c4": c4, "full": full, "transform": transform}[a.what](a)
