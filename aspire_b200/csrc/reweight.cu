@@ -124,6 +124,7 @@ __global__ void __launch_bounds__(kBlock) ess_sums_kernel(const double* __restri
 // already converged - the same passes on every rank, their states being bit-identical) do not consume epochs.
 // ---------------------------------------------------------------------------
 constexpr int kBoxStride = 16;
+constexpr unsigned long long kPeerWaitNs = 20000000000ull;  // 20 s of %globaltimer: far above any launch skew
 template <int NV>
 __device__ __forceinline__ bool p2p_allreduce_sum(double (&v)[NV], const asp_peer_t& P) {
     static_assert(NV < kBoxStride, "mailbox slot too small");
@@ -146,10 +147,10 @@ __device__ __forceinline__ bool p2p_allreduce_sum(double (&v)[NV], const asp_pee
     for (int w = 0; w < P.world; ++w) {
         volatile double* slot = P.box[P.rank] + par + (size_t)w * kBoxStride;
         unsigned long long t0 = 0, t1;
-        while (slot[15] != flag) {  // bounded: a peer that has not arrived within 5 s is reported, never waited for
+        while (slot[15] != flag) {  // bounded: a peer that has not arrived in time is reported, never waited for
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
             if (!t0) t0 = t1;
-            if (t1 - t0 > 5000000000ull) {
+            if (t1 - t0 > kPeerWaitNs) {
                 ok = false;
                 break;
             }
@@ -222,7 +223,7 @@ __global__ void __launch_bounds__(kBlock) beta_pass_kernel(const double* __restr
                                                            asp_beta_state_t* st, int fused_decide, ReduceWs* ws,
                                                            const asp_peer_t P) {
     __shared__ double smem[2 * 32];
-    if (st->phase == 2) return;  // uniform across the grid: phase only changes in the last block's epilogue
+    if (st->phase == 2 || st->reserved == -1) return;  // uniform across the grid: both only change in the last block's epilogue (-1: a peer timed out, the host raises)
     const double db = st->beta_try - st->beta_prev;
     const double c = db * (db >= 0.0 ? st->d_max : st->d_min);
     double v[2] = {0.0, 0.0};
@@ -299,7 +300,7 @@ __global__ void __launch_bounds__(kBlock, 2) beta_pass3_kernel(const double* __r
                                                             asp_beta_state_t* st, double* __restrict__ sums,
                                                             int fused_decide, ReduceWs* ws, const asp_peer_t P) {
     __shared__ double smem[2 * kBetaCand * 32];
-    if (st->phase != 1) return;  // uniform across the grid
+    if (st->phase != 1 || st->reserved == -1) return;  // uniform across the grid
     const double d_max = st->d_max;
     const double db0 = st->beta_min - st->beta_prev;
     const double h = (st->beta_max - st->beta_min) * 0.125;

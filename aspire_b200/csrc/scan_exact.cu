@@ -34,13 +34,13 @@ enum { ERR_PLAN = 1, ERR_CROSSED = 2, ERR_BAD_WEIGHT = 4 };
 constexpr int kChainBase = 2 * ASP_MAX_PEERS * 16 + 8;
 constexpr int kChainCounter = kChainBase + 8;
 
-// waits (bounded: 5 s of %globaltimer) until *flag == epoch; false = the writer never arrived
+// waits (bounded: 20 s of %globaltimer) until *flag == epoch; false = the writer never arrived
 __device__ __forceinline__ bool chain_wait(volatile double* flag, double epoch) {
     unsigned long long t0 = 0, t1;
     while (*flag != epoch) {
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
         if (!t0) t0 = t1;
-        if (t1 - t0 > 5000000000ull) return false;
+        if (t1 - t0 > 20000000000ull) return false;
     }
     __threadfence_system();
     return true;

@@ -201,7 +201,7 @@ class ShardedSMC:
             cdf, chain = ops.cdf_resolve_write_p2p(p, self._peer.desc)
             c_in, th, c_last = torch.stack([chain[0], chain[1], cdf[-1]]).tolist()   # one device -> host read
             if not (math.isfinite(th) and math.isfinite(c_in)):
-                raise RuntimeError("exact CDF: a peer GPU did not hand over its running sum within 5 s")
+                raise RuntimeError("exact CDF: a peer GPU did not hand over its running sum within 20 s")
             return cdf, (c_in / th if r > 0 else 0.0), (1.0 if r == g - 1 else c_last), host
         if r > 0:                                            # exact carry chain: rank r-1 -> r
             inc = torch.empty(2, dtype=torch.float64, device=dev)

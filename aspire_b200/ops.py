@@ -174,7 +174,7 @@ def beta_search(d, stats, beta_prev: float, target_eff: float, tol: float, n_tot
     host = state.cpu().numpy().tobytes()
     out = _lib.BetaState.from_buffer_copy(host)
     if out.reserved == -1:
-        raise AspireB200Error("beta bisection: a peer GPU did not reach the in-kernel all-reduce within 5 s")
+        raise AspireB200Error("beta bisection: a peer GPU did not reach the in-kernel all-reduce within 20 s")
     if out.phase != 2:
         raise AspireB200Error("beta bisection did not converge within the planned number of passes")
     return out
@@ -555,6 +555,12 @@ def transform_apply(x, kind, lower, upper, bounded: int, eps: float, mean=None, 
         t.d_mean, t.d_std = mean.data_ptr(), std.data_ptr()
     out = torch.empty_like(x)
     log_j = torch.empty(n, dtype=torch.float64, device=x.device) if want_log_j else None
+    if dims < 1 or dims > 256:
+        raise AspireB200Error("asp_transform: dims must be in [1, 256]")
+    if int(bounded) not in (_lib.BOUNDED_NONE, _lib.BOUNDED_LOGIT, _lib.BOUNDED_PROBIT):
+        raise AspireB200Error("asp_transform: unknown bounded transform")
+    if n == 0:  # an empty tensor has no storage to point at
+        return out, log_j
     fn = _lib.load().asp_transform_inverse if inverse else _lib.load().asp_transform_forward
     check(fn(C.byref(t), x.data_ptr(), n, out.data_ptr(), _ptr(log_j), _stream()),
           "asp_transform_inverse" if inverse else "asp_transform_forward")

@@ -200,7 +200,7 @@ int asp_cdf_resolve(const double* d_p, int64_t n, const double* d_carry, double*
  * resolves its slice and stores its own running sum into rank r+1's mailbox; the last rank stores the exact
  * total into every mailbox, where each rank's write stage picks it up.  Every rank calls resolve then write on
  * one stream, once per CDF.  d_chain_out[2] = {running sum before this slice, exact total}; a rank that waited
- * more than 5 s gets NaN there (and in its cdf) instead of hanging. */
+ * more than 20 s gets NaN there (and in its cdf) instead of hanging. */
 int asp_cdf_resolve_p2p(const double* d_p, int64_t n, double* d_cdf, double* d_chain_out, const asp_peer_t* peer,
                         void* ws, void* stream);
 int asp_cdf_write_p2p(const double* d_p, int64_t n, int normalise, double* d_cdf, double* d_chain_out,
