@@ -3,10 +3,10 @@
 ``.sample_posterior(n, sampler="smc" | "importance", ...)``.
 
 Only the dispatch that sits on the SMC / importance hot path is mirrored
-(``get_sampler_class`` :272-305, ``init_sampler`` :307-381, ``sample_posterior``
-:383-570, ``sample_flow`` :891-907); checkpointing, HDF5 config and the
-flow-based preconditioning is out of scope; bounded / periodic / affine transforms are
-``aspire_b200.transforms``.
+(``init_flow`` :175-205, ``get_sampler_class`` :272-305, ``init_sampler`` :307-381, ``sample_posterior``
+:383-570, ``sample_flow`` :891-907), including the bounded / periodic / affine preconditioning transforms
+(``aspire_b200.transforms``); the HDF5 config / flow files and flow-based preconditioning are not
+built.
 """
 
 from __future__ import annotations
@@ -83,7 +83,9 @@ class Aspire:
 
     def config_dict(self, **kwargs) -> dict:
         """Subset of ``Aspire.config_dict`` (aspire.py:820-860) that concerns this path."""
-        cfg = dict(dims=self.dims, parameters=self.parameters, device=str(self.device), eps=self.eps,
+        cfg = dict(dims=self.dims, parameters=self.parameters, periodic_parameters=self.periodic_parameters,
+                   prior_bounds=self.prior_bounds, bounded_to_unbounded=self.bounded_to_unbounded,
+                   bounded_transform=self.bounded_transform, device=str(self.device), eps=self.eps,
                    flow_backend=self.flow_backend, flow_kwargs=dict(self.flow_kwargs))
         if self._sampler is not None:
             cfg["sampler_config"] = self._sampler.config_dict(**kwargs)
