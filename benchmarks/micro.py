@@ -8,6 +8,7 @@
     python benchmarks/micro.py full        # whole sample_posterior(sampler="smc") run through the drop-in API
     python benchmarks/micro.py c4          # C4: mixture SMC step with the tcgen05 flow as proposal (unfused moves)
     python benchmarks/micro.py transform   # 8f-4: preconditioning transforms, N = 2e7, D = 32 (HBM-bound pass)
+    python benchmarks/micro.py precond     # 8f-4: SMC step with bounded parameters (logit + affine preconditioning)
 
 Each prints JSON lines; times are CUDA events over `--iters` launches after 3 warm-ups, on inputs
 larger than L2 where the size allows (noted per line otherwise).
@@ -244,6 +245,55 @@ def full(args):
                       "likelihood_evaluations": a.n_likelihood_evaluations}))
 
 
+def precond(args):
+    """Scope row 8f-4 end to end: one tempering step of a 32-D problem with bounded parameters - Gaussian likelihood
+    inside the unit box, flat prior, the proposal a Gaussian on the logit image of the box (`TransformedFlow`) and the
+    pCN moves in the logit + affine preconditioned space (`SMCSampler._mutate_preconditioned`: per move one
+    propose, one transform, three density evaluations, one accept - unfused).  The same step without bounds runs
+    the fused sweep; both are timed."""
+    from aspire_b200 import transforms as T
+    from aspire_b200.flows import DiagGaussianFlow, TransformedFlow
+    from aspire_b200.history import SMCHistory
+    from aspire_b200.rng import PhiloxRNG
+    from aspire_b200.samplers import SMCSampler
+    from aspire_b200.samples import SMCSamples
+
+    dev = torch.device("cuda")
+    n, dims, moves = args.n or 10_000_000, 32, args.moves
+    params = [f"x{j}" for j in range(dims)]
+    bounds = {p: [0.0, 1.0] for p in params}
+    like = tg.GaussianDensity([0.3 + 0.4 * j / dims for j in range(dims)], 0.15, dims, normalised=False, device=dev)
+    prior = tg.UniformDensity(0.0, 1.0, dims, device=dev)
+    ft = T.FlowTransform(params, prior_bounds=bounds, bounded_transform="logit", affine_transform=False, device=dev)
+    flow = TransformedFlow(DiagGaussianFlow(dims, device=dev, mean=[0.0] * dims, sigma=[1.2] * dims, rng=PhiloxRNG(3)), ft)
+    pt = T.CompositeTransform(params, prior_bounds=bounds, bounded_to_unbounded=True, bounded_transform="logit",
+                              affine_transform=True, device=dev)
+    out = {}
+    for name, transform in (("preconditioned", pt), ("unbounded_space_reference", None)):
+        s = SMCSampler(like, prior, dims, flow, rng=PhiloxRNG(4), preconditioning_transform=transform)
+        s._configure_kernel(dict(n_steps=moves, rho=0.3, adapt_rho=False))
+        s.resampling, s.target_efficiency, s.target_efficiency_rate = "multinomial", 0.5, 1.0
+        s.adaptive, s.adaptive_min_beta_step, s.max_beta_step = True, False, 1.0
+        s.history = SMCHistory()
+        x0, lq0 = flow.sample_and_log_prob(n)
+        p0 = SMCSamples(x0, log_likelihood=like.log_prob(x0), log_prior=prior.log_prob(x0), log_q=lq0, beta=0.0,
+                        device=dev)
+
+        def step():
+            p0.__dict__.pop("_slope_cache", None)
+            return s.tempering_step(p0, 0.0, float("nan"), 0.0, 1e-6)
+
+        ms = timed(step, max(2, args.iters // 3))
+        out[name] = dict(ms_per_step=ms, particles_per_s=n / ms * 1e3, beta=s.history.beta[-1],
+                         acceptance=s.history.mcmc_acceptance[-1])
+        del p0, x0, lq0
+    print(json.dumps({"bench": "smc_step_bounded_parameters", "particles": n, "dims": dims, "moves": moves,
+                      "route": "preconditioned: unfused moves in the logit + affine space (propose, transform, 3 density "
+                               "evaluations, accept per move); unbounded_space_reference: the same problem and proposal "
+                               "without preconditioning, semi-fused moves on x (asp_pcn_propose_eval + accept_scalar)",
+                      **out}))
+
+
 def transform(args):
     """Preconditioning transforms (scope row 8f-4): forward and inverse pass over N x 32 rows, for an all-logit, an
     all-probit, a periodic + affine and a mixed description.  Algorithmic bytes: 8 D read + 8 D + 8 written."""
@@ -281,7 +331,7 @@ def transform(args):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["flow", "resample", "importance", "sweep", "c4", "full", "transform"])
+    ap.add_argument("what", choices=["flow", "resample", "importance", "sweep", "c4", "full", "transform", "precond"])
     ap.add_argument("--n", type=int, default=0)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--moves", type=int, default=10)
@@ -289,4 +339,4 @@ if __name__ == "__main__":
     ap.add_argument("--dump", default="")
     a = ap.parse_args()
     ops.device_check()
-    {"flow": flow, "resample": resample, "importance": importance, "sweep": sweep, "c4": c4, "full": full, "transform": transform}[a.what](a)
+    {"flow": flow, "resample": resample, "importance": importance, "sweep": sweep, "c4": c4, "full": full, "transform": transform, "precond": precond}[a.what](a)
