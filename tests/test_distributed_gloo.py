@@ -128,3 +128,43 @@ def test_two_rank_tempering_loop_equals_single_rank_loop():
     d = 4
     exact = d * (-0.5 * np.log(2 * np.pi * (1.0 + 0.49)) - 0.5 * 0.25 / (1.0 + 0.49))
     assert one["log_z"] == pytest.approx(exact, abs=0.15)
+
+
+def _peer_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from aspire_b200.distributed import Comm, PeerMailboxes
+
+    # no CUDA device: every rank must agree to keep the NCCL / gloo collectives (create is itself collective)
+    ret[rank] = PeerMailboxes.create(Comm(), "cpu") is None
+    dist.destroy_process_group()
+
+
+def test_peer_mailboxes_fall_back_together_without_gpus():
+    """The in-kernel collectives are an all-or-nothing upgrade: ``PeerMailboxes.create`` returns None on every rank
+    when any rank cannot map the mailboxes (here: no GPU at all), and the sharded step keeps its collectives."""
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_peer_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
+    assert dict(ret) == {0: True, 1: True}
+
+
+def test_peer_descriptor_layout_matches_the_header():
+    """``asp_peer_t`` / ``ASP_PEER_BOX_BYTES`` in include/aspire_b200.h against the ctypes mirror."""
+    import ctypes as C
+    import re
+
+    from aspire_b200 import _lib
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    h = open(os.path.join(root, "include", "aspire_b200.h")).read()
+    max_peers = int(re.search(r"#define ASP_MAX_PEERS (\d+)", h).group(1))
+    box = re.search(r"#define ASP_PEER_BOX_BYTES \((.+)\)", h).group(1).replace("ASP_MAX_PEERS", str(max_peers))
+    assert _lib.MAX_PEERS == max_peers
+    assert _lib.PEER_BOX_BYTES == eval(box)  # noqa: S307 - arithmetic from our own header
+    assert C.sizeof(_lib.PeerDesc) == 8 * max_peers + 8
+    assert _lib.PeerDesc.rank.offset == 8 * max_peers and _lib.PeerDesc.world.offset == 8 * max_peers + 4
+    # the chain region (csrc/scan_exact.cu: kChainBase = 2 * 8 * 16 + 8, counter 8 doubles later) fits in the box
+    assert (2 * max_peers * 16 + 8 + 8 + 1) * 8 <= _lib.PEER_BOX_BYTES

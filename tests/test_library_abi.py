@@ -49,3 +49,49 @@ def test_product_does_not_import_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """Every struct that crosses the C-ABI: sizeof and the offset of each field as a C compiler lays out
+    include/aspire_b200.h (gcc, the header is plain C) against the ctypes mirrors in aspire_b200/_lib.py."""
+    import ctypes as C
+    import shutil
+    import subprocess
+
+    from aspire_b200 import _lib
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not found")
+    pairs = {"asp_density_t": _lib.Density, "asp_beta_state_t": _lib.BetaState, "asp_peer_t": _lib.PeerDesc,
+             "asp_pcn_params_t": _lib.PcnParams, "asp_flow_t": _lib.Flow, "asp_transform_t": _lib.TransformDesc}
+    text = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "aspire_b200.h")).read(), flags=re.S)
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "aspire_b200.h"', "int main(void) {"]
+    fields = {}
+    for cname in pairs:
+        tag = cname[:-2]
+        body = re.search(r"typedef struct " + tag + r"\s*\{(.*?)\}\s*" + cname + ";", text, flags=re.S).group(1)
+        names = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            for part in decl.split(","):  # "int32_t rank, world" / "double* box[ASP_MAX_PEERS]"
+                names.append(re.search(r"([A-Za-z_][A-Za-z0-9_]*)\s*(\[[^\]]*\])?\s*$", part.strip()).group(1))
+        fields[cname] = names
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        lines += [f'  printf("{cname}.{f} %zu\\n", offsetof({cname}, {f}));' for f in names]
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run([gcc, "-std=c11", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True,
+                   capture_output=True, text=True)
+    out = dict(line.split() for line in subprocess.run([str(exe)], check=True, capture_output=True,
+                                                       text=True).stdout.splitlines())
+    for cname, cls in pairs.items():
+        assert int(out[cname]) == C.sizeof(cls), cname
+        mirror = [n for n, *_ in cls._fields_]
+        assert mirror == fields[cname], (cname, mirror, fields[cname])
+        for f in mirror:
+            assert int(out[f"{cname}.{f}"]) == getattr(cls, f).offset, (cname, f)
