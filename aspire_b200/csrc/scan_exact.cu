@@ -15,6 +15,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "scan_math.cuh"
 
 namespace asp {
 
@@ -22,9 +23,6 @@ constexpr int kTile = ASP_CDF_TILE;       // 2048 weights per tile
 constexpr int kItems = kTile / kBlock;    // 8 per thread (blocked)
 constexpr int kResolveThreads = 1024;
 constexpr int kDirty = -100000;           // tile_e flag
-constexpr int kEMin = -1022;
-constexpr long long kTwo53 = 1LL << 53;
-constexpr long long kSatMax = 1LL << 60;
 
 enum { ERR_PLAN = 1, ERR_CROSSED = 2, ERR_BAD_WEIGHT = 4 };
 
@@ -45,10 +43,6 @@ __device__ __forceinline__ bool chain_wait(volatile double* flag, double epoch) 
     __threadfence_system();
     return true;
 }
-
-struct Pair {
-    long long d0, d1;  // increment if incoming mantissa is even / odd
-};
 
 struct CdfLayout {
     int64_t n_tiles;
@@ -78,42 +72,8 @@ static CdfLayout cdf_layout(int64_t n) {
     return L;
 }
 
-// ---- small exact-arithmetic helpers ----------------------------------------
-__device__ __forceinline__ int binade_of(double v) {
-    if (!(v > 0.0)) return kEMin;
-    int be = (int)((__double_as_longlong(v) >> 52) & 0x7ff);
-    return be == 0 ? kEMin : be - 1023;
-}
-// x * 2^k, exact whenever the true result is representable
-__device__ __forceinline__ double scale_pow2(double x, int k) {
-    if (k >= -1022 && k <= 1023) return x * __longlong_as_double((long long)(k + 1023) << 52);
-    return ldexp(x, k);
-}
-__device__ __forceinline__ Pair element_pair(double w, int e) {
-    double q = scale_pow2(w, 52 - e);
-    Pair r;
-    if (!(q < 9007199254740992.0)) {  // >= 2^53, inf or NaN: forces a crossing
-        r.d0 = r.d1 = kTwo53;
-        return r;
-    }
-    long long n = __double2ll_rd(q);
-    double frac = q - (double)n;
-    long long up = frac > 0.5 ? 1 : 0;
-    bool tie = frac == 0.5;
-    long long odd = n & 1;
-    r.d0 = n + up + ((tie && odd) ? 1 : 0);
-    r.d1 = n + up + ((tie && !odd) ? 1 : 0);
-    return r;
-}
-__device__ __forceinline__ long long sat(long long a) { return a < kSatMax ? a : kSatMax; }
-// a then b
-__device__ __forceinline__ Pair compose(Pair a, Pair b) {
-    Pair h;
-    h.d0 = sat(a.d0 + ((a.d0 & 1) ? b.d1 : b.d0));
-    h.d1 = sat(a.d1 + ((a.d1 & 1) ? b.d0 : b.d1));
-    return h;
-}
-__device__ __forceinline__ long long apply(Pair a, long long m0) { return m0 + ((m0 & 1) ? a.d1 : a.d0); }
+// the exact-arithmetic helpers (binade_of, scale_pow2, element_pair, compose, apply) live in scan_math.cuh,
+// host + device, so that the CPU tests run the shipped arithmetic against numpy.cumsum
 __device__ __forceinline__ Pair shfl_up_pair(Pair a, int o) {
     Pair r;
     r.d0 = __shfl_up_sync(0xffffffffu, a.d0, o);
