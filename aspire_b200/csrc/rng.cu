@@ -4,6 +4,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "pcg64_math.cuh"
 #include "philox.cuh"
 
 namespace asp {
@@ -59,33 +60,7 @@ __global__ void __launch_bounds__(kBlock) philox_normal_kernel(uint64_t seed, ui
 // after j + 1 steps.  Thread g jumps to draw offset + g with the O(log) affine power of the LCG, then
 // strides by the grid size with the affine map of T steps (computed once per block), so stores are
 // coalesced.  Spec + pin against numpy: oracle/pcg64.py, tests/test_pcg64_oracle.py.
-typedef unsigned __int128 u128;
-__device__ __forceinline__ u128 pcg_mult() {
-    return ((u128)0x2360ED051FC65DA4ULL << 64) | (u128)0x4385DF649FCCF645ULL;
-}
-// (A, C) such that state_{t + delta} = A state_t + C
-__device__ __forceinline__ void pcg_affine_power(uint64_t delta, u128 inc, u128& a_out, u128& c_out) {
-    u128 acc_mult = 1, acc_plus = 0, cur_mult = pcg_mult(), cur_plus = inc;
-    while (delta > 0) {
-        if (delta & 1) {
-            acc_mult *= cur_mult;
-            acc_plus = acc_plus * cur_mult + cur_plus;
-        }
-        cur_plus = (cur_mult + 1) * cur_plus;
-        cur_mult *= cur_mult;
-        delta >>= 1;
-    }
-    a_out = acc_mult;
-    c_out = acc_plus;
-}
-__device__ __forceinline__ double pcg_double(u128 state) {
-    const uint64_t hi = (uint64_t)(state >> 64), lo = (uint64_t)state;
-    const uint64_t x = hi ^ lo;
-    const unsigned rot = (unsigned)(hi >> 58);
-    const uint64_t r = (x >> rot) | (x << ((64u - rot) & 63u));
-    return (double)(r >> 11) * 0x1p-53;
-}
-
+// The 128-bit arithmetic lives in pcg64_math.cuh (host + device: tests/native/pcg64_host.cu runs it on the CPU).
 __global__ void __launch_bounds__(kBlock) pcg64_uniform_kernel(uint64_t s_hi, uint64_t s_lo, uint64_t i_hi,
                                                                uint64_t i_lo, int64_t offset, int64_t n,
                                                                double* __restrict__ out) {
