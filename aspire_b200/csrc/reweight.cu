@@ -11,6 +11,7 @@
 //   src/aspire/samples.py:457-475    Samples.compute_weights
 #include <math.h>
 
+#include "beta_math.cuh"
 #include "common.cuh"
 
 namespace asp {
@@ -167,54 +168,9 @@ __device__ __forceinline__ bool p2p_allreduce_sum(double (&v)[NV], const asp_pee
 // ---------------------------------------------------------------------------
 // device-driven bisection
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void beta_decide(asp_beta_state_t* st) {
-    if (st->phase == 2) return;
-    const double eff = (st->s1 * st->s1 / st->s2) / st->n_total;
-    if (st->phase == 0) {
-        st->eff_beta_max = eff;
-        if (eff >= st->target_eff) {  // smc/base.py:174-175
-            st->beta_min = 1.0;
-            st->s1_min = st->s1;
-            st->s2_min = st->s2;
-            st->min_valid = 1;
-        }
-        st->phase = 1;
-    } else {
-        if (eff >= st->target_eff) {  // smc/base.py:182-185
-            st->beta_min = st->beta_try;
-            st->s1_min = st->s1;
-            st->s2_min = st->s2;
-            st->min_valid = 1;
-        } else {
-            st->beta_max = st->beta_try;
-        }
-    }
-    st->n_evals += 1;
-    if (st->beta_max - st->beta_min > st->tol) {  // smc/base.py:177-178
-        st->beta_try = 0.5 * (st->beta_max + st->beta_min);
-    } else {
-        st->phase = 2;
-    }
-}
-
 __global__ void beta_init_kernel(asp_beta_state_t* st, double beta_prev, double target_eff, double tol, double n_total,
                                  const double* stats) {
-    st->beta_prev = beta_prev;
-    st->beta_min = beta_prev;
-    st->beta_max = 1.0;
-    st->target_eff = target_eff;
-    st->tol = tol;
-    st->n_total = n_total;
-    st->beta_try = 1.0;
-    st->s1 = st->s2 = 0.0;
-    st->eff_beta_max = 0.0;
-    st->s1_min = st->s2_min = 0.0;
-    st->d_min = stats[0];
-    st->d_max = stats[1];
-    st->phase = 0;
-    st->n_evals = 0;
-    st->min_valid = 0;
-    st->reserved = 0;
+    beta_init_state(st, beta_prev, target_eff, tol, n_total, stats[0], stats[1]);
 }
 
 __global__ void beta_decide_kernel(asp_beta_state_t* st) { beta_decide(st); }
@@ -261,39 +217,7 @@ __global__ void __launch_bounds__(kBlock) beta_pass_kernel(const double* __restr
 // particle instead of three dependent passes (each one exp).  The decisions are the reference's
 // (smc/base.py:177-185: beta_try = 0.5 (max + min), ESS/N >= target), replayed on the seven (S1, S2) pairs.
 // ---------------------------------------------------------------------------
-constexpr int kBetaLevels = 3;
-constexpr int kBetaCand = (1 << kBetaLevels) - 1;  // 7
-
-__device__ __forceinline__ void beta_decide3(asp_beta_state_t* st, const double* sums) {
-    if (st->phase != 1) return;
-    double lo = st->beta_min, hi = st->beta_max;
-    int k_lo = 0, k_hi = 1 << kBetaLevels;  // grid indices of lo / hi
-    for (int level = 0; level < kBetaLevels; ++level) {
-        if (!(hi - lo > st->tol)) break;
-        const double mid = 0.5 * (hi + lo);  // the reference's beta_try
-        const int k = (k_lo + k_hi) >> 1;
-        const double s1 = sums[2 * (k - 1)], s2 = sums[2 * (k - 1) + 1];
-        const double eff = (s1 * s1 / s2) / st->n_total;
-        if (eff >= st->target_eff) {
-            lo = mid;
-            k_lo = k;
-            st->s1_min = s1;
-            st->s2_min = s2;
-            st->min_valid = 1;
-        } else {
-            hi = mid;
-            k_hi = k;
-        }
-        st->s1 = s1;
-        st->s2 = s2;
-        st->n_evals += 1;
-    }
-    st->beta_min = lo;
-    st->beta_max = hi;
-    if (hi - lo > st->tol) st->beta_try = 0.5 * (hi + lo);
-    else st->phase = 2;
-}
-
+// kBetaLevels, kBetaCand, beta_decide3: beta_math.cuh
 __global__ void beta_decide3_kernel(asp_beta_state_t* st, const double* sums) { beta_decide3(st, sums); }
 
 __global__ void __launch_bounds__(kBlock, 2) beta_pass3_kernel(const double* __restrict__ d, int64_t n,
