@@ -45,6 +45,8 @@ class Density(C.Structure):
     ]
 
 
+DEFAULT_DEVICE = "cuda"  # where objects live when the caller names no device (the kernels run nowhere else)
+
 MAX_PEERS = 8
 PEER_BOX_BYTES = 2 * MAX_PEERS * 16 * 8 + 64 + 128
 

@@ -17,6 +17,7 @@ from typing import Any, Callable
 
 import torch
 
+from . import _lib
 from .flows import CouplingFlow, DiagGaussianFlow, Flow
 from .samplers import ImportanceSampler, MiniPCNSMC
 from .samples import Samples
@@ -60,7 +61,7 @@ class Aspire:
         self.log_prior = log_prior
         self.dims = dims
         self.parameters = parameters
-        self.device = torch.device(device if device is not None else "cuda")
+        self.device = torch.device(device if device is not None else _lib.DEFAULT_DEVICE)
         self.eps = eps
         self.flow_backend = flow_backend
         self.flow_kwargs = kwargs

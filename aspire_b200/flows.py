@@ -16,7 +16,7 @@ import math
 import numpy as np
 import torch
 
-from . import ops
+from . import _lib, ops
 from .history import FlowHistory
 from .rng import as_uniform_source
 from .targets import GaussianDensity
@@ -31,7 +31,7 @@ class Flow:
 
     def __init__(self, dims: int, device=None, data_transform=None, dtype=None):
         self.dims = int(dims)
-        self.device = torch.device(device if device is not None else "cuda")
+        self.device = torch.device(device if device is not None else _lib.DEFAULT_DEVICE)
         self.data_transform = data_transform
         self.dtype = torch.float64
 

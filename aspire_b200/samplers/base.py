@@ -13,6 +13,7 @@ from typing import Any, Callable
 
 import torch
 
+from .. import _lib
 from ..samples import Samples
 
 logger = logging.getLogger(__name__)
@@ -54,7 +55,7 @@ class Sampler:
         self.n_likelihood_evaluations = 0
         # samplers/base.py:63-66; None / an identity transform keep the fused kernels of the samplers
         self.preconditioning_transform = preconditioning_transform
-        self.device = torch.device(getattr(prior_flow, "device", None) or "cuda")
+        self.device = torch.device(getattr(prior_flow, "device", None) or _lib.DEFAULT_DEVICE)
 
     def fit_preconditioning_transform(self, x):
         """samplers/base.py:68-75."""

@@ -16,7 +16,7 @@ from typing import Any
 import numpy as np
 import torch
 
-from . import ops
+from . import _lib, ops
 from .rng import as_uniform_source
 
 logger = logging.getLogger(__name__)
@@ -49,7 +49,8 @@ class BaseSamples:
         self.xp = torch
         self.dtype = torch.float64  # the kernels compute in fp64 (reference parity mode)
         if self.device is None:
-            self.device = self.x.device if isinstance(self.x, torch.Tensor) and self.x.is_cuda else torch.device("cuda")
+            self.device = (self.x.device if isinstance(self.x, torch.Tensor) and self.x.is_cuda
+                           else torch.device(_lib.DEFAULT_DEVICE))
         self.device = torch.device(self.device)
         self.x = _as_dev(self.x, self.device)
         if self.x.ndim == 1:

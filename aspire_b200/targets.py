@@ -32,7 +32,7 @@ class Density:
 
     def __init__(self, dims: int, device=None):
         self.dims = int(dims)
-        self.device = torch.device(device if device is not None else "cuda")
+        self.device = torch.device(device if device is not None else _lib.DEFAULT_DEVICE)
         self._struct = None
 
     # -- descriptor ---------------------------------------------------------

@@ -34,7 +34,7 @@ class BaseTransform:
     def __init__(self, xp=None, dtype: Any = None, device=None):
         self.xp = torch
         self.dtype = torch.float64
-        self.device = torch.device(device if device is not None else "cuda")
+        self.device = torch.device(device if device is not None else _lib.DEFAULT_DEVICE)
 
     def _rows(self, x) -> torch.Tensor:
         x = torch.as_tensor(x, dtype=torch.float64, device=self.device)

@@ -1,0 +1,88 @@
+"""HOST logic of the samplers in the CPU suite: the ctypes layer (``aspire_b200.ops``) is replaced by the test doubles
+of tests/ops_double.py and the very test functions of the GPU suite are run against them on ``device="cpu"`` -
+tempering loop against the reference's golden loop, fused / unfused route equivalence, statistics of the
+quickstart problem, reference KATs on the containers, initial-sample filtering, argument errors, checkpoint /
+resume, tpCN, the preconditioned (bounded / periodic) route and the reference's integration tests.  What this
+establishes is that the Python above the C-ABI is right; that the kernels are right is the GPU suite's job."""
+import os
+import sys
+
+import pytest
+
+sys.path.insert(0, os.path.dirname(__file__))
+
+import ops_double  # noqa: E402
+
+
+@pytest.fixture
+def cpu(monkeypatch):
+    ops_double.install(monkeypatch)
+    return "cpu"
+
+
+def _mod(name):
+    import importlib
+
+    return importlib.import_module(name)
+
+
+@pytest.mark.parametrize("name,mk,dims", [("quick4", "quickstart_problem", 4), ("rosen4", "rosenbrock_problem", 4)])
+def test_smc_loop_matches_reference_loop(cpu, name, mk, dims):
+    _mod("test_gpu_samplers").test_smc_loop_matches_reference_loop(cpu, name, mk, dims)
+
+
+def test_unfused_path_equals_fused(cpu):
+    _mod("test_gpu_samplers").test_unfused_path_equals_fused(cpu)
+
+
+def test_smc_quickstart_statistics(cpu):
+    _mod("test_gpu_samplers").test_smc_quickstart_statistics_philox(cpu)
+
+
+def test_importance_sampler_c2(cpu):
+    _mod("test_gpu_samplers").test_importance_sampler_c2(cpu)
+
+
+@pytest.mark.parametrize("fn", ["test_samples_compute_weights_constant_case",
+                                "test_smc_unnormalized_and_normalized_log_weights_and_ratio",
+                                "test_smc_log_weights_nan_guard_raises", "test_smc_variance_and_standard_samples",
+                                "test_draw_initial_samples_filters_and_errors", "test_sampler_argument_errors",
+                                "test_smc_with_tpcn_step"])
+def test_reference_kats_and_errors(cpu, fn):
+    getattr(_mod("test_gpu_samplers"), fn)(cpu)
+
+
+def test_smc_resample_shapes_and_reference_indices(cpu, caplog):
+    _mod("test_gpu_samplers").test_smc_resample_shapes_beta_same_beta_and_reference_indices(cpu, caplog)
+
+
+@pytest.mark.parametrize("source", ["dict", "bytes", "file"])
+def test_smc_checkpoint_resume_reproduces_the_run(cpu, tmp_path, source):
+    _mod("test_gpu_samplers").test_smc_checkpoint_resume_reproduces_the_run(cpu, tmp_path, source)
+
+
+def test_smc_checkpoint_every_with_default_callback(cpu, tmp_path):
+    _mod("test_gpu_samplers").test_smc_checkpoint_every_with_default_callback(cpu, tmp_path)
+
+
+@pytest.mark.parametrize("step_fn", ["pcn", "tpcn"])
+def test_smc_with_bounded_parameters(cpu, step_fn):
+    _mod("test_gpu_transforms").test_smc_with_bounded_parameters(cpu, step_fn)
+
+
+def test_smc_with_a_periodic_parameter(cpu):
+    _mod("test_gpu_transforms").test_smc_with_a_periodic_parameter(cpu)
+
+
+@pytest.mark.parametrize("bounded_to_unbounded", [True, False])
+@pytest.mark.parametrize("sampler,kwargs", [
+    ("importance", {}),
+    ("minipcn_smc", {"adaptive": True, "sampler_kwargs": {"n_steps": 10}}),
+])
+def test_integration(cpu, bounded_to_unbounded, sampler, kwargs):
+    _mod("test_gpu_integration").test_integration(cpu, bounded_to_unbounded, sampler, kwargs)
+
+
+@pytest.mark.parametrize("value", [float("-inf"), float("nan")])
+def test_smc_log_likelihood_with_invalid_value(cpu, value):
+    _mod("test_gpu_integration").test_smc_log_likelihood_with_invalid_value(cpu, value)
