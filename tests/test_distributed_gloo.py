@@ -163,7 +163,8 @@ def test_peer_descriptor_layout_matches_the_header():
     max_peers = int(re.search(r"#define ASP_MAX_PEERS (\d+)", h).group(1))
     box = re.search(r"#define ASP_PEER_BOX_BYTES \((.+)\)", h).group(1).replace("ASP_MAX_PEERS", str(max_peers))
     assert _lib.MAX_PEERS == max_peers
-    assert _lib.PEER_BOX_BYTES == eval(box)  # noqa: S307 - arithmetic from our own header
+    assert re.fullmatch(r"[0-9+*() ]+", box), box  # plain integer arithmetic only
+    assert _lib.PEER_BOX_BYTES == eval(box, {"__builtins__": {}})  # noqa: S307
     assert C.sizeof(_lib.PeerDesc) == 8 * max_peers + 8
     assert _lib.PeerDesc.rank.offset == 8 * max_peers and _lib.PeerDesc.world.offset == 8 * max_peers + 4
     # the chain region (csrc/scan_exact.cu: kChainBase = 2 * 8 * 16 + 8, counter 8 doubles later) fits in the box
