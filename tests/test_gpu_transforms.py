@@ -260,3 +260,22 @@ def test_smc_with_a_periodic_parameter(cuda):
     assert ang == pytest.approx(m, abs=0.05)
     # both sides of the seam are populated
     assert float((phi > two_pi - 1.0).double().mean()) > 0.05 and float((phi < 1.0).double().mean()) > 0.2
+
+
+def test_bounded_parameters_example_runs(cuda, capsys):
+    """examples/bounded_parameters.py: bounded (logit) + periodic + free parameter, standard preconditioning."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location(
+        "bounded_parameters", os.path.join(os.path.dirname(__file__), "..", "examples", "bounded_parameters.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    posterior, history = mod.main()
+    x = posterior.x
+    assert history.beta[-1] == 1.0
+    assert float(x[:, 0].min()) > 0.0 and float(x[:, 0].max()) < 1.0
+    assert float(x[:, 1].min()) >= 0.0 and float(x[:, 1].max()) < 2 * math.pi
+    assert abs(math.atan2(float(torch.sin(x[:, 1]).mean()), float(torch.cos(x[:, 1]).mean())) - 0.3) < 0.08
+    assert float(x[:, 2].std()) == pytest.approx(3 / math.sqrt(10), rel=0.05)
+    assert float(x[:, 0].mean()) == pytest.approx(0.899, abs=0.01)  # mean of N(0.95, 0.1) truncated to (0, 1)
+    assert "log evidence" in capsys.readouterr().out

@@ -86,3 +86,25 @@ def test_integration(cpu, bounded_to_unbounded, sampler, kwargs):
 @pytest.mark.parametrize("value", [float("-inf"), float("nan")])
 def test_smc_log_likelihood_with_invalid_value(cpu, value):
     _mod("test_gpu_integration").test_smc_log_likelihood_with_invalid_value(cpu, value)
+
+
+def test_bounded_parameters_example(cpu, capsys):
+    """examples/bounded_parameters.py end to end (bounded + periodic + free parameter, logit flow transform,
+    standard preconditioning) on the doubles."""
+    import importlib.util
+    import math
+
+    import torch
+
+    spec = importlib.util.spec_from_file_location(
+        "bounded_parameters", os.path.join(os.path.dirname(__file__), "..", "examples", "bounded_parameters.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    posterior, history = mod.main(device="cpu", n_samples=4000)
+    x = posterior.x
+    assert history.beta[-1] == 1.0
+    assert float(x[:, 0].min()) > 0.0 and float(x[:, 0].max()) < 1.0
+    assert float(x[:, 1].min()) >= 0.0 and float(x[:, 1].max()) < 2 * math.pi
+    assert abs(math.atan2(float(torch.sin(x[:, 1]).mean()), float(torch.cos(x[:, 1]).mean())) - 0.3) < 0.1
+    assert float(x[:, 2].std()) == pytest.approx(3 / math.sqrt(10), rel=0.1)
+    assert "log evidence" in capsys.readouterr().out
