@@ -147,6 +147,66 @@ def loop_case(name, problem, n, seed, n_moves=4, rho=0.5):
     print(f"loop_{name}: {len(h.beta)} steps, logZ={float(out.log_evidence):.4f} +/- {float(out.log_evidence_error):.4f}")
 
 
+def loop_precond_case(name, problem, n, seed, n_moves=5, rho=0.4, bounded_transform="logit"):
+    """The reference's tempering loop WITH a preconditioning transform: its own ``CompositeTransform`` (logit +
+    affine over the prior bounds), its own ``SMCSampler.log_prob`` (smc/base.py:507-519: T^-1, tempered target,
+    + log|det J|) as the target of the restated pCN, driven the way ``MiniPCNSMC.mutate`` drives minipcn
+    (smc/minipcn.py:89-131: z = fit(x), chain in z, x = T^-1(z_last), the three logs recomputed at x)."""
+    xp, SMCSampler, Samples, SMCSamples, _ = _reference_objects()
+    from aspire.transforms import CompositeTransform
+
+    rng = np.random.default_rng(seed)
+    like, prior, q = problem["like"], problem["prior"], problem["q"]
+    d = problem["dims"]
+    params = [f"x{j}" for j in range(d)]
+    bounds = {p: [float(prior["lo"][j]), float(prior["hi"][j])] for j, p in enumerate(params)}
+    transform = CompositeTransform(parameters=params, prior_bounds=bounds, bounded_to_unbounded=True,
+                                   bounded_transform=bounded_transform, affine_transform=True, xp=xp, dtype="float64")
+
+    class _S(SMCSampler):
+        def mutate(self, particles, beta, n_steps=None):
+            z = np.asarray(self.fit_preconditioning_transform(particles.x))
+            mu, sigma = z.mean(axis=0), z.std(axis=0)
+            m = n_moves
+            xi = self.rng.standard_normal((m, len(z), z.shape[1]))
+            log_u = np.log(1.0 - self.rng.random((m, len(z))))
+            cur = np.asarray(self.log_prob(z, beta=beta))
+            a = np.sqrt(1.0 - rho * rho)
+            n_acc = 0
+            for t in range(m):
+                zp = mu + (a * (z - mu) + (rho * sigma) * xi[t])
+                new = np.asarray(self.log_prob(zp, beta=beta))
+                log_a = (new - cur) + (pcn.ref_quad(zp, mu, 1.0 / sigma) - pcn.ref_quad(z, mu, 1.0 / sigma))
+                acc = log_u[t] < log_a
+                z = np.where(acc[:, None], zp, z)
+                cur = np.where(acc, new, cur)
+                n_acc += int(acc.sum())
+            self.history.mcmc_acceptance.append(n_acc / (m * len(z)))
+            x = np.asarray(self.preconditioning_transform.inverse(z)[0])
+            out = SMCSamples(x=x, beta=beta, xp=self.xp, dtype=self.dtype, parameters=self.parameters)
+            out.log_q = np.asarray(self.prior_flow.log_prob(out.x))
+            out.log_prior = np.asarray(self.log_prior(out))
+            out.log_likelihood = np.asarray(self.log_likelihood(out))
+            return out
+
+    s = _S(lambda s_: dn.evaluate(like, np.asarray(s_.x)), lambda s_: dn.evaluate(prior, np.asarray(s_.x)), d,
+           _Flow(q, rng, xp), xp, dtype="float64", rng=rng, parameters=params, preconditioning_transform=transform)
+    s.sampler_kwargs = {}
+    out = s.sample(n, adaptive=True, target_efficiency=0.5, beta_tolerance=1e-6, store_sample_history=False)
+    h = s.history
+    np.savez_compressed(
+        os.path.join(OUT, f"loop_precond_{name}.npz"),
+        seed=seed, n=n, n_moves=n_moves, rho=rho, bounded_transform=np.array(bounded_transform),
+        beta=np.array(h.beta), ess=np.array(h.ess), log_norm_ratio=np.array(h.log_norm_ratio),
+        log_norm_ratio_var=np.array(h.log_norm_ratio_var), mcmc_acceptance=np.array(h.mcmc_acceptance),
+        log_evidence=float(out.log_evidence), log_evidence_error=float(out.log_evidence_error),
+        x=np.asarray(out.x), log_l=np.asarray(out.log_likelihood), log_p=np.asarray(out.log_prior),
+        n_likelihood_evaluations=int(s.n_likelihood_evaluations),
+    )
+    print(f"loop_precond_{name}: {len(h.beta)} steps, logZ={float(out.log_evidence):.4f}, acceptance "
+          f"{np.mean(h.mcmc_acceptance):.3f}, x in [{np.asarray(out.x).min():.4f}, {np.asarray(out.x).max():.4f}]")
+
+
 def transforms_case(name, d, periodic, bounded, bounded_transform, affine, n, seed):
     """``CompositeTransform`` of the reference itself (numpy namespace, ``src/aspire/transforms.py:142-358``):
     fit / forward / inverse on seeded points that include values on and beyond the bounds (clamped by eps) and
@@ -220,6 +280,7 @@ def transforms_main():
     transforms_case("mixed32", 32, periodic=[10, 11, 12, 13], bounded=list(range(10)), bounded_transform="logit",
                     affine=True, n=257, seed=43)
     transforms_case("affine5", 5, periodic=[], bounded=[], bounded_transform="logit", affine=True, n=33, seed=44)
+    loop_precond_case("box4", problems.box_problem(4), 1500, 51)
 
 
 if __name__ == "__main__":

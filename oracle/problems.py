@@ -51,6 +51,14 @@ def gmm_problem(dims=64, n_comp=8, seed=20251104):
     return dict(dims=dims, like=like, prior=_gauss(0.0, 4.0, dims), q=_gauss(0.0, 2.5, dims))
 
 
+def box_problem(dims=4):
+    """Bounded parameters (scope row 8f-4): unnormalised Gaussian likelihood inside the unit box, flat prior on the
+    box, diagonal-Gaussian proposal centred in it (its draws outside the box are dropped by the samplers)."""
+    mu, sigma = np.linspace(0.25, 0.8, dims), np.linspace(0.12, 0.3, dims)
+    prior = dict(kind=dn.KIND_UNIFORM, lo=np.zeros(dims), hi=np.ones(dims), const=0.0)
+    return dict(dims=dims, like=_gauss(mu, sigma, dims, normalised=False), prior=prior, q=_gauss(0.5, 0.22, dims))
+
+
 def draw(problem, n, seed):
     """Draw ``n`` particles from the diagonal-Gaussian proposal with a numpy
     Generator and evaluate the three log-densities."""
