@@ -151,7 +151,8 @@ class SMCSampler(Sampler):
                     "Adaptive beta search could not find a beta above %.6g that satisfies the target efficiency "
                     "%.3f within tolerance %.1e; beta may remain unchanged. Consider decreasing beta_tolerance or "
                     "target_efficiency.", beta_prev, target_eff, beta_tolerance)
-            if self.adaptive_min_beta_step:
+            if self.adaptive_min_beta_step and beta_star < 1.0:
+                # smc/base.py:198-201; the reference divides by zero here when the search lands on beta = 1
                 min_beta_step = min_beta_step * (1 - beta_prev) / (1 - beta_star)
             beta = max(beta_star, beta_prev + min_beta_step)
             beta = min(beta, beta_prev + max_beta_step, 1.0)

@@ -175,3 +175,98 @@ def test_transformed_flow_is_a_normalised_density_on_the_box(cpu, bounded_transf
     xs, lq = flow.sample_and_log_prob(5000)
     assert float(xs.min()) > -2.0 and float(xs.max()) < 3.0
     np.testing.assert_allclose(flow.log_prob(xs).numpy(), lq.numpy(), rtol=1e-9, atol=1e-9)
+
+
+def _quickstart_sampler(cpu, seed=3, fused=True):
+    from aspire_b200 import targets as tg
+    from aspire_b200.flows import DiagGaussianFlow
+    from aspire_b200.rng import PhiloxRNG
+    from aspire_b200.samplers import SMCSampler
+
+    dims = 4
+    prob = tg.quickstart_problem(dims, device=cpu)
+    flow = DiagGaussianFlow(dims, device=cpu, mean=[0.0] * dims, sigma=[1.3] * dims, rng=PhiloxRNG(seed))
+    like = prob["like"] if fused else (lambda s: prob["like"].log_prob(s.x))
+    prior = prob["prior"] if fused else (lambda s: prob["prior"].log_prob(s.x))
+    return SMCSampler(like, prior, dims, flow, rng=PhiloxRNG(seed + 1))
+
+
+def test_fixed_schedule_runs_exactly_n_steps(cpu):
+    """adaptive=False: beta advances by 1 / n_steps (smc/base.py:162-165) and ends at exactly 1."""
+    import math
+
+    s = _quickstart_sampler(cpu)
+    out = s.sample(3000, n_steps=5, adaptive=False, sampler_kwargs=dict(n_steps=4), store_sample_history=False)
+    assert len(s.history.beta) == 5 and s.history.beta[-1] == 1.0
+    assert s.history.beta[:4] == pytest.approx([0.2, 0.4, 0.6, 0.8])
+    assert out.log_evidence == pytest.approx(2 * math.log(math.pi), abs=5 * out.log_evidence_error + 0.05)
+    assert s.n_likelihood_evaluations == 3000 + 5 * 4 * 3000
+
+
+def test_max_n_steps_and_beta_step_clamps(cpu):
+    """max_n_steps -> min_beta_step = 1 / max_n_steps, rescaled each step (smc/base.py:198-201) and the loop stops
+    after max_n_steps iterations; max_beta_step caps the increase (:202-203)."""
+    s = _quickstart_sampler(cpu)
+    s.sample(2000, max_n_steps=2, sampler_kwargs=dict(n_steps=3), store_sample_history=False)
+    assert len(s.history.beta) <= 2
+    s = _quickstart_sampler(cpu)
+    s.sample(2000, max_beta_step=0.15, sampler_kwargs=dict(n_steps=3), store_sample_history=False)
+    steps = [b - a for a, b in zip([0.0] + s.history.beta[:-1], s.history.beta)]
+    assert max(steps) <= 0.15 + 1e-12 and len(s.history.beta) >= 7 and s.history.beta[-1] == 1.0
+    s = _quickstart_sampler(cpu)
+    s.sample(2000, min_beta_step=0.5, sampler_kwargs=dict(n_steps=3), store_sample_history=False)
+    assert len(s.history.beta) <= 2 and s.history.beta[-1] == 1.0
+
+
+def test_target_efficiency_ramp_history_and_final_samples(cpu):
+    """target_efficiency=(lo, hi) ramps with beta (smc/base.py:114-121); store_sample_history keeps a host copy per
+    step plus the initial one; n_final_samples resamples at beta = 1 and mutates n_final_steps times (:457-474)."""
+    s = _quickstart_sampler(cpu, fused=False)
+    out = s.sample(1500, target_efficiency=(0.3, 0.8), target_efficiency_rate=2.0, n_final_samples=700,
+                   sampler_kwargs=dict(n_steps=3, n_final_steps=2), store_sample_history=True,
+                   resampling="systematic")
+    h = s.history
+    # recorded at the beta just chosen (smc/base.py:412-414); the search itself aimed at the value for the old beta
+    assert h.eff_target == pytest.approx([0.3 + 0.5 * b ** 2.0 for b in h.beta])
+    assert h.ess[0] / 1500 == pytest.approx(0.3, abs=0.01)
+    assert len(h.sample_history) == len(h.beta) + 1 and h.sample_history[0]["x"].shape == (1500, 4)
+    assert out.x.shape == (700, 4) and out.log_likelihood.shape == (700,)
+    assert len(h.mcmc_acceptance) == len(h.beta) + 1  # one more mutation for the final samples
+    assert out.log_q is None and out.log_w is None
+
+
+def test_importance_sampler_fields(cpu):
+    """ImportanceSampler.sample (importance.py:6-22): every field of Samples filled, prior evaluated before the
+    likelihood and visible to it."""
+    import math
+
+    import torch
+
+    from aspire_b200 import targets as tg
+    from aspire_b200.flows import DiagGaussianFlow
+    from aspire_b200.rng import PhiloxRNG
+    from aspire_b200.samplers import ImportanceSampler
+
+    prob = tg.gaussian_problem(3, device=cpu)
+    seen = []
+
+    def log_prior(s):
+        seen.append("prior")
+        return prob["prior"].log_prob(s.x)
+
+    def log_likelihood(s):
+        seen.append("like")
+        assert s.log_prior is not None  # docs/recipes.rst:7-27
+        return prob["like"].log_prob(s.x)
+
+    flow = DiagGaussianFlow(3, device=cpu, mean=prob["q"].mean_np, sigma=prob["q"].sigma_np, rng=PhiloxRNG(8))
+    out = ImportanceSampler(log_likelihood, log_prior, 3, flow).sample(20_000)
+    assert seen == ["prior", "like"]
+    for name in ("log_likelihood", "log_prior", "log_q", "log_w", "weights"):
+        assert getattr(out, name).shape == (20_000,)
+    assert torch.allclose(out.log_w, out.log_likelihood + out.log_prior - out.log_q)
+    assert 0 < float(out.effective_sample_size) <= 20_000 and 0 < out.efficiency <= 1
+    assert math.isfinite(out.log_evidence) and out.evidence == pytest.approx(math.exp(out.log_evidence))
+    # Z = prod_j N(0.5; 0, 1 + 0.7^2): normalised Gaussian likelihood in x under a standard normal prior
+    log_z = 3 * (-0.5 * math.log(2 * math.pi * 1.49) - 0.25 / (2 * 1.49))
+    assert out.log_evidence == pytest.approx(log_z, abs=5 * out.log_evidence_error + 0.02)
