@@ -117,11 +117,34 @@ class BaseSamples:
         return self._numpy_fields()
 
     def to_dict(self, flat: bool = True):
-        d = self._numpy_fields()
+        """samples.py:142-181: every field (host copies) plus one key per parameter (``flat``) or a ``"samples"``
+        dictionary of parameter columns."""
+        d = self.to_numpy()
         xs = d.pop("x")
-        out = {p: xs[:, i] for i, p in enumerate(self.parameters)} if flat else {"x": xs}
-        out.update({k: v for k, v in d.items() if k != "parameters"})
-        return out
+        columns = {p: xs[:, i] for i, p in enumerate(self.parameters)}
+        if flat:
+            d.update(columns)
+        else:
+            d["samples"] = columns
+        return d
+
+    def __str__(self):
+        return f"No. samples: {len(self.x)}\nNo. parameters: {self.x.shape[-1]}\n"  # samples.py:276-280
+
+    # pickling swaps the namespace module for its name (samples.py:394-413)
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state.pop("_slope_cache", None)  # device scratch of SMCSamples, rebuilt on demand
+        state["xp"] = "torch"
+        state["device"] = None if self.device is None else str(self.device)
+        return state
+
+    def __setstate__(self, state):
+        state = dict(state)
+        state["xp"] = torch
+        if state.get("device") is not None:
+            state["device"] = torch.device(state["device"])
+        self.__dict__.update(state)
 
 
 @dataclass
@@ -192,8 +215,8 @@ class Samples(BaseSamples):
         sliced.log_evidence_error = self.log_evidence_error
         return sliced
 
-    def __str__(self):
-        out = f"Samples: {len(self)} x {self.dims}\n"
+    def __str__(self):  # samples.py:506-515
+        out = super().__str__()
         if self.log_evidence is not None and self.log_evidence_error is not None:
             out += f"Log evidence: {self.log_evidence:.2f} +/- {self.log_evidence_error:.2f}\n"
         if self.log_w is not None:
@@ -310,6 +333,12 @@ class SMCSamples(BaseSamples):
         d = self._numpy_fields()
         d.update(beta=self.beta, log_evidence=self.log_evidence, log_evidence_error=self.log_evidence_error)
         return d
+
+    def __str__(self):  # samples.py:1289-1293
+        out = super().__str__()
+        if self.log_evidence is not None:
+            out += f"Log evidence: {self.log_evidence:.2f}\n"
+        return out
 
     def __getitem__(self, idx):
         sliced = super().__getitem__(idx)
