@@ -128,6 +128,39 @@ class BaseSamples:
             d["samples"] = columns
         return d
 
+    @classmethod
+    def from_dict(cls, dictionary: dict, device=None):
+        """samples.py:182-206: the inverse of ``to_dict`` for both layouts; derived quantities (weights, evidence
+        of ``Samples``) are recomputed by the constructor, not read back."""
+        import dataclasses
+
+        d = dict(dictionary)
+        parameters = d.pop("parameters", None)
+        if "samples" in d:
+            columns = d.pop("samples")
+            parameters = sorted(columns) if parameters is None else parameters
+        else:
+            if parameters is None:
+                raise ValueError("Parameters must be provided if samples are not nested in a 'samples' key")
+            columns = {p: d.pop(p) for p in parameters}
+        x = np.stack([np.asarray(columns[p]) for p in parameters], axis=-1)
+        init = {f.name for f in dataclasses.fields(cls) if f.init} - {"x", "parameters", "xp", "dtype", "device"}
+        return cls(x=x, parameters=list(parameters), device=device, **{k: v for k, v in d.items() if k in init})
+
+    def to_dataframe(self, include: list | None = None):
+        """samples.py:208-250: parameter columns plus the per-sample fields named in ``include`` (default: the
+        three log densities that are set)."""
+        import pandas as pd
+
+        d = self.to_dict(flat=True)
+        names = list(self._dataframe_fields) if include is None else list(include)
+        data = {p: d[p] for p in self.parameters}
+        for k in names:  # a field that is not set becomes a column of NaN, as in the reference
+            data[k] = d[k] if d.get(k) is not None else np.full(len(self.x), np.nan)
+        return pd.DataFrame(data)
+
+    _dataframe_fields = ("log_likelihood", "log_prior", "log_q")
+
     def __str__(self):
         return f"No. samples: {len(self.x)}\nNo. parameters: {self.x.shape[-1]}\n"  # samples.py:276-280
 
@@ -214,6 +247,8 @@ class Samples(BaseSamples):
         sliced.log_evidence = self.log_evidence
         sliced.log_evidence_error = self.log_evidence_error
         return sliced
+
+    _dataframe_fields = ("log_likelihood", "log_prior", "log_q", "log_w")  # samples.py:559-577
 
     def __str__(self):  # samples.py:506-515
         out = super().__str__()

@@ -170,3 +170,35 @@ def test_str_contains_counts_and_metrics():  # :762-772
     text = str(Samples(x=x, log_likelihood=ll, log_prior=lp, log_q=lq, parameters=["a", "b"]))
     for needle in ("No. samples: 4", "No. parameters: 2", "Log evidence:", "Effective sample size:", "Efficiency:"):
         assert needle in text
+
+
+@pytest.mark.parametrize("flat", [True, False])
+def test_basesamples_from_dict(flat):  # :144-152
+    from aspire_b200.samples import BaseSamples, Samples
+
+    ll = np.array([0.1, 0.2, 0.3])
+    bs = BaseSamples(x=np.arange(6.0).reshape(3, 2), log_likelihood=ll, parameters=["a", "b"])
+    bs2 = BaseSamples.from_dict(bs.to_dict(flat=flat))
+    assert isinstance(bs2, BaseSamples) and bs2.parameters == bs.parameters
+    assert np.allclose(bs2.log_likelihood.numpy(), ll) and np.allclose(bs2.x.numpy(), bs.x.numpy())
+    x, l2, lp, lq = make_simple_samples(n=4, d=2, a=0.3)
+    s = Samples(x=x, log_likelihood=l2, log_prior=lp, log_q=lq, parameters=["a", "b"])
+    s2 = Samples.from_dict(s.to_dict(flat=flat))  # weights and evidence are recomputed, not read back
+    assert s2.log_evidence == pytest.approx(s.log_evidence) and np.allclose(s2.weights.numpy(), s.weights.numpy())
+    with pytest.raises(ValueError, match="Parameters must be provided"):
+        BaseSamples.from_dict({"a": np.zeros(3)})
+
+
+def test_to_dataframe():  # :155-160, :309-319, :794-806
+    from aspire_b200.samples import BaseSamples, Samples, SMCSamples
+
+    bs = BaseSamples(x=np.arange(6.0).reshape(3, 2), log_likelihood=np.array([0.1, 0.2, 0.3]), parameters=["a", "b"])
+    df = bs.to_dataframe(include=["log_likelihood"])
+    assert "log_likelihood" in df.columns and "log_prior" not in df.columns
+    assert "a" in df.columns and "b" in df.columns and len(df) == len(bs)
+    assert bs.to_dataframe()["log_prior"].isna().all()
+    x, ll, lp, lq = make_simple_samples(n=4, d=2, a=0.5)
+    df = Samples(x=x, log_likelihood=ll, log_prior=lp, log_q=lq, parameters=["a", "b"]).to_dataframe()
+    assert {"a", "b", "log_w", "log_likelihood"} <= set(df.columns) and len(df) == 4
+    df = SMCSamples(x=x, log_likelihood=ll, log_prior=lp, log_q=lq, beta=0.2, parameters=["a", "b"]).to_dataframe()
+    assert {"a", "b", "log_likelihood"} <= set(df.columns) and len(df) == 4
