@@ -10,7 +10,6 @@ Problem shapes follow SURVEY 8d (C1-C4).
 
 from __future__ import annotations
 
-import ctypes as C
 import math
 
 import numpy as np
