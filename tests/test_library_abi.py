@@ -95,3 +95,24 @@ def test_struct_layouts_match_the_header(tmp_path):
         assert mirror == fields[cname], (cname, mirror, fields[cname])
         for f in mirror:
             assert int(out[f"{cname}.{f}"]) == getattr(cls, f).offset, (cname, f)
+
+
+def test_integration_doc_stub_matches_the_abi():
+    """The ctypes stub INTEGRATION.md shows a maintainer of the reference (section 2) declares the same argument
+    lists as the binding this package uses - and every function it names exists."""
+    import ctypes as C
+
+    from aspire_b200 import _lib
+
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    env = {"_P": C.c_void_p, "_I64": C.c_int64, "_D": C.c_double, "C": C}
+    stubs = re.findall(r"_lib\.(asp_\w+)\.argtypes = \[(.*?)\]", text)
+    assert len(stubs) >= 7
+    for name, args in stubs:
+        assert list(eval("[" + args + "]", {"__builtins__": {}}, env)) == list(_lib.SIGNATURES[name][1]), name  # noqa: S307
+    for name in set(re.findall(r"\b(asp_[a-z0-9_]+)\b", text)):
+        if name.rstrip("_") != name or name in ("asp_status", "asp_density_t", "asp_peer_t", "asp_transform_t",
+                                                "asp_beta_state_t", "asp_pcn_params_t", "asp_flow_t"):
+            continue
+        candidates = [s for s in _lib.SIGNATURES if s == name or s.startswith(name)]
+        assert candidates, f"INTEGRATION.md names {name}, which the header does not declare"
