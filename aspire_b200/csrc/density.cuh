@@ -5,7 +5,7 @@
 // Everything is specialised on the density KIND at compile time: a runtime
 // switch around the group shuffles makes ptxas wrap every SHFL in a
 // WARPSYNC/ENDCOLLECTIVE convergence sequence and blows the register budget
-// (profiles/r1_ncu_v1.md).
+// (seen in the SASS of the first sweep kernel of round 1).
 #pragma once
 #include "common.cuh"
 
