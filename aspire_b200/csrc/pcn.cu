@@ -131,8 +131,8 @@ __device__ __forceinline__ double gamma_mt(uint64_t seed, uint32_t stream, uint6
     const float d = a - (1.0f / 3.0f);
     const float c = 1.0f / sqrtf(9.0f * d);
     for (uint32_t it = 0; it < 64; ++it) {
-        const uint4 r = philox4x32_10((uint32_t)index, (uint32_t)(index >> 32), stream, kGammaBlock0 + it,
-                                      (uint32_t)seed, (uint32_t)(seed >> 32));
+        const uint4 r = philox4x32<kNoiseRounds>((uint32_t)index, (uint32_t)(index >> 32), stream, kGammaBlock0 + it,
+                                                 (uint32_t)seed, (uint32_t)(seed >> 32));
         float z, z1;
         box_muller_f32(r.x, r.y, z, z1);
         const float u = u01_f32(r.z);

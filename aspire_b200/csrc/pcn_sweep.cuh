@@ -51,11 +51,12 @@ __device__ __forceinline__ double ref_quad(const double (&x)[kDPL], const double
 
 // log(u) of move `move`: word (move & 3) of the accept block of stream stream0 + (move & ~3)
 __device__ __forceinline__ uint4 accept_words(uint64_t seed, uint32_t stream0, int move, uint64_t index) {
-    return philox4x32_10((uint32_t)index, (uint32_t)(index >> 32), stream0 + (uint32_t)(move & ~3), kAcceptBlock,
-                         (uint32_t)seed, (uint32_t)(seed >> 32));
+    return philox4x32<kNoiseRounds>((uint32_t)index, (uint32_t)(index >> 32), stream0 + (uint32_t)(move & ~3),
+                                    kAcceptBlock, (uint32_t)seed, (uint32_t)(seed >> 32));
 }
 __device__ __forceinline__ uint4 accept_words(const PhiloxKeys& K, uint32_t stream0, int move, uint64_t index) {
-    return philox4x32_10((uint32_t)index, (uint32_t)(index >> 32), stream0 + (uint32_t)(move & ~3), kAcceptBlock, K);
+    return philox4x32<kNoiseRounds>((uint32_t)index, (uint32_t)(index >> 32), stream0 + (uint32_t)(move & ~3),
+                                    kAcceptBlock, K);
 }
 __device__ __forceinline__ double accept_log_u(const uint4& w, int move) {
     const uint32_t r = (move & 3) == 0 ? w.x : (move & 3) == 1 ? w.y : (move & 3) == 2 ? w.z : w.w;

@@ -113,6 +113,8 @@ __global__ void __launch_bounds__(kTppBlock, tpp_min_blocks<DL>()) pcn_sweep_tpp
     __shared__ double2 s_c01[DT];  // {rho sigma_k, mu_k}
     __shared__ double2 s_c23[DT];  // {a2_k, a1_k}: folded quadratic of the accept test
     __shared__ double2 s_pbox[kPBox ? DT : 1], s_lbox[kLBox ? DT : 1];
+    // final logs: a Gaussian density at x = mu + y is  s0 - 1/2 sum_k (is_k y_k + is_k (mu_k - m_k))^2
+    __shared__ double2 s_fq[DT], s_fp[kPriorQuad ? DT : 1], s_fl[kLikeQuad ? DT : 1];  // {is_k, is_k (mu_k - m_k)}
     __shared__ unsigned int s_acc[kMaxMovesSmem];
     extern __shared__ __align__(16) double s_dyn[];  // mixture: means [DT][ncp], {1/2 is^2, logc}[ncp]; then row staging
 
@@ -156,6 +158,15 @@ __global__ void __launch_bounds__(kTppBlock, tpp_min_blocks<DL>()) pcn_sweep_tpp
         }
         s_c01[j] = make_double2(rho * sg, mu);
         s_c23[j] = make_double2(c2, c1);
+        s_fq[j] = make_double2(isq, isq * (mu - __ldg(A.q.p0 + j)));
+        if constexpr (kPriorQuad) {
+            const double is = __ldg(A.prior.p1 + j);
+            s_fp[j] = make_double2(is, is * (mu - __ldg(A.prior.p0 + j)));
+        }
+        if constexpr (kLikeQuad) {
+            const double is = __ldg(A.like.p1 + j);
+            s_fl[j] = make_double2(is, is * (mu - __ldg(A.like.p0 + j)));
+        }
         if constexpr (kPBox) s_pbox[j] = make_double2(__ldg(A.prior.p0 + j), __ldg(A.prior.p1 + j));
         if constexpr (kLBox) s_lbox[j] = make_double2(__ldg(A.like.p0 + j), __ldg(A.like.p1 + j));
     }
@@ -397,17 +408,20 @@ __global__ void __launch_bounds__(kTppBlock, tpp_min_blocks<DL>()) pcn_sweep_tpp
 #pragma unroll
         for (int k = 0; k < DL; ++k) {
             const int j = lane * DL + k;
-            const double zq = (x[k] - __ldg(A.q.p0 + j)) * __ldg(A.q.p1 + j);
+            const double2 fq = lds2(&s_fq[j]);
+            const double zq = fma(y[k], fq.x, fq.y);
             sq_ = fma(zq, zq, sq_);
             if constexpr (kPriorQuad) {
-                const double z = (x[k] - __ldg(A.prior.p0 + j)) * __ldg(A.prior.p1 + j);
+                const double2 fp = lds2(&s_fp[j]);
+                const double z = fma(y[k], fp.x, fp.y);
                 sp_ = fma(z, z, sp_);
             } else {
                 const double2 b = PBOX(k);
                 pbad |= !(x[k] > b.x && x[k] < b.y);
             }
             if constexpr (kLikeQuad) {
-                const double z = (x[k] - __ldg(A.like.p0 + j)) * __ldg(A.like.p1 + j);
+                const double2 fl = lds2(&s_fl[j]);
+                const double z = fma(y[k], fl.x, fl.y);
                 sl_ = fma(z, z, sl_);
             } else if constexpr (kLBox) {
                 const double2 b = LBOX(k);
@@ -416,9 +430,9 @@ __global__ void __launch_bounds__(kTppBlock, tpp_min_blocks<DL>()) pcn_sweep_tpp
                 double x1;
                 if (k + 1 < DL) x1 = x[(k + 1) % DL];
                 else x1 = (G > 1) ? __shfl_down_sync(0xffffffffu, x[0], 1, G) : 0.0;
-                const double tt = x1 - x[k] * x[k];
+                const double tt = fma(-x[k], x[k], x1);
                 const double u = A.like.s1 - x[k];
-                if (k + 1 < DL || lane < G - 1) r_ += A.like.s0 * tt * tt + u * u;
+                if (k + 1 < DL || lane < G - 1) r_ = fma(u, u, fma(A.like.s0 * tt, tt, r_));
             }
         }
         double lq = A.q.s0 - 0.5 * group_sum<G>(sq_);

@@ -1,4 +1,4 @@
-// Philox4x32-10 (Salmon et al., SC'11) and the uniform / normal conversions.
+// Philox4x32 (Salmon et al., SC'11; 10 rounds, 7 for the sweep noise) and the uniform / normal conversions.
 // Bit layout and conversions are specified in oracle/philox.py; the generator is
 // pinned there against the Random123 known-answer vectors.
 #pragma once
@@ -11,11 +11,20 @@ constexpr uint32_t kPhiloxM1 = 0xCD9E8D57u;
 constexpr uint32_t kPhiloxW0 = 0x9E3779B9u;
 constexpr uint32_t kPhiloxW1 = 0xBB67AE85u;
 constexpr uint32_t kAcceptBlock = 0xFFFFFFFFu;
+// Rounds of the sweep's noise streams (proposal normals, accept uniforms, tpCN gamma variates): Philox4x32-7,
+// the smallest round count reported crush-resistant by Salmon et al.; the uniform / fp64-normal fills keep 10.
+// Measured on B200 (profiles/r2_sweep_experiments.md): 10 -> 7 rounds takes the 10-move sweep from 10.44 to
+// 9.26 ms per 2e7 x 32-D particles.  Spec: oracle/philox.py::NOISE_ROUNDS.
+#ifndef ASP_NOISE_ROUNDS
+#define ASP_NOISE_ROUNDS 7
+#endif
+constexpr int kNoiseRounds = ASP_NOISE_ROUNDS;
 
-__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
-                                               uint32_t k1) {
+template <int R>
+__device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                            uint32_t k1) {
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < R; ++r) {
         const uint64_t p0 = (uint64_t)kPhiloxM0 * c0, p1 = (uint64_t)kPhiloxM1 * c2;  // one IMAD.WIDE each
         const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
         const uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
@@ -28,6 +37,10 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
         k1 += kPhiloxW1;
     }
     return make_uint4(c0, c1, c2, c3);
+}
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                               uint32_t k1) {
+    return philox4x32<10>(c0, c1, c2, c3, k0, k1);
 }
 
 // Round keys precomputed on the host and passed by value in the kernel parameters:
@@ -46,10 +59,10 @@ inline PhiloxKeys philox_keys(uint64_t seed) {
     }
     return K;
 }
-__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                               const PhiloxKeys& K) {
+template <int R>
+__device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys& K) {
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < R; ++r) {
         const uint64_t p0 = (uint64_t)kPhiloxM0 * c0, p1 = (uint64_t)kPhiloxM1 * c2;  // one IMAD.WIDE each
         const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
         const uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
@@ -60,6 +73,10 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
         c3 = lo0;
     }
     return make_uint4(c0, c1, c2, c3);
+}
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                               const PhiloxKeys& K) {
+    return philox4x32<10>(c0, c1, c2, c3, K);
 }
 
 __device__ __forceinline__ float sfu_lg2(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
@@ -88,15 +105,15 @@ __device__ __forceinline__ void box_muller_f32(uint32_t ra, uint32_t rb, float& 
 // four fp32 normals for (element index, stream, block)
 __device__ __forceinline__ void philox_normal4(uint64_t seed, uint32_t stream, uint64_t index, uint32_t block,
                                                float (&z)[4]) {
-    const uint4 r = philox4x32_10((uint32_t)index, (uint32_t)(index >> 32), stream, block, (uint32_t)seed,
-                                  (uint32_t)(seed >> 32));
+    const uint4 r = philox4x32<kNoiseRounds>((uint32_t)index, (uint32_t)(index >> 32), stream, block, (uint32_t)seed,
+                                             (uint32_t)(seed >> 32));
     box_muller_f32(r.x, r.y, z[0], z[1]);
     box_muller_f32(r.z, r.w, z[2], z[3]);
 }
 
 __device__ __forceinline__ void philox_normal4(const PhiloxKeys& K, uint32_t stream, uint64_t index, uint32_t block,
                                                float (&z)[4]) {
-    const uint4 r = philox4x32_10((uint32_t)index, (uint32_t)(index >> 32), stream, block, K);
+    const uint4 r = philox4x32<kNoiseRounds>((uint32_t)index, (uint32_t)(index >> 32), stream, block, K);
     box_muller_f32(r.x, r.y, z[0], z[1]);
     box_muller_f32(r.z, r.w, z[2], z[3]);
 }

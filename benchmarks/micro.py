@@ -144,6 +144,7 @@ def sweep(args):
         if args.only and args.only != name:
             continue
         n = args.n or n
+        dims = args.dims or dims
         pg = mk[name](dims, device=dev)
         x = ops.philox_normal(5, 0, n, dims, dev, mean=pg["q"].mean, sigma=pg["q"].sigma)
         lq, lp, ll = pg["q"].log_prob(x), pg["prior"].log_prob(x), pg["like"].log_prob(x)
@@ -335,6 +336,7 @@ if __name__ == "__main__":
     ap.add_argument("--n", type=int, default=0)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--moves", type=int, default=10)
+    ap.add_argument("--dims", type=int, default=0)
     ap.add_argument("--only", default="")
     ap.add_argument("--dump", default="")
     a = ap.parse_args()

@@ -147,7 +147,8 @@ def gamma_mt_f32(seed: int, stream: int, index, a: float, max_iter: int = 64) ->
     for it in range(max_iter):
         if not todo.any():
             break
-        r = philox.philox4x32(c0, c1, np.uint32(stream), np.uint32((GAMMA_BLOCK0 + it) & 0xFFFFFFFF), k0, k1)
+        r = philox.philox4x32(c0, c1, np.uint32(stream), np.uint32((GAMMA_BLOCK0 + it) & 0xFFFFFFFF), k0, k1,
+                              rounds=philox.NOISE_ROUNDS)
         z, _ = philox.box_muller_f32(r[0], r[1])
         u = philox._u01_f32(r[2])
         t = (np.float32(1.0) + c * z).astype(np.float32)
