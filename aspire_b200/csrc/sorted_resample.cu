@@ -1,0 +1,351 @@
+// Multinomial resampling with SORTED uniforms (throughput mode of SMCSamples.resample,
+// /root/reference/src/aspire/samples.py:1251-1287: idx = searchsorted(cumsum(w), rng.random(M), 'right')).
+//
+// The reference draws M iid uniforms and binary-searches each one: M dependent chains of ~27 random reads over a
+// CDF far larger than L2 (4.2 ms + 1.1 ms for a guide table at M = N = 1e8).  Only the MULTISET of ancestors
+// matters - the particles are exchangeable - and the order statistics of M iid uniforms are the normalised
+// partial sums of M + 1 iid exponentials.  So in throughput mode the uniforms are generated already sorted:
+//
+//   q_j   = floor(-ln(1 - u_j) 2^26), u_j the Philox uniform stream          (spacing_math.cuh; j = 0 .. M)
+//   S_j   = q_0 + ... + q_j  (integers: exact, any scan order, any sharding),   total = S_M
+//   T_k   = rint(cdf_k * total)                                               (cdf: the exact fp64 CDF, as before)
+//   idx_j = #{k : T_k <= S_j}  (clamped to N - 1)                             == searchsorted(T, S, 'right')
+//
+// i.e. the same searchsorted-right of the same CDF, at the sorted uniforms S_j / total.  Two sorted sequences are
+// merged by streaming: the slot tile of a block and the CDF tile(s) its slots fall into meet in shared memory, every
+// HBM access is sequential, and the ancestors come out sorted - the gather of the following sweep reads ascending
+// rows.  Slot j is keyed by its rank among the uniforms, so a GPU that owns the CDF slice [k0, k1) owns the
+// contiguous slot range {j : T_{k0-1} <= S_j < T_{k1-1}} and can regenerate those spacings itself: no uniform and
+// no index crosses NVLink.  Supplied uniforms / PCG64 parity mode keep the guided search (search_gather.cu).
+// Spec: oracle/sorted_resample.py.
+#include "common.cuh"
+#include "philox.cuh"
+#include "spacing_math.cuh"
+
+namespace asp {
+
+constexpr int kSpBlock = 256;
+constexpr int kSpItems = kSpacingTile / kSpBlock;  // 8 consecutive slots per thread
+
+__device__ __forceinline__ uint64_t warp_scan_incl_u64(uint64_t v) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint64_t t = __shfl_up_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) >= o) v += t;
+    }
+    return v;
+}
+
+// block-wide exclusive scan of one value per thread (kSpBlock threads); total returned through `total`
+__device__ __forceinline__ uint64_t block_scan_excl_u64(uint64_t v, uint64_t* s_warp /*[8]*/, uint64_t& total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint64_t incl = warp_scan_incl_u64(v);
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    uint64_t base = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < kSpBlock / 32; ++w) {
+        const uint64_t t = s_warp[w];
+        if (w < wid) base += t;
+        tot += t;
+    }
+    total = tot;
+    __syncthreads();
+    return base + incl - v;
+}
+
+// q for elements [j0, j0 + tiles * 2048) (j0 a multiple of 2048; elements > m_total get 0) and their tile sums
+__global__ void __launch_bounds__(kSpBlock) spacings_kernel(PhiloxKeys K, uint32_t stream, int64_t j0, int64_t n_tiles,
+                                                            int64_t m_total, uint32_t* __restrict__ q,
+                                                            unsigned long long* __restrict__ tile_sums) {
+    __shared__ uint64_t s_warp[kSpBlock / 32];
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t e0 = j0 + tile * kSpacingTile + (int64_t)threadIdx.x * kSpItems;  // global element index, even
+        uint32_t v[kSpItems];
+        uint64_t sum = 0;
+#pragma unroll
+        for (int b = 0; b < kSpItems / 2; ++b) {
+            const uint64_t blk = (uint64_t)(e0 >> 1) + b;  // Philox block of elements (2 blk, 2 blk + 1): asp_philox_uniform's layout
+            const uint4 r = philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), stream, 0u, K);
+            const uint64_t ka = ((((uint64_t)r.x) << 32) | r.y) >> 11, kb = ((((uint64_t)r.z) << 32) | r.w) >> 11;
+            v[2 * b] = e0 + 2 * b <= m_total ? spacing_q(ka) : 0u;
+            v[2 * b + 1] = e0 + 2 * b + 1 <= m_total ? spacing_q(kb) : 0u;
+            sum += (uint64_t)v[2 * b] + v[2 * b + 1];
+        }
+        uint4* dst = reinterpret_cast<uint4*>(q + tile * kSpacingTile + threadIdx.x * kSpItems);
+        dst[0] = make_uint4(v[0], v[1], v[2], v[3]);
+        dst[1] = make_uint4(v[4], v[5], v[6], v[7]);
+        uint64_t tot;
+        (void)block_scan_excl_u64(sum, s_warp, tot);
+        if (threadIdx.x == 0) tile_sums[tile] = tot;
+    }
+}
+
+// exclusive prefix of the tile sums and the grand total (one block; integer sums: the order is immaterial)
+__global__ void __launch_bounds__(1024) tile_scan_kernel(const unsigned long long* __restrict__ sums, int64_t n_tiles,
+                                                         unsigned long long* __restrict__ prefix,
+                                                         unsigned long long* __restrict__ total) {
+    __shared__ uint64_t s_part[1024];
+    const int64_t per = (n_tiles + blockDim.x - 1) / blockDim.x;
+    const int64_t a = (int64_t)threadIdx.x * per, b = a + per < n_tiles ? a + per : n_tiles;
+    uint64_t s = 0;
+    for (int64_t t = a; t < b; ++t) s += sums[t];
+    s_part[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t run = 0;
+        for (int i = 0; i < (int)blockDim.x; ++i) {
+            const uint64_t t = s_part[i];
+            s_part[i] = run;
+            run += t;
+        }
+        *total = run;
+    }
+    __syncthreads();
+    uint64_t run = s_part[threadIdx.x];
+    for (int64_t t = a; t < b; ++t) {
+        prefix[t] = run;
+        run += sums[t];
+    }
+}
+
+// largest CDF tile ct in [0, n_ct) whose first threshold is <= s (0 if none): 32-ary search by one warp
+__device__ __forceinline__ int64_t coarse_tile(const double* __restrict__ cdf, int64_t n_ct, double total, uint64_t s) {
+    const int lane = threadIdx.x & 31;
+    int64_t lo = 0, hi = n_ct;  // answer in [lo, hi): first(lo) <= s or lo == 0
+    while (hi - lo > 1) {
+        const int64_t span = hi - lo, step = (span + 31) / 32;
+        const int64_t t = lo + (int64_t)(lane + 1) * step;  // probes lo + step, lo + 2 step, ...
+        const bool le = t < hi && spacing_threshold(__ldg(cdf + t * kSpacingTile), total) <= s;
+        const unsigned int votes = __ballot_sync(0xffffffffu, le);  // monotone: a prefix of lanes
+        const int c = __popc(votes);
+        const int64_t new_lo = lo + (int64_t)c * step;
+        const int64_t new_hi = new_lo + step < hi ? new_lo + step : hi;
+        lo = new_lo;
+        hi = new_hi;
+    }
+    return lo;
+}
+
+// idx[j - j_lo] = min(#{k < n_cdf : T_k <= S_j}, n_cdf - 1) for the slots j_lo <= j < j_hi; q[0] is element q_j0
+__global__ void __launch_bounds__(kSpBlock) search_sorted_kernel(const double* __restrict__ cdf, int64_t n_cdf,
+                                                                 const uint32_t* __restrict__ q, int64_t q_j0,
+                                                                 const unsigned long long* __restrict__ tile_prefix,
+                                                                 const unsigned long long* __restrict__ total_p,
+                                                                 int64_t j_lo, int64_t j_hi,
+                                                                 int64_t* __restrict__ idx) {
+    __shared__ uint64_t s_S[kSpacingTile];
+    __shared__ uint64_t s_T[kSpacingTile];
+    __shared__ uint64_t s_warp[kSpBlock / 32];
+    __shared__ int64_t s_ct;
+    const double total = (double)*total_p;
+    const int64_t n_ct = (n_cdf + kSpacingTile - 1) / kSpacingTile;
+    const int64_t gt = j_lo / kSpacingTile + blockIdx.x;  // global slot tile
+    const int64_t tile0 = gt * kSpacingTile;
+    // ---- partial sums of this slot tile
+    uint64_t S[kSpItems];
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(q + (tile0 - q_j0) + threadIdx.x * kSpItems);
+        const uint4 a = __ldg(src), b = __ldg(src + 1);
+        const uint32_t v[kSpItems] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        uint64_t run = 0;
+#pragma unroll
+        for (int i = 0; i < kSpItems; ++i) {
+            run += v[i];
+            S[i] = run;
+        }
+        uint64_t tot;
+        const uint64_t base = block_scan_excl_u64(run, s_warp, tot) + tile_prefix[gt];
+#pragma unroll
+        for (int i = 0; i < kSpItems; ++i) {
+            S[i] += base;
+            s_S[threadIdx.x * kSpItems + i] = S[i];
+        }
+    }
+    __syncthreads();
+    const int first = (int)(j_lo > tile0 ? j_lo - tile0 : 0);
+    const int end = (int)(j_hi - tile0 < kSpacingTile ? j_hi - tile0 : kSpacingTile);
+    int64_t anc[kSpItems];
+#pragma unroll
+    for (int i = 0; i < kSpItems; ++i) anc[i] = n_cdf - 1;
+    int cur = first;
+    int64_t ct = -1;
+    while (cur < end) {
+        const uint64_t sc = s_S[cur];
+        // the CDF tile holding the ancestor of slot `cur`: the next tile if it still covers sc, else a search
+        bool next_ok = false;
+        if (ct >= 0 && ct + 1 < n_ct) {
+            next_ok = ct + 2 >= n_ct || sc < spacing_threshold(__ldg(cdf + (ct + 2) * kSpacingTile), total);
+        }
+        if (next_ok) {
+            ct = ct + 1;
+        } else {
+            if (threadIdx.x < 32) {
+                const int64_t c = coarse_tile(cdf, n_ct, total, sc);
+                if (threadIdx.x == 0) s_ct = c;
+            }
+            __syncthreads();
+            ct = s_ct;
+        }
+        const int64_t k0 = ct * kSpacingTile;
+        const int cnt = (int)(n_cdf - k0 < kSpacingTile ? n_cdf - k0 : kSpacingTile);
+#pragma unroll
+        for (int i = 0; i < kSpItems; ++i) {
+            const int e = i * kSpBlock + threadIdx.x;
+            s_T[e] = e < cnt ? spacing_threshold(ld_stream(cdf + k0 + e), total) : ~0ull;
+        }
+        const bool last_tile = ct + 1 >= n_ct;
+        const uint64_t t_next = last_tile ? ~0ull : spacing_threshold(__ldg(cdf + k0 + kSpacingTile), total);
+        __syncthreads();
+        // slots with S < t_next have their ancestor in [k0, k0 + cnt] (k0 + cnt: the first entry of the next tile)
+        int hint = 0;
+#pragma unroll
+        for (int i = 0; i < kSpItems; ++i) {
+            const int ls = threadIdx.x * kSpItems + i;
+            if (ls >= cur && ls < end && (S[i] < t_next || last_tile)) {
+                const uint64_t s = S[i];
+                int lo = hint, hi = cnt, step = 1;  // count of thresholds <= s, in [lo, hi]
+                while (lo + step <= hi && s_T[lo + step - 1] <= s) {
+                    lo += step;
+                    step <<= 1;
+                }
+                if (lo + step - 1 < hi) hi = lo + step - 1;
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (s_T[mid - 1] <= s) lo = mid;
+                    else hi = mid - 1;
+                }
+                hint = lo;
+                const int64_t a = k0 + lo;
+                anc[i] = a < n_cdf - 1 ? a : n_cdf - 1;
+            }
+        }
+        // first slot not resolved by this tile: lower_bound(S, t_next)
+        int new_cur = end;
+        if (!last_tile) {
+            int lo = cur, hi = end;  // S[lo-1] < t_next <= S[hi] conceptually
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (s_S[mid] < t_next) lo = mid + 1;
+                else hi = mid;
+            }
+            new_cur = lo;
+        }
+        __syncthreads();  // s_T and s_ct are rewritten by the next round
+        cur = new_cur;
+    }
+#pragma unroll
+    for (int i = 0; i < kSpItems; ++i) {
+        const int ls = threadIdx.x * kSpItems + i;
+        if (ls >= first && ls < end) idx[tile0 + ls - j_lo] = anc[i];
+    }
+}
+
+// #{j < m : S_j < t}: the first slot whose partial sum reaches t (shard boundaries).  One block.
+__global__ void __launch_bounds__(kSpBlock) lower_bound_kernel(const uint32_t* __restrict__ q, int64_t q_j0, int64_t q_tiles,
+                                                               const unsigned long long* __restrict__ tile_prefix,
+                                                               int64_t n_tiles, int64_t m, const unsigned long long* t_p,
+                                                               int n_t, long long* __restrict__ out) {
+    __shared__ uint64_t s_warp[kSpBlock / 32];
+    __shared__ int s_count;
+    for (int it = 0; it < n_t; ++it) {
+        const uint64_t t = t_p[it];
+        // tile: the last one whose exclusive prefix is < t
+        int64_t lo = 0, hi = n_tiles;  // prefix[lo] < t (prefix[0] = 0; t == 0 handled below)
+        while (hi - lo > 1) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (tile_prefix[mid] < t) lo = mid;
+            else hi = mid;
+        }
+        if (threadIdx.x == 0) s_count = 0;
+        __syncthreads();
+        int64_t res;
+        if (t == 0) {
+            res = 0;
+        } else {
+            const int64_t lt = lo - q_j0 / kSpacingTile;  // local tile of q
+            if (lt < 0 || lt >= q_tiles) {
+                res = -1;  // the caller's q window does not cover the tile
+            } else {
+                const uint4* src = reinterpret_cast<const uint4*>(q + lt * kSpacingTile + threadIdx.x * kSpItems);
+                const uint4 a = src[0], b = src[1];
+                const uint32_t v[kSpItems] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                uint64_t run = 0, S[kSpItems];
+#pragma unroll
+                for (int i = 0; i < kSpItems; ++i) {
+                    run += v[i];
+                    S[i] = run;
+                }
+                uint64_t tot;
+                const uint64_t base = block_scan_excl_u64(run, s_warp, tot) + tile_prefix[lo];
+                int c = 0;
+#pragma unroll
+                for (int i = 0; i < kSpItems; ++i) c += (S[i] + base < t) ? 1 : 0;
+                atomicAdd(&s_count, c);
+                __syncthreads();
+                res = lo * kSpacingTile + s_count;
+            }
+        }
+        if (res > m) res = m;
+        if (threadIdx.x == 0) out[it] = res;
+        __syncthreads();
+    }
+}
+
+}  // namespace asp
+
+using namespace asp;
+
+extern "C" {
+
+int64_t asp_sorted_tiles(int64_t m_total) { return (m_total + 1 + kSpacingTile - 1) / kSpacingTile; }
+
+int asp_sorted_spacings(uint64_t seed, uint32_t stream_id, int64_t j0, int64_t n_tiles, int64_t m_total, uint32_t* d_q,
+                        unsigned long long* d_tile_sums, void* stream) {
+    ASP_DEVICE_OR_RETURN();
+    ASP_REQUIRE(d_q && d_tile_sums, "null pointer");
+    ASP_REQUIRE(m_total > 0 && n_tiles > 0, "sizes must be positive");
+    ASP_REQUIRE(j0 >= 0 && j0 % kSpacingTile == 0, "j0 must be a multiple of 2048");
+    const int64_t cap = (int64_t)kNumSMs * 8;
+    spacings_kernel<<<(int)(n_tiles < cap ? n_tiles : cap), kSpBlock, 0, (cudaStream_t)stream>>>(
+        philox_keys(seed), stream_id, j0, n_tiles, m_total, d_q, d_tile_sums);
+    return check_launch("asp_sorted_spacings");
+}
+
+int asp_sorted_tile_scan(const unsigned long long* d_tile_sums, int64_t n_tiles, unsigned long long* d_tile_prefix,
+                         unsigned long long* d_total, void* stream) {
+    ASP_DEVICE_OR_RETURN();
+    ASP_REQUIRE(d_tile_sums && d_tile_prefix && d_total, "null pointer");
+    ASP_REQUIRE(n_tiles > 0, "n_tiles must be positive");
+    tile_scan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(d_tile_sums, n_tiles, d_tile_prefix, d_total);
+    return check_launch("asp_sorted_tile_scan");
+}
+
+int asp_search_sorted(const double* d_cdf, int64_t n_cdf, const uint32_t* d_q, int64_t q_j0,
+                      const unsigned long long* d_tile_prefix, const unsigned long long* d_total, int64_t j_lo,
+                      int64_t j_hi, int64_t* d_idx, void* stream) {
+    ASP_DEVICE_OR_RETURN();
+    ASP_REQUIRE(d_cdf && d_q && d_tile_prefix && d_total && d_idx, "null pointer");
+    ASP_REQUIRE(n_cdf > 0, "n_cdf must be positive");
+    ASP_REQUIRE(q_j0 >= 0 && q_j0 % kSpacingTile == 0, "q_j0 must be a multiple of 2048");
+    ASP_REQUIRE(j_lo >= q_j0 && j_hi >= j_lo, "bad slot range");
+    if (j_hi == j_lo) return ASP_OK;
+    const int64_t tiles = (j_hi - 1) / kSpacingTile - j_lo / kSpacingTile + 1;
+    ASP_REQUIRE(tiles < (1ll << 31), "too many slot tiles");
+    search_sorted_kernel<<<(int)tiles, kSpBlock, 0, (cudaStream_t)stream>>>(d_cdf, n_cdf, d_q, q_j0, d_tile_prefix,
+                                                                          d_total, j_lo, j_hi, d_idx);
+    return check_launch("asp_search_sorted");
+}
+
+int asp_sorted_lower_bound(const uint32_t* d_q, int64_t q_j0, int64_t q_tiles, const unsigned long long* d_tile_prefix,
+                           int64_t n_tiles, int64_t m_total, const unsigned long long* d_thresholds, int32_t n_thresholds,
+                           long long* d_out, void* stream) {
+    ASP_DEVICE_OR_RETURN();
+    ASP_REQUIRE(d_q && d_tile_prefix && d_thresholds && d_out, "null pointer");
+    ASP_REQUIRE(n_tiles > 0 && n_thresholds > 0, "sizes must be positive");
+    lower_bound_kernel<<<1, kSpBlock, 0, (cudaStream_t)stream>>>(d_q, q_j0, q_tiles, d_tile_prefix, n_tiles, m_total,
+                                                                d_thresholds, n_thresholds, d_out);
+    return check_launch("asp_sorted_lower_bound");
+}
+
+}  // extern "C"

@@ -306,6 +306,63 @@ def search_multinomial(cdf, u, guided: bool | None = None) -> torch.Tensor:
     return idx
 
 
+SPACING_TILE = 2048
+
+
+class SortedSpacings:
+    """Integer exponential spacings of ``m`` sorted uniforms (``oracle/sorted_resample.py``): ``q`` covers the
+    elements ``[j0, j0 + tiles * 2048)``, ``tile_prefix`` / ``total`` are global."""
+
+    def __init__(self, seed: int, stream_id: int, m: int, device, j0: int = 0, n_tiles: int | None = None):
+        lib = _lib.load()
+        self.seed, self.stream_id, self.m, self.j0 = int(seed) & 0xFFFFFFFFFFFFFFFF, stream_id & 0xFFFFFFFF, int(m), int(j0)
+        self.tiles_total = int(lib.asp_sorted_tiles(self.m))
+        self.n_tiles = self.tiles_total - self.j0 // SPACING_TILE if n_tiles is None else int(n_tiles)
+        self.q = torch.empty(self.n_tiles * SPACING_TILE, dtype=torch.int32, device=device)
+        self.tile_sums = torch.empty(self.n_tiles, dtype=torch.int64, device=device)
+        check(lib.asp_sorted_spacings(self.seed, self.stream_id, self.j0, self.n_tiles, self.m, self.q.data_ptr(),
+                                      self.tile_sums.data_ptr(), _stream()), "asp_sorted_spacings")
+        self.tile_prefix = None
+        self.total = None
+
+    def scan(self, all_tile_sums: torch.Tensor | None = None):
+        """Exclusive prefix over ALL tiles (``all_tile_sums``: the all-gathered sums when sharded)."""
+        sums = self.tile_sums if all_tile_sums is None else all_tile_sums
+        if sums.numel() != self.tiles_total:
+            raise AspireB200Error("tile sums do not cover all tiles")
+        self.tile_prefix = torch.empty(self.tiles_total, dtype=torch.int64, device=sums.device)
+        self.total = torch.empty(1, dtype=torch.int64, device=sums.device)
+        check(_lib.load().asp_sorted_tile_scan(sums.data_ptr(), self.tiles_total, self.tile_prefix.data_ptr(),
+                                               self.total.data_ptr(), _stream()), "asp_sorted_tile_scan")
+        return self
+
+    def search(self, cdf, j_lo: int = 0, j_hi: int | None = None) -> torch.Tensor:
+        """Ancestors (indices into ``cdf``) of the slots ``[j_lo, j_hi)``: sorted ascending."""
+        cdf = _f64(cdf, "cdf")
+        j_hi = self.m if j_hi is None else int(j_hi)
+        idx = torch.empty(j_hi - j_lo, dtype=torch.int64, device=cdf.device)
+        if j_hi > j_lo:
+            check(_lib.load().asp_search_sorted(cdf.data_ptr(), cdf.numel(), self.q.data_ptr(), self.j0,
+                                                self.tile_prefix.data_ptr(), self.total.data_ptr(), int(j_lo), j_hi,
+                                                idx.data_ptr(), _stream()), "asp_search_sorted")
+        return idx
+
+    def lower_bound(self, thresholds: torch.Tensor) -> torch.Tensor:
+        """``#{j < m : S_j < t}`` for each (int64 device) threshold."""
+        out = torch.empty(thresholds.numel(), dtype=torch.int64, device=thresholds.device)
+        check(_lib.load().asp_sorted_lower_bound(self.q.data_ptr(), self.j0, self.n_tiles, self.tile_prefix.data_ptr(),
+                                                 self.tiles_total, self.m, thresholds.data_ptr(), thresholds.numel(),
+                                                 out.data_ptr(), _stream()), "asp_sorted_lower_bound")
+        return out
+
+
+def search_multinomial_sorted(cdf, seed: int, stream_id: int, m: int) -> torch.Tensor:
+    """Multinomial resampling at ``m`` sorted uniforms generated on the device (throughput mode): the same
+    ``searchsorted(cdf, u, 'right')`` as :func:`search_multinomial`, ancestors ascending."""
+    cdf = _f64(cdf, "cdf")
+    return SortedSpacings(seed, stream_id, m, cdf.device).scan().search(cdf)
+
+
 def search_systematic(cdf, u0: float, m: int, j0: int = 0, m_total: int | None = None) -> torch.Tensor:
     cdf = _f64(cdf, "cdf")
     m_total = m if m_total is None else m_total

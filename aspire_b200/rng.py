@@ -12,10 +12,11 @@ The reference passes a ``numpy.random.Generator`` (or ``orng.ArrayRNG``) around
                    host generator is advanced by the same count, so the stream, and hence
                    the ancestors, are bit-identical to the reference's with no host draw or
                    upload.  Scalars and normals still come from the host generator.
-``PhiloxRNG``      device-side counter-based Philox4x32-10 (``asp_philox_*`` and
-                   the in-kernel stream of ``asp_pcn_sweep``) - THROUGHPUT mode;
-                   results are independent of launch geometry and of how
-                   particles are sharded across GPUs.
+``PhiloxRNG``      device-side counter-based Philox4x32 (``asp_philox_*``, the sorted
+                   resampling uniforms of ``asp_sorted_spacings`` and the in-kernel
+                   stream of ``asp_pcn_sweep``) - THROUGHPUT mode; results are
+                   independent of launch geometry and of how particles are sharded
+                   across GPUs.
 """
 
 from __future__ import annotations
@@ -47,6 +48,12 @@ class PhiloxRNG:
     def uniform(self, n: int, device, index0: int = 0) -> torch.Tensor:
         return ops.philox_uniform(self.seed, self.next_stream(), n, device, index0=index0)
 
+    def multinomial_ancestors(self, cdf: torch.Tensor, m: int) -> torch.Tensor:
+        """``searchsorted(cdf, u, 'right')`` at ``m`` iid uniforms.  Throughput mode generates the uniforms already
+        sorted (``asp_sorted_spacings`` / ``asp_search_sorted``, ``oracle/sorted_resample.py``): the same multiset
+        law, ancestors ascending, every HBM access sequential."""
+        return ops.search_multinomial_sorted(cdf, self.seed, self.next_stream(), m)
+
     def scalar_uniform(self) -> float:
         # one host-side Philox-free draw is enough for the systematic offset: derive it from the seed/stream
         s = self.next_stream()
@@ -68,6 +75,10 @@ class HostGenerator:
 
     def uniform(self, n: int, device, index0: int = 0) -> torch.Tensor:
         return torch.from_numpy(self.rng.random(n)).to(device)
+
+    def multinomial_ancestors(self, cdf: torch.Tensor, m: int) -> torch.Tensor:
+        """The reference's draw order: ``searchsorted(cdf, rng.random(m), 'right')`` (``Generator.choice``)."""
+        return ops.search_multinomial(cdf, self.uniform(m, cdf.device))
 
     def scalar_uniform(self) -> float:
         return float(self.rng.random())

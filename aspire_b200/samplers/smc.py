@@ -313,7 +313,7 @@ class SMCSampler(Sampler):
         if self.resampling == "systematic":
             idx = ops.search_systematic(cdf, self.rng.scalar_uniform(), n)
         else:
-            idx = ops.search_multinomial(cdf, self.rng.uniform(n, self.device))
+            idx = self.rng.multinomial_ancestors(cdf, n)
         del p, cdf
         mark("resample")
         samples = self.mutate(samples, beta, idx=idx, out=out, mark=mark)
@@ -469,19 +469,26 @@ class SMCSampler(Sampler):
             return self._mutate_preconditioned(particles, beta, n_moves, idx, mark)
         n = len(particles) if idx is None else idx.numel()
         dims = self.dims
-        # reference measure of the pCN proposal: moments of the (resampled) ensemble; beyond
-        # `moment_particles` rows (default 2^22) the first rows - an iid sample of it - are used
+        # reference measure of the pCN proposal: moments of the (resampled) ensemble; beyond `moment_particles`
+        # rows (default 2^22) every (n // moment_particles)-th offspring is used - the ancestors of the sorted
+        # resampler are ascending, so a strided sample is spread over the whole genealogy (a prefix would not be)
         m_use = min(n, int(self.sampler_kwargs.get("moment_particles", 1 << 22)))
-        if idx is not None:
-            mom = ops.weighted_moments(particles.x, idx=idx[:m_use])
+        stride = max(n // max(m_use, 1), 1)
+        if stride > 1:
+            sub = (idx[::stride] if idx is not None
+                   else torch.arange(0, n, stride, dtype=torch.int64, device=self.device)).contiguous()
+            mom = ops.weighted_moments(particles.x, idx=sub)
+        elif idx is not None:
+            mom = ops.weighted_moments(particles.x, idx=idx)
         else:
-            mom = ops.weighted_moments(particles.x[:m_use])
+            mom = ops.weighted_moments(particles.x)
         mu, sigma = ops.moments_to_mu_sigma(mom, dims)
         sigma = torch.clamp_min(sigma, 1e-150)
         tpcn = getattr(self, "step_fn", "pcn") == "tpcn"
         nu = 0.0
         if tpcn:  # Student-t reference measure t_nu(mu, diag sigma^2) fitted to (a sample of) the ensemble
-            rows = particles.x[:min(m_use, 1 << 20)] if idx is None else particles.x[idx[:min(m_use, 1 << 20)]]
+            t_stride = max(n // min(m_use, 1 << 20), 1)
+            rows = particles.x[::t_stride] if idx is None else particles.x[idx[::t_stride]]
             mu, sigma, nu = fit_student_t_diag(rows, mu, sigma)
             self.history.__dict__.setdefault("tpcn_nu", []).append(nu)
         if mark:

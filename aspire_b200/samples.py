@@ -341,7 +341,7 @@ class SMCSamples(BaseSamples):
         cdf = ops.cdf_exact(p, tile_stats=tiles)
         src = as_uniform_source(rng)
         if method == "multinomial":
-            return ops.search_multinomial(cdf, src.uniform(n_samples, self.device))
+            return src.multinomial_ancestors(cdf, n_samples)
         if method == "systematic":
             return ops.search_systematic(cdf, src.scalar_uniform(), n_samples)
         raise ValueError(f"unknown resampling method {method!r}")

@@ -232,6 +232,34 @@ size_t asp_search_systematic_workspace_bytes(int64_t m);
 int asp_search_systematic(const double* d_cdf, int64_t n_cdf, double u0, int64_t j0, int64_t m,
                           int64_t m_total, int64_t* d_idx, void* ws, void* stream);
 
+/* ---- multinomial resampling with sorted uniforms (throughput mode of K6) ------------------
+ * SMCSamples.resample, src/aspire/samples.py:1251-1287 (idx = searchsorted(cumsum(w), rng.random(M), 'right')):
+ * only the multiset of ancestors matters, and the order statistics of M iid uniforms are the normalised
+ * partial sums of M + 1 iid exponentials.  Element j = 0 .. m_total draws q_j = floor(-ln(1 - u_j) 2^26) from
+ * the Philox uniform stream (seed, stream_id) - asp_philox_uniform's stream; S_j = q_0 + ... + q_j are integers,
+ * so tiles, blocks and ranks may be summed in any order; total = S_{m_total};
+ *     idx_j = min(#{k : rint(cdf_k * total) <= S_j}, n_cdf - 1)         (sorted: idx_j <= idx_{j+1})
+ * Spec: oracle/sorted_resample.py.  Tiles are 2048 elements, aligned to the global element index.
+ *   asp_sorted_tiles(m_total)   tiles covering elements 0 .. m_total
+ *   asp_sorted_spacings         d_q[n_tiles * 2048] (uint32) and d_tile_sums[n_tiles] (uint64) for the elements
+ *                               j0 .. j0 + n_tiles * 2048 - 1 (j0 a multiple of 2048; elements > m_total give 0)
+ *   asp_sorted_tile_scan        exclusive prefix of ALL tile sums (after an all-gather when sharded) + total
+ *   asp_search_sorted           ancestors of the slots j_lo <= j < j_hi within the CDF (slice) d_cdf[n_cdf];
+ *                               d_q[0] is element q_j0; d_tile_prefix is indexed by the global tile
+ *   asp_sorted_lower_bound      d_out[i] = #{j < m_total : S_j < d_thresholds[i]} (shard boundaries; -1 if the
+ *                               tile it falls in is outside the d_q window) */
+int64_t asp_sorted_tiles(int64_t m_total);
+int asp_sorted_spacings(uint64_t seed, uint32_t stream_id, int64_t j0, int64_t n_tiles, int64_t m_total, uint32_t* d_q,
+                        unsigned long long* d_tile_sums, void* stream);
+int asp_sorted_tile_scan(const unsigned long long* d_tile_sums, int64_t n_tiles, unsigned long long* d_tile_prefix,
+                         unsigned long long* d_total, void* stream);
+int asp_search_sorted(const double* d_cdf, int64_t n_cdf, const uint32_t* d_q, int64_t q_j0,
+                      const unsigned long long* d_tile_prefix, const unsigned long long* d_total, int64_t j_lo,
+                      int64_t j_hi, int64_t* d_idx, void* stream);
+int asp_sorted_lower_bound(const uint32_t* d_q, int64_t q_j0, int64_t q_tiles, const unsigned long long* d_tile_prefix,
+                           int64_t n_tiles, int64_t m_total, const unsigned long long* d_thresholds, int32_t n_thresholds,
+                           long long* d_out, void* stream);
+
 /* ---- row gather (K7) ----------------------------------------------------
  * x[idx], logL[idx], logP[idx], logq[idx] - src/aspire/samples.py:1279-1287.
  * Any of the three log pointers (and its output) may be NULL. */

@@ -120,6 +120,12 @@ class Doubles:
         return torch.searchsorted(cdf, u, right=True).clamp_max(cdf.numel() - 1)
 
     @staticmethod
+    def search_multinomial_sorted(cdf, seed, stream_id, m):
+        from oracle import sorted_resample
+
+        return torch.from_numpy(sorted_resample.resample(cdf.numpy(), seed, stream_id, m))
+
+    @staticmethod
     def search_systematic(cdf, u0, n):
         u = (torch.arange(n, dtype=F64) + u0) / n
         return torch.searchsorted(cdf, u, right=True).clamp_max(cdf.numel() - 1)
@@ -240,7 +246,7 @@ class Doubles:
 
 
 NAMES = ["_f64", "_i64", "_stream", "device_check", "reweight", "ess_sums", "beta_search", "smc_weights",
-         "importance_weights", "cdf_exact", "search_multinomial", "search_systematic", "gather_rows",
+         "importance_weights", "cdf_exact", "search_multinomial", "search_multinomial_sorted", "search_systematic", "gather_rows",
          "weighted_moments", "moments_to_mu_sigma", "philox_uniform", "philox_normal", "pcg64_uniform", "make_pcn_params",
          "tpcn_scales", "pcn_propose", "pcn_accept", "pcn_sweep", "pcn_propose_eval_supported", "logdensity",
          "transform_apply"]
