@@ -172,8 +172,9 @@ SIGNATURES = {
     "asp_sorted_tiles": (_I64, [_I64]),
     "asp_sorted_spacings": (C.c_int, [C.c_uint64, C.c_uint32, _I64, _I64, _I64, _P, _P, _P]),
     "asp_sorted_tile_scan": (C.c_int, [_P, _I64, _P, _P, _P]),
-    "asp_search_sorted": (C.c_int, [_P, _I64, _P, _I64, _P, _P, _I64, _I64, _P, _P]),
-    "asp_sorted_lower_bound": (C.c_int, [_P, _I64, _I64, _P, _I64, _I64, _P, _I32, _P, _P]),
+    "asp_search_sorted_workspace_bytes": (C.c_size_t, [_I64]),
+    "asp_search_sorted": (C.c_int, [_P, _I64, _P, _I64, _P, _P, _I64, _I64, _P, _P, _P]),
+    "asp_sorted_lower_bound": (C.c_int, [C.c_uint64, C.c_uint32, _P, _I64, _I64, _P, _I32, _P, _P]),
     "asp_gather_rows": (C.c_int, [_P, _I32, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _P]),
     "asp_moments_workspace_bytes": (C.c_size_t, [_I32]),
     "asp_weighted_moments": (C.c_int, [_P, _I32, _P, _P, _I64, _D, _D, _P, _P, _P]),
@@ -234,7 +235,7 @@ KERNELS_PER_CALL = {"asp_importance_weights": 3, "asp_cdf_exact": 6, "asp_cdf_ti
                     "asp_cdf_set_tile_stats": 2, "asp_cdf_info": 0, "asp_device_check": 0,
                     "asp_search_multinomial_guided": 4, "asp_select_uniforms": 3, "asp_search_systematic": 3,
                     "asp_search_systematic_workspace_bytes": 0, "asp_pcn_propose_eval_supported": 0, "asp_beta_search_max_passes3": 0,
-                    "asp_sorted_tiles": 0}
+                    "asp_sorted_tiles": 0, "asp_search_sorted": 2}
 launch_count = 0
 
 

@@ -13,13 +13,18 @@ tempering step the ranks exchange only scalars:
 * ``sum``  all-reduce of the pCN reference-measure moments                (1 + 2 D doubles)
 * ``sum``  all-reduce of the accept counters                              (n_moves int64)
 
-Resampling is OWNER-COMPUTES: every rank walks the same global stream of uniforms and
-keeps the output slots whose ancestor lies in its own CDF slice (``asp_select_uniforms``),
-so offspring are born on the rank that holds their ancestor and no particle row crosses
-NVLink.  The union over ranks of (slot, ancestor) is exactly the single-GPU result;
-shard sizes drift by O(sqrt(N/G)) per step (multinomial noise), far inside the buffers'
-head-room.  Particle order in the global array becomes (rank, slot) - a permutation of
-the single-process order, harmless because SMC particles are exchangeable.
+* all-gather of the integer tile sums of the sorted-uniform spacings       (N / 2048 int64 in total)
+* all-gather of the CDF value in front of every slice                    (1 double per rank)
+
+Resampling is OWNER-COMPUTES on SORTED uniforms (``asp_sorted_spacings`` / ``asp_search_sorted``,
+``oracle/sorted_resample.py``): output slot j is the j-th smallest uniform, so the rank that holds the CDF slice
+[k0, k1) owns the CONTIGUOUS slot range {j : T_{k0-1} <= S_j < T_{k1-1}}; it regenerates those spacings itself
+(counter-based), resolves its ancestors locally and mutates the offspring where their ancestors live.  The union
+over ranks of (slot, ancestor) is exactly the single-GPU result, slot for slot.  Afterwards the shards are
+REBALANCED: rank r keeps the slots of its target range [r N/G, (r+1) N/G) and only the slivers that cross a shard
+boundary - the weight imbalance of the step - travel peer to peer (one grouped NCCL send/recv over NVLink),
+straight into their final rows; the sweep has already written the rows that stay into place.  The global array
+stays in slot order, every shard keeps exactly N/G particles, and nothing depends on head-room.
 """
 
 from __future__ import annotations
@@ -67,6 +72,36 @@ class Comm:
 
     def barrier(self):
         self.dist.barrier(group=self.group)
+
+
+class SoloComm(Comm):
+    """A one-rank communicator: the sharded step on a single process (reference side of the parity checks)."""
+
+    def __init__(self):
+        import torch.distributed as dist
+
+        self.dist, self.group, self.rank, self.world = dist, None, 0, 1
+
+    def all_reduce_sum(self, t):
+        return t
+
+    def all_reduce_max(self, t):
+        return t
+
+    def all_gather(self, t):
+        return t.unsqueeze(0)
+
+    def send(self, t, dst):
+        pass
+
+    def recv(self, t, src):
+        pass
+
+    def broadcast(self, t, src):
+        return t
+
+    def barrier(self):
+        pass
 
 
 class PeerMailboxes:
@@ -126,14 +161,14 @@ class PeerMailboxes:
 
 @dataclass
 class Shard:
-    """This rank's particles: rows + logs + the global output slot of every row
-    (the Philox counter of its noise; contiguous at the start of a run)."""
+    """This rank's particles: rows + logs of the global slots [slot0, slot0 + len) (slot order: the Philox
+    counter of a particle's noise is its global slot)."""
 
     x: torch.Tensor
     log_l: torch.Tensor
     log_p: torch.Tensor
     log_q: torch.Tensor
-    slot: torch.Tensor | None = None
+    slot0: int = 0
 
     def __len__(self):
         return self.x.shape[0]
@@ -157,7 +192,7 @@ class ShardedSMC:
     (the CPU tests inject an oracle-backed stand-in with the same functions)."""
 
     def __init__(self, comm: Comm, like, prior, q, backend=None, seed: int = 0, n_moves: int = 10, rho: float = 0.5,
-                 target_efficiency: float = 0.5, beta_tolerance: float = 1e-6, headroom: float = 1.05,
+                 target_efficiency: float = 0.5, beta_tolerance: float = 1e-6, headroom: float = 1.04,
                  moment_particles: int = 1 << 22):
         if backend is None:
             from . import ops as backend
@@ -256,21 +291,32 @@ class ShardedSMC:
         var_sum = float(host[:, 2].sum())
         mean_u = s1 / n_total
         mark("cdf")
-        # owner-computes multinomial resampling
+        # owner-computes multinomial resampling at sorted uniforms
+        r, g = comm.rank, comm.world
         stream_u = self.next_stream()
-        capacity = int(max(n_local, n_total / comm.world) * self.headroom) + 1024
-        slot, u = ops.select_uniforms(n_total, lo, hi, capacity, dev, seed=self.seed, stream_id=stream_u, u_all=u_all)
+        per = -(-ops.sorted_tiles(n_total) // g)                 # tiles generated per rank (ceil)
+        tiles_total = ops.sorted_tiles(n_total)
+        t_lo = min(r * per, tiles_total)
+        sp = ops.SortedSpacings(self.seed, stream_u, n_total, dev, j0=t_lo * ops.SPACING_TILE,
+                                n_tiles=min(per, tiles_total - t_lo))
+        sums = torch.zeros(per, dtype=torch.int64, device=dev)
+        sums[:sp.n_tiles] = sp.tile_sums
+        sp.scan(comm.all_gather(sums).reshape(-1)[:tiles_total].contiguous() if g > 1 else sp.tile_sums)
+        lo_all = comm.all_gather(torch.tensor([lo], dtype=torch.float64, device=dev)).reshape(-1) if g > 1 else \
+            torch.zeros(1, dtype=torch.float64, device=dev)
+        bounds = ops.sorted_bounds(sp, lo_all, n_total)          # host ints J_0 .. J_G: rank s owns slots [J_s, J_s+1)
+        j_lo, j_hi = bounds[r], bounds[r + 1]
+        n_out = j_hi - j_lo
         mark("select")
-        idx = ops.search_multinomial(cdf, u)
-        n_out = slot.numel()
+        idx = sp.window(j_lo, j_hi).search(cdf, j_lo, j_hi)
         mark("resample")
         dims = shard.x.shape[1]
-        # reference measure: moments of the offspring in output slots < moment_particles (slots are
-        # sorted on every rank, so these are a prefix) - the same set whatever the sharding
-        m_use = int(torch.searchsorted(slot, torch.tensor([self.moment_particles], dtype=slot.dtype,
-                                                           device=slot.device))[0]) if n_out else 0
-        if m_use > 0:
-            mom = ops.weighted_moments(shard.x, idx=idx[:m_use])
+        # reference measure: moments of every (n_total // moment_particles)-th slot - the same set whatever the
+        # sharding, spread over the whole genealogy (the ancestors are ascending)
+        stride = max(n_total // max(self.moment_particles, 1), 1)
+        first = (-j_lo) % stride
+        if first < n_out:
+            mom = ops.weighted_moments(shard.x, idx=idx[first::stride].contiguous())
         else:
             mom = torch.zeros(1 + 2 * dims, dtype=torch.float64, device=dev)
         comm.all_reduce_sum(mom)
@@ -278,12 +324,35 @@ class ShardedSMC:
         sigma = torch.clamp_min(sigma, 1e-150)
         mark("moments")
         prm = ops.make_pcn_params(beta, self.rho, mu, sigma, self.n_moves, seed=self.seed,
-                                  stream0=self.next_stream(self.n_moves) + 0x40000000, slot=slot,
+                                  stream0=self.next_stream(self.n_moves) + 0x40000000, index0=j_lo,
                                   total_accepts_only=True)
-        x, ll, lp, lq, accepts = ops.pcn_sweep(shard.x, shard.log_l, shard.log_p, shard.log_q, idx, self.like,
-                                               self.prior, self.q, prm)
+        # target partition: slot order, N/G slots per rank.  The sweep writes slot j to row margin + (j - A_r) of
+        # the new buffers, so the slots that stay are already in place; the slivers sit in the margins.
+        base, rem = divmod(n_total, g)
+        target = [s_ * base + min(s_, rem) for s_ in range(g + 1)]
+        a_lo, a_hi = target[r], target[r + 1]
+        n_keep = a_hi - a_lo
+        margin = 0 if g == 1 else max(int(n_keep * (self.headroom - 1.0)), 0) + 4096
+        off = margin + (j_lo - a_lo)
+        in_place = off >= 0 and off + n_out <= n_keep + 2 * margin
+        bufs = (torch.empty(n_keep + 2 * margin, dims, dtype=torch.float64, device=dev),
+                *(torch.empty(n_keep + 2 * margin, dtype=torch.float64, device=dev) for _ in range(3)))
+        if in_place:
+            src, src_off = bufs, off
+        else:  # an imbalance beyond the margins: sweep into a scratch set, every kept row is copied once
+            src = (torch.empty(max(n_out, 1), dims, dtype=torch.float64, device=dev),
+                   *(torch.empty(max(n_out, 1), dtype=torch.float64, device=dev) for _ in range(3)))
+            src_off = 0
+        if n_out > 0:
+            out = tuple(t[src_off:src_off + n_out] for t in src)
+            _, _, _, _, accepts = ops.pcn_sweep(shard.x, shard.log_l, shard.log_p, shard.log_q, idx, self.like,
+                                                self.prior, self.q, prm, out=out)
+            acc = accepts.sum().reshape(1).to(torch.float64)
+        else:
+            acc = torch.zeros(1, dtype=torch.float64, device=dev)
         mark("pcn_sweep")
-        acc = accepts.sum().reshape(1).to(torch.float64)
+        self.exchange(src, src_off, j_lo, j_hi, bufs, margin, bounds, target)
+        mark("exchange")
         comm.all_reduce_sum(acc)
         rec = StepRecord(
             beta=beta, ess=s1 * s1 / s2, ess_target=state.eff_beta_max * n_total,
@@ -291,7 +360,38 @@ class ShardedSMC:
             log_norm_ratio_var=var_sum / n_total / (n_total * mean_u * mean_u) if mean_u != 0 else math.nan,
             acceptance=float(acc[0]) / max(self.n_moves * n_total, 1), n_total=n_total, n_local_out=n_out,
             n_beta_evals=state.n_evals)
-        return Shard(x, ll, lp, lq, slot), rec
+        x, ll, lp, lq = (t[margin:margin + n_keep] for t in bufs)
+        return Shard(x, ll, lp, lq, a_lo), rec
+
+    def exchange(self, src, src_off, j_lo, j_hi, dst, margin, bounds, target):
+        """Shard rebalancing: this rank produced the slots [j_lo, j_hi) (rows ``src[src_off:]``) and keeps the slots
+        [target[r], target[r+1]) (rows ``dst[margin:]``).  Slot ranges that cross a shard boundary are sent to
+        their target rank and received straight into their final rows: one grouped send/recv, nothing else moves
+        (``src is dst``: the rows that stay were written in place by the sweep)."""
+        comm = self.comm
+        r, g = comm.rank, comm.world
+        a_lo, a_hi = target[r], target[r + 1]
+        k_lo, k_hi = max(j_lo, a_lo), min(j_hi, a_hi)
+        if src is not dst and k_hi > k_lo:
+            for s_t, d_t in zip(src, dst):
+                d_t[margin + k_lo - a_lo:margin + k_hi - a_lo].copy_(s_t[src_off + k_lo - j_lo:src_off + k_hi - j_lo])
+        if g == 1:
+            return
+        ops_ = []
+        for s in range(g):
+            if s == r:
+                continue
+            lo_s, hi_s = max(j_lo, target[s]), min(j_hi, target[s + 1])          # mine, theirs to keep
+            if hi_s > lo_s:
+                ops_ += [comm.dist.P2POp(comm.dist.isend, t[src_off + lo_s - j_lo:src_off + hi_s - j_lo], s, comm.group)
+                         for t in src]
+            lo_r, hi_r = max(bounds[s], a_lo), min(bounds[s + 1], a_hi)          # theirs, mine to keep
+            if hi_r > lo_r:
+                ops_ += [comm.dist.P2POp(comm.dist.irecv, t[margin + lo_r - a_lo:margin + hi_r - a_lo], s, comm.group)
+                         for t in dst]
+        if ops_:
+            for w in comm.dist.batch_isend_irecv(ops_):
+                w.wait()
 
 
 def run_tempering(engine: "ShardedSMC", shard: "Shard", beta: float = 0.0, max_steps: int = 10_000):
@@ -306,6 +406,44 @@ def run_tempering(engine: "ShardedSMC", shard: "Shard", beta: float = 0.0, max_s
     log_z = float(sum(r.log_norm_ratio for r in records))
     err = math.sqrt(float(sum(r.log_norm_ratio_var for r in records)))
     return shard, records, log_z, err
+
+
+def parity_check(comm: Comm, dev, n_total: int = 1_000_003, dims: int = 32, moves: int = 4, seed: int = 4242) -> dict:
+    """One sharded tempering step on all ranks against the same step on rank 0 alone (same global particles, same
+    Philox streams): beta identical, every particle of the rebalanced global array compared with the single-GPU
+    array row by row.  Collective: every rank must call it.  -> dict (filled on rank 0)."""
+    from . import ops
+    from . import targets as tg
+
+    r, g = comm.rank, comm.world
+    prob = tg.rosenbrock_problem(dims, device=dev)
+    base, rem = divmod(n_total, g)
+    n_local, start = base + (1 if r < rem else 0), r * base + min(r, rem)
+    x0 = ops.philox_normal(seed, 0, n_local, dims, dev, mean=prob["q"].mean, sigma=prob["q"].sigma, index0=start)
+    shard = Shard(x0, prob["like"].log_prob(x0), prob["prior"].log_prob(x0), prob["q"].log_prob(x0), start)
+    eng = ShardedSMC(comm, prob["like"], prob["prior"], prob["q"], seed=seed + 1, n_moves=moves, rho=0.5)
+    new, rec = eng.step(shard, 0.0)
+    cap = base + (1 if rem else 0)
+    pad = lambda t: torch.cat([t, t.new_zeros((cap - t.shape[0],) + tuple(t.shape[1:]))])  # noqa: E731
+    xs, lls = comm.all_gather(pad(new.x)), comm.all_gather(pad(new.log_l))
+    produced = comm.all_gather(torch.tensor([rec.n_local_out], dtype=torch.int64, device=dev)).reshape(-1).tolist()
+    out = {}
+    if r == 0:
+        counts = [base + (1 if i < rem else 0) for i in range(g)]
+        x = torch.cat([xs[i, :c] for i, c in enumerate(counts)])
+        ll = torch.cat([lls[i, :c] for i, c in enumerate(counts)])
+        xg = ops.philox_normal(seed, 0, n_total, dims, dev, mean=prob["q"].mean, sigma=prob["q"].sigma)
+        full = Shard(xg, prob["like"].log_prob(xg), prob["prior"].log_prob(xg), prob["q"].log_prob(xg))
+        solo = ShardedSMC(SoloComm(), prob["like"], prob["prior"], prob["q"], seed=seed + 1, n_moves=moves, rho=0.5)
+        ref, rrec = solo.step(full, 0.0)
+        dx = (x - ref.x).abs().max(dim=1).values
+        out = {"ranks": g, "particles": n_total, "dims": dims, "moves": moves, "beta_identical": rec.beta == rrec.beta,
+               "beta": rec.beta, "ess_rel_diff": abs(rec.ess - rrec.ess) / rrec.ess,
+               "log_norm_ratio_rel_diff": abs(rec.log_norm_ratio - rrec.log_norm_ratio) / abs(rrec.log_norm_ratio),
+               "acceptance_diff": abs(rec.acceptance - rrec.acceptance), "max_abs_dx": float(dx.max()),
+               "max_abs_dlogl": float((ll - ref.log_l).abs().max()), "produced_per_rank": produced,
+               "ok": bool(rec.beta == rrec.beta and float(dx.max()) < 1e-9 and sum(produced) == n_total)}
+    return out
 
 
 def _host_buffer_leg(args, comm, engine, shard0, n_total, dev, unit):
@@ -390,7 +528,7 @@ def run_bench(args, rank, world, dev, metric, unit, workload_config, bytes_per_p
     x0 = ops.philox_normal(seed, 0, n_local, dims, dev, mean=prob["q"].mean, sigma=prob["q"].sigma, index0=start)
     shard0 = Shard(x0, prob["like"].log_prob(x0), prob["prior"].log_prob(x0), prob["q"].log_prob(x0))
     engine = ShardedSMC(comm, prob["like"], prob["prior"], prob["q"], seed=seed + 1, n_moves=moves, rho=0.5)
-    phases = ["beta_search", "cdf_local", "cdf", "select", "resample", "moments", "pcn_sweep"]
+    phases = ["beta_search", "cdf_local", "cdf", "select", "resample", "moments", "pcn_sweep", "exchange"]
     stream = torch.cuda.current_stream()
 
     def one_step(record=None):
@@ -408,6 +546,7 @@ def run_bench(args, rank, world, dev, metric, unit, workload_config, bytes_per_p
             record.append(evs)
         return new, rec
 
+    parity = parity_check(comm, dev)  # the N-rank step against the 1-GPU step, before anything is timed
     for _ in range(max(args.warmup, 3)):
         one_step()
     torch.cuda.synchronize()
@@ -462,7 +601,7 @@ def run_bench(args, rank, world, dev, metric, unit, workload_config, bytes_per_p
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {**workload_config(args, n_total), "parallelism": f"particle-sharded x{world}, owner-computes "
-                       "resampling, scalar collectives only",
+                       "resampling on sorted uniforms, scalar collectives + boundary-crossing slivers peer to peer",
                        "beta_search_allreduce": ("inside the pass kernel over NVLink peer memory (" + engine._peer.how + ")"
                                                  if engine._peer else "NCCL")},
             "clocks": clock_info, "gpu_launches": launches,
@@ -476,7 +615,7 @@ def run_bench(args, rank, world, dev, metric, unit, workload_config, bytes_per_p
             "cpu_baseline": None, "phase_ms": phase_ms,
             "phase_ms_per_rank": [[round(v, 3) for v in row] for row in per_rank],
             "step_ms_per_rank": [[round(v, 2) for v in row] for row in step_ms_per_rank], "beta_after_step": rec.beta, "acceptance": rec.acceptance,
-            "n_local_out": rec.n_local_out,
+            "n_local_out": rec.n_local_out, "multi_gpu_parity": parity,
         }
         print(json.dumps(line))
     dist.destroy_process_group()

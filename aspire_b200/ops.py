@@ -320,8 +320,9 @@ class SortedSpacings:
         self.n_tiles = self.tiles_total - self.j0 // SPACING_TILE if n_tiles is None else int(n_tiles)
         self.q = torch.empty(self.n_tiles * SPACING_TILE, dtype=torch.int32, device=device)
         self.tile_sums = torch.empty(self.n_tiles, dtype=torch.int64, device=device)
-        check(lib.asp_sorted_spacings(self.seed, self.stream_id, self.j0, self.n_tiles, self.m, self.q.data_ptr(),
-                                      self.tile_sums.data_ptr(), _stream()), "asp_sorted_spacings")
+        if self.n_tiles > 0:
+            check(lib.asp_sorted_spacings(self.seed, self.stream_id, self.j0, self.n_tiles, self.m, self.q.data_ptr(),
+                                          self.tile_sums.data_ptr(), _stream()), "asp_sorted_spacings")
         self.tile_prefix = None
         self.total = None
 
@@ -342,18 +343,44 @@ class SortedSpacings:
         j_hi = self.m if j_hi is None else int(j_hi)
         idx = torch.empty(j_hi - j_lo, dtype=torch.int64, device=cdf.device)
         if j_hi > j_lo:
-            check(_lib.load().asp_search_sorted(cdf.data_ptr(), cdf.numel(), self.q.data_ptr(), self.j0,
-                                                self.tile_prefix.data_ptr(), self.total.data_ptr(), int(j_lo), j_hi,
-                                                idx.data_ptr(), _stream()), "asp_search_sorted")
+            lib = _lib.load()
+            ws = _sized_ws("sorted", lib.asp_search_sorted_workspace_bytes(j_hi - j_lo), cdf.device)
+            check(lib.asp_search_sorted(cdf.data_ptr(), cdf.numel(), self.q.data_ptr(), self.j0,
+                                        self.tile_prefix.data_ptr(), self.total.data_ptr(), int(j_lo), j_hi,
+                                        idx.data_ptr(), ws.data_ptr(), _stream()), "asp_search_sorted")
         return idx
 
     def lower_bound(self, thresholds: torch.Tensor) -> torch.Tensor:
-        """``#{j < m : S_j < t}`` for each (int64 device) threshold."""
+        """``#{j < m : S_j < t}`` for each (int64 device) threshold; needs :meth:`scan` only."""
         out = torch.empty(thresholds.numel(), dtype=torch.int64, device=thresholds.device)
-        check(_lib.load().asp_sorted_lower_bound(self.q.data_ptr(), self.j0, self.n_tiles, self.tile_prefix.data_ptr(),
+        check(_lib.load().asp_sorted_lower_bound(self.seed, self.stream_id, self.tile_prefix.data_ptr(),
                                                  self.tiles_total, self.m, thresholds.data_ptr(), thresholds.numel(),
                                                  out.data_ptr(), _stream()), "asp_sorted_lower_bound")
         return out
+
+    def window(self, j_lo: int, j_hi: int) -> "SortedSpacings":
+        """Spacings covering the slots ``[j_lo, j_hi)`` with this object's global tile table: itself when it
+        already covers them, else a regenerated window (counter-based: no exchange)."""
+        t0, t1 = j_lo // SPACING_TILE, max((j_hi - 1) // SPACING_TILE + 1, j_lo // SPACING_TILE + 1)
+        if self.j0 <= t0 * SPACING_TILE and t1 * SPACING_TILE <= self.j0 + self.n_tiles * SPACING_TILE:
+            return self
+        win = SortedSpacings(self.seed, self.stream_id, self.m, self.q.device, j0=t0 * SPACING_TILE, n_tiles=t1 - t0)
+        win.tile_prefix, win.total = self.tile_prefix, self.total
+        return win
+
+
+def sorted_tiles(m: int) -> int:
+    return int(_lib.load().asp_sorted_tiles(int(m)))
+
+
+def sorted_bounds(sp: SortedSpacings, lo_all: torch.Tensor, m: int) -> list:
+    """Slot boundaries of the owner-computes partition: ``lo_all[s]`` is the global CDF value in front of rank s's
+    slice; rank s owns the slots ``[J_s, J_{s+1})``, ``J_s = #{j : S_j < rint(lo_s total)}``, ``J_G = m``.
+    -> host ints [J_0 .. J_G] (one device -> host read)."""
+    thr = torch.round(lo_all.to(torch.float64) * sp.total.to(torch.float64)).to(torch.int64).contiguous()
+    j = sp.lower_bound(thr).cpu().tolist()
+    j[0] = 0
+    return [int(v) for v in j] + [int(m)]
 
 
 def search_multinomial_sorted(cdf, seed: int, stream_id: int, m: int) -> torch.Tensor:

@@ -149,6 +149,8 @@ def sweep(args):
         x = ops.philox_normal(5, 0, n, dims, dev, mean=pg["q"].mean, sigma=pg["q"].sigma)
         lq, lp, ll = pg["q"].log_prob(x), pg["prior"].log_prob(x), pg["like"].log_prob(x)
         idx = (ops.philox_uniform(6, 0, n, dev) * n).to(torch.int64).clamp_(0, n - 1)
+        if args.sorted_idx:  # what the sorted-uniform resampler hands to the sweep
+            idx = torch.sort(idx).values
         mom = ops.weighted_moments(x[: 1 << 20])
         mu, sigma = ops.moments_to_mu_sigma(mom, dims)
         prm = ops.make_pcn_params(0.1, 0.3, mu, sigma, args.moves, seed=99, stream0=3, total_accepts_only=True)
@@ -337,6 +339,7 @@ if __name__ == "__main__":
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--moves", type=int, default=10)
     ap.add_argument("--dims", type=int, default=0)
+    ap.add_argument("--sorted-idx", action="store_true")
     ap.add_argument("--only", default="")
     ap.add_argument("--dump", default="")
     a = ap.parse_args()

@@ -245,19 +245,22 @@ int asp_search_systematic(const double* d_cdf, int64_t n_cdf, double u0, int64_t
  *                               j0 .. j0 + n_tiles * 2048 - 1 (j0 a multiple of 2048; elements > m_total give 0)
  *   asp_sorted_tile_scan        exclusive prefix of ALL tile sums (after an all-gather when sharded) + total
  *   asp_search_sorted           ancestors of the slots j_lo <= j < j_hi within the CDF (slice) d_cdf[n_cdf];
- *                               d_q[0] is element q_j0; d_tile_prefix is indexed by the global tile
- *   asp_sorted_lower_bound      d_out[i] = #{j < m_total : S_j < d_thresholds[i]} (shard boundaries; -1 if the
- *                               tile it falls in is outside the d_q window) */
+ *                               d_q[0] is element q_j0; d_tile_prefix is indexed by the global tile;
+ *                               ws: asp_search_sorted_workspace_bytes(j_hi - j_lo)
+ *   asp_sorted_lower_bound      d_out[i] = #{j < m_total : S_j < d_thresholds[i]}: the shard boundaries - the rank
+ *                               that owns the CDF slice [k0, k1) owns the slots from the bound of rint(cdf_{k0-1}
+ *                               total) to that of rint(cdf_{k1-1} total) (the tile is regenerated in the kernel) */
 int64_t asp_sorted_tiles(int64_t m_total);
 int asp_sorted_spacings(uint64_t seed, uint32_t stream_id, int64_t j0, int64_t n_tiles, int64_t m_total, uint32_t* d_q,
                         unsigned long long* d_tile_sums, void* stream);
 int asp_sorted_tile_scan(const unsigned long long* d_tile_sums, int64_t n_tiles, unsigned long long* d_tile_prefix,
                          unsigned long long* d_total, void* stream);
+size_t asp_search_sorted_workspace_bytes(int64_t n_slots);
 int asp_search_sorted(const double* d_cdf, int64_t n_cdf, const uint32_t* d_q, int64_t q_j0,
                       const unsigned long long* d_tile_prefix, const unsigned long long* d_total, int64_t j_lo,
-                      int64_t j_hi, int64_t* d_idx, void* stream);
-int asp_sorted_lower_bound(const uint32_t* d_q, int64_t q_j0, int64_t q_tiles, const unsigned long long* d_tile_prefix,
-                           int64_t n_tiles, int64_t m_total, const unsigned long long* d_thresholds, int32_t n_thresholds,
+                      int64_t j_hi, int64_t* d_idx, void* ws, void* stream);
+int asp_sorted_lower_bound(uint64_t seed, uint32_t stream_id, const unsigned long long* d_tile_prefix, int64_t n_tiles,
+                           int64_t m_total, const unsigned long long* d_thresholds, int32_t n_thresholds,
                            long long* d_out, void* stream);
 
 /* ---- row gather (K7) ----------------------------------------------------

@@ -100,11 +100,69 @@ def cdf_write(p, total, normalise=True):
     return _t(raw / float(_np(total)[0]) if normalise else raw)
 
 
-def select_uniforms(n_total, lo, hi, capacity, device, seed=0, stream_id=0, u_all=None):
-    u = oph.uniform_f64(seed, stream_id, np.arange(n_total)) if u_all is None else _np(u_all)
-    keep = np.nonzero((u >= lo) & (u < hi))[0]
-    assert len(keep) <= capacity
-    return _t(keep.astype(np.int64)), _t(u[keep])
+SPACING_TILE = 2048
+
+
+def sorted_tiles(m):
+    return (m + 1 + SPACING_TILE - 1) // SPACING_TILE
+
+
+class SortedSpacings:
+    """oracle/sorted_resample.py behind the interface of ``aspire_b200.ops.SortedSpacings``."""
+
+    def __init__(self, seed, stream_id, m, device, j0=0, n_tiles=None):
+        from oracle import sorted_resample as sr
+
+        self.seed, self.stream_id, self.m, self.j0 = seed, stream_id, m, j0
+        self.tiles_total = sorted_tiles(m)
+        self.n_tiles = self.tiles_total - j0 // SPACING_TILE if n_tiles is None else n_tiles
+        e = np.arange(j0, j0 + self.n_tiles * SPACING_TILE, dtype=np.uint64)
+        q = sr.spacing_q(sr.uniform_k53(seed, stream_id, e)).astype(np.int64) if e.size else np.zeros(0, np.int64)
+        q[e > m] = 0
+        self._q = q
+        self.tile_sums = _t(q.reshape(self.n_tiles, SPACING_TILE).sum(axis=1)) if e.size else torch.zeros(0, dtype=torch.int64)
+        self.tile_prefix = self.total = None
+
+    def scan(self, all_tile_sums=None):
+        sums = _np(self.tile_sums if all_tile_sums is None else all_tile_sums).astype(np.int64)
+        assert sums.size == self.tiles_total
+        self.tile_prefix = _t(np.concatenate([[0], np.cumsum(sums)[:-1]]))
+        self.total = _t(np.array([sums.sum()]))
+        return self
+
+    def window(self, j_lo, j_hi):
+        t0, t1 = j_lo // SPACING_TILE, max((j_hi - 1) // SPACING_TILE + 1, j_lo // SPACING_TILE + 1)
+        if self.j0 <= t0 * SPACING_TILE and t1 * SPACING_TILE <= self.j0 + self.n_tiles * SPACING_TILE:
+            return self
+        win = SortedSpacings(self.seed, self.stream_id, self.m, None, j0=t0 * SPACING_TILE, n_tiles=t1 - t0)
+        win.tile_prefix, win.total = self.tile_prefix, self.total
+        return win
+
+    def partial_sums(self, j_lo, j_hi):
+        t0 = self.j0 // SPACING_TILE
+        s = np.cumsum(self._q) + int(_np(self.tile_prefix)[t0])
+        return s[j_lo - self.j0:j_hi - self.j0].astype(np.uint64)
+
+    def search(self, cdf, j_lo=0, j_hi=None):
+        from oracle import sorted_resample as sr
+
+        j_hi = self.m if j_hi is None else j_hi
+        t = sr.thresholds(_np(cdf), int(_np(self.total)[0]))
+        idx = np.minimum(np.searchsorted(t, self.partial_sums(j_lo, j_hi), side="right"), len(t) - 1)
+        return _t(idx.astype(np.int64))
+
+
+def sorted_bounds(sp, lo_all, m):
+    from oracle import sorted_resample as sr
+
+    total = int(_np(sp.total)[0])
+    full = SortedSpacings(sp.seed, sp.stream_id, m, None)
+    full.tile_prefix, full.total = sp.tile_prefix, sp.total
+    s = full.partial_sums(0, m)
+    thr = sr.thresholds(_np(lo_all), total)
+    j = [int(np.searchsorted(s, t, side="left")) for t in thr]
+    j[0] = 0
+    return j + [m]
 
 
 def search_multinomial(cdf, u, guided=None):
@@ -135,7 +193,12 @@ def pcn_sweep(x, ll, lp, lq, idx, like, prior, q, prm, out=None):
     r = opcn.sweep(_np(x)[i], _np(ll)[i], _np(lp)[i], _np(lq)[i], like=like, prior=prior, q=q, beta=prm.beta,
                    mu=prm.mu, sigma=prm.sigma, rho=prm.rho, n_moves=prm.n_moves, seed=prm.seed,
                    stream0=prm.stream0 & 0xFFFFFFFF, index0=prm.index0, index=prm.slot)
-    return _t(r[0]), _t(r[1]), _t(r[2]), _t(r[3]), _t(r[4])
+    res = [_t(a) for a in r]
+    if out is not None:
+        for o, v in zip(out, res[:4]):
+            o.copy_(v)
+        res[:4] = out
+    return tuple(res)
 
 
 def evaluate(desc, x):

@@ -73,21 +73,22 @@ def main():
         p2p_note += f"; CDF chain over peer memory == NCCL chain ({ms_a:.3f} ms vs {ms_b:.3f} ms)"
     if r == 0:
         print(p2p_note)
-    # gather (slot, x, logL) on rank 0
-    cnt = torch.tensor([len(new)], dtype=torch.int64, device=dev)
-    counts = comm.all_gather(cnt).reshape(-1).tolist()
+    # gather (x, logL) on rank 0: the shards are rebalanced, rank r holds the slots [r N/G, (r+1) N/G) in order
+    cnt = torch.tensor([len(new), new.slot0, rec.n_local_out], dtype=torch.int64, device=dev)
+    info = comm.all_gather(cnt).tolist()
+    counts = [c[0] for c in info]
     cap = max(counts)
     pad = lambda t: torch.cat([t, t.new_zeros((cap - t.shape[0],) + tuple(t.shape[1:]))])  # noqa: E731
-    slots = comm.all_gather(pad(new.slot))
     xs = comm.all_gather(pad(new.x))
     lls = comm.all_gather(pad(new.log_l))
     ok = True
     if r == 0:
-        slot = torch.cat([slots[i, :c] for i, c in enumerate(counts)])
         x = torch.cat([xs[i, :c] for i, c in enumerate(counts)])
         ll = torch.cat([lls[i, :c] for i, c in enumerate(counts)])
-        assert sorted(slot.tolist()) == list(range(n_total)), "slots are not a partition"
-        order = torch.argsort(slot)
+        assert sum(counts) == n_total and max(counts) - min(counts) <= 1, counts
+        assert [c[1] for c in info] == [sum(counts[:i]) for i in range(g)], "shards are not in slot order"
+        assert sum(c[2] for c in info) == n_total, "the produced slot ranges are not a partition"
+        order = torch.arange(n_total, device=dev)
         # single-GPU reference: the same engine with a trivial communicator
         class Solo(Comm):
             def __init__(self):
@@ -103,14 +104,14 @@ def main():
         full = Shard(xg, prob["like"].log_prob(xg), prob["prior"].log_prob(xg), prob["q"].log_prob(xg))
         solo = ShardedSMC(Solo(), prob["like"], prob["prior"], prob["q"], seed=seed + 1, n_moves=moves, rho=0.5)
         ref, rrec = solo.step(full, 0.0)
-        assert torch.equal(ref.slot, torch.arange(n_total, device=dev))
+        assert ref.slot0 == 0 and len(ref) == n_total
         assert rrec.beta == rec.beta, (rrec.beta, rec.beta)
         np.testing.assert_allclose(rec.ess, rrec.ess, rtol=1e-12)
         np.testing.assert_allclose(rec.log_norm_ratio, rrec.log_norm_ratio, rtol=1e-12)
         np.testing.assert_allclose(rec.log_norm_ratio_var, rrec.log_norm_ratio_var, rtol=1e-10)
         dx = (x[order] - ref.x).abs().max(dim=1).values
         frac_bad = float((dx > 1e-9).double().mean())
-        print(f"G={g} N={n_total} beta={rec.beta:.6g} acc={rec.acceptance:.4f} shard sizes={counts} "
+        print(f"G={g} N={n_total} beta={rec.beta:.6g} acc={rec.acceptance:.4f} produced per rank={[c[2] for c in info]} "
               f"max|dx|={float(dx.max()):.3e} frac(|dx|>1e-9)={frac_bad:.2e}")
         ok = frac_bad < 1e-5 and abs(rec.acceptance - rrec.acceptance) < 1e-5
         np.testing.assert_allclose(ll[order][dx <= 1e-9].cpu().numpy(), ref.log_l[dx <= 1e-9].cpu().numpy(),

@@ -22,7 +22,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, splits, ret):
+def _worker(rank, world, port, splits, headroom, ret):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     import torch.distributed as dist
 
@@ -37,39 +37,46 @@ def _worker(rank, world, port, splits, ret):
     t = lambda v: torch.as_tensor(np.ascontiguousarray(v))  # noqa: E731
     shard = Shard(t(x[a:b]), t(ll[a:b]), t(lp[a:b]), t(lq[a:b]))
     eng = ShardedSMC(Comm(), prob["like"], prob["prior"], prob["q"], backend=cpu_backend, seed=SEED, n_moves=MOVES,
-                     rho=0.4)
+                     rho=0.4, headroom=headroom)
     new, rec = eng.step(shard, 0.0)
-    ret[rank] = dict(slot=new.slot.numpy(), x=new.x.numpy(), ll=new.log_l.numpy(), rec=rec)
+    ret[rank] = dict(slot0=new.slot0, x=new.x.numpy(), ll=new.log_l.numpy(), rec=rec)
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("splits", [[0, 3000, 6000], [0, 1, 6000], [0, 4097, 6000]])
-def test_two_rank_step_equals_single_process(splits):
+@pytest.mark.parametrize("splits,headroom", [([0, 3000, 6000], 1.04), ([0, 1, 6000], 1.04), ([0, 4097, 6000], 1.04),
+                                             ([0, 3000, 6000], 0.0), ([0, 1, 6000], 0.0)])
+def test_two_rank_step_equals_single_process(splits, headroom):
+    """``headroom = 0`` shrinks the margins to the 4096-row floor: with the [0, 1, 6000] split rank 1 produces slots
+    far outside them, sweeps into scratch and copies the rows it keeps."""
     import sys
+
+    from oracle import sorted_resample as sr
 
     sys.path.insert(0, os.path.dirname(__file__))
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(2, _free_port(), splits, ret), nprocs=2, join=True)
-    # single-process oracle of the same step (same Philox streams: uniforms stream 0, noise from stream 1 + 2^30)
+    mp.spawn(_worker, args=(2, _free_port(), splits, headroom, ret), nprocs=2, join=True)
+    # single-process oracle of the same step (same Philox streams: spacings stream 0, noise from stream 1 + 2^30)
     prob = problems.rosenbrock_problem(DIMS)
     x, ll, lp, lq = problems.draw(prob, N, 4)
     beta, _ = sn.determine_beta(ll, lp, lq, 0.0, beta_tolerance=1e-6)
     p = sn.resample_weights(ll, lp, lq, 0.0, beta)
-    u = oph.uniform_f64(SEED, 0, np.arange(N))
-    idx = sn.choice_indices(p, u)
+    cdf = np.cumsum(p)
+    cdf /= cdf[-1]
+    idx = sr.resample(cdf, SEED, 0, N)
     mu, sigma = opcn.weighted_moments(x[idx], np.ones(N))
     ref = opcn.sweep(x[idx], ll[idx], lp[idx], lq[idx], like=prob["like"], prior=prob["prior"], q=prob["q"], beta=beta,
                      mu=mu, sigma=sigma, rho=0.4, n_moves=MOVES, seed=SEED, stream0=1 + 0x40000000)
-    slot = np.concatenate([ret[0]["slot"], ret[1]["slot"]])
+    # rebalanced: every rank holds its N / G slots, in slot order
+    assert ret[0]["slot0"] == 0 and ret[1]["slot0"] == N // 2
+    assert len(ret[0]["x"]) == N // 2 and len(ret[1]["x"]) == N - N // 2
     xs = np.concatenate([ret[0]["x"], ret[1]["x"]])
     lls = np.concatenate([ret[0]["ll"], ret[1]["ll"]])
-    assert sorted(slot.tolist()) == list(range(N))          # every output slot born exactly once
-    order = np.argsort(slot)
-    # ancestors live where their offspring were born: rank 0 holds exactly the slots with idx < split
-    assert set(ret[0]["slot"].tolist()) == set(np.nonzero(idx < splits[1])[0].tolist())
-    np.testing.assert_allclose(xs[order], ref[0], rtol=1e-9, atol=1e-9)
-    np.testing.assert_allclose(lls[order], ref[1], rtol=1e-8, atol=1e-8)
+    # ancestors live where their offspring were born: rank 0 produced exactly the slots with idx < split
+    assert ret[0]["rec"].n_local_out == int((idx < splits[1]).sum())
+    assert ret[1]["rec"].n_local_out == int((idx >= splits[1]).sum())
+    np.testing.assert_allclose(xs, ref[0], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(lls, ref[1], rtol=1e-8, atol=1e-8)
     for r in (0, 1):
         rec = ret[r]["rec"]
         assert rec.beta == beta and rec.n_total == N
@@ -95,14 +102,15 @@ def _loop_worker(rank, world, port, ret):
     t = lambda v: torch.as_tensor(np.ascontiguousarray(v))  # noqa: E731
     eng = ShardedSMC(Comm(), prob["like"], prob["prior"], prob["q"], backend=cpu_backend, seed=7, n_moves=2, rho=0.5)
     shard, recs, log_z, err = run_tempering(eng, Shard(t(x[a:b]), t(ll[a:b]), t(lp[a:b]), t(lq[a:b])))
-    ret[(world, rank)] = dict(beta=[r.beta for r in recs], log_z=log_z, err=err, slot=shard.slot.numpy(),
+    ret[(world, rank)] = dict(beta=[r.beta for r in recs], log_z=log_z, err=err, slot0=shard.slot0,
                              x=shard.x.numpy())
     dist.destroy_process_group()
 
 
 def test_two_rank_tempering_loop_equals_single_rank_loop():
-    """The whole loop to beta = 1 on two ranks: same beta schedule and evidence increments as on one rank (the sums
-    are permutation-invariant), the same posterior in law."""
+    """The whole loop to beta = 1 on two ranks against one rank: the shards are rebalanced into slot order after
+    every step, so the two runs hold the same particle in the same global row - same beta schedule, same evidence
+    increments, same ensemble row by row (the all-reduced sums differ in the last bits only)."""
     import sys
 
     sys.path.insert(0, os.path.dirname(__file__))
@@ -115,11 +123,9 @@ def test_two_rank_tempering_loop_equals_single_rank_loop():
     assert r0["beta"] == one["beta"] and r1["beta"] == one["beta"]
     assert r0["log_z"] == pytest.approx(one["log_z"], rel=1e-10) and r1["log_z"] == pytest.approx(one["log_z"], rel=1e-10)
     assert r0["err"] == pytest.approx(one["err"], rel=1e-8)
-    slot = np.concatenate([r0["slot"], r1["slot"]])
+    assert (r0["slot0"], r1["slot0"]) == (0, len(r0["x"])) and len(r0["x"]) + len(r1["x"]) == len(one["x"])
     xs = np.concatenate([r0["x"], r1["x"]])
-    assert sorted(slot.tolist()) == sorted(one["slot"].tolist())
-    # after the first resampling the storage order is (rank, slot) - a permutation of the single-rank order - so
-    # later steps pair uniforms with different (exchangeable) particles: the ensembles agree in law, not row by row
+    np.testing.assert_allclose(xs, one["x"], rtol=1e-8, atol=1e-8)
     var = 1.0 / (1.0 / 0.49 + 1.0)
     for ens in (xs, one["x"]):
         assert np.abs(ens.mean(axis=0) - var * 0.5 / 0.49).max() < 0.06
