@@ -335,8 +335,7 @@ class ShardedSMC:
         margin = 0 if g == 1 else max(int(n_keep * (self.headroom - 1.0)), 0) + 4096
         off = margin + (j_lo - a_lo)
         in_place = off >= 0 and off + n_out <= n_keep + 2 * margin
-        bufs = (torch.empty(n_keep + 2 * margin, dims, dtype=torch.float64, device=dev),
-                *(torch.empty(n_keep + 2 * margin, dtype=torch.float64, device=dev) for _ in range(3)))
+        bufs = self._output_buffers(n_keep + 2 * margin, dims, dev, shard)
         if in_place:
             src, src_off = bufs, off
         else:  # an imbalance beyond the margins: sweep into a scratch set, every kept row is copied once
@@ -362,6 +361,45 @@ class ShardedSMC:
             n_beta_evals=state.n_evals)
         x, ll, lp, lq = (t[margin:margin + n_keep] for t in bufs)
         return Shard(x, ll, lp, lq, a_lo), rec
+
+    def _output_buffers(self, rows, dims, dev, shard):
+        """Two persistent buffer sets, used alternately (the set that holds the input shard is never the one
+        written): a Shard returned by ``step`` stays valid until the second next step.  Fresh allocations per
+        step would be tied to the NCCL stream by the exchange and come back late, so the caching allocator keeps
+        falling back to cudaMalloc / cudaFree of ~14 GB blocks (seen as 40 - 290 ms stalls at 2 GPUs)."""
+        sets = self.__dict__.setdefault("_buffer_sets", {})
+        key = (rows, dims, str(dev))
+        pair = sets.get(key)
+        if pair is None:
+            sets.clear()
+            pair = sets[key] = [tuple([torch.empty(rows, dims, dtype=torch.float64, device=dev)] +
+                                      [torch.empty(rows, dtype=torch.float64, device=dev) for _ in range(3)])
+                                for _ in range(2)]
+            self._buffer_turn = 0
+            self._warm_exchange(pair[0], dev)
+        held = shard.x.untyped_storage().data_ptr()
+        for _ in range(2):
+            bufs = pair[self._buffer_turn]
+            self._buffer_turn ^= 1
+            if bufs[0].untyped_storage().data_ptr() != held:
+                return bufs
+        raise RuntimeError("unreachable: both buffer sets hold the input shard")
+
+    def _warm_exchange(self, bufs, dev, rows: int = 1 << 16):
+        """NCCL connects its send / recv channels lazily, per peer and per message-size class (seen: a 110 ms stall
+        the first time a sliver is larger than every earlier one).  One exchange of `rows` rows with every peer,
+        before the first step, connects them all."""
+        comm = self.comm
+        if comm.world == 1 or dev.type != "cuda":
+            return
+        n = min(rows, bufs[0].shape[0] // 2)
+        ops_ = []
+        for s in range(comm.world):
+            if s != comm.rank:
+                ops_ += [comm.dist.P2POp(comm.dist.isend, bufs[0][:n], s, comm.group),
+                         comm.dist.P2POp(comm.dist.irecv, bufs[0][n:2 * n], s, comm.group)]
+        for w in comm.dist.batch_isend_irecv(ops_):
+            w.wait()
 
     def exchange(self, src, src_off, j_lo, j_hi, dst, margin, bounds, target):
         """Shard rebalancing: this rank produced the slots [j_lo, j_hi) (rows ``src[src_off:]``) and keeps the slots
