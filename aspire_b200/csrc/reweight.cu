@@ -266,6 +266,204 @@ __global__ void __launch_bounds__(kBlock, 2) beta_pass3_kernel(const double* __r
 }
 
 // ---------------------------------------------------------------------------
+// Root-guided search (beta_math.cuh): subsample estimate -> Newton passes -> one node pass with the reference's
+// formula.  The node pass costs what one three-level pass costs and replaces seven of them.
+// ---------------------------------------------------------------------------
+constexpr int kSubBlock = 1024;
+constexpr int kSubSamples = 32768;  // fp32 (d - d_max) of every (n / kSubSamples)-th particle, in shared memory
+constexpr int kSubLevels = 26;
+
+// One block: bisection of ESS/N = target on the subsample, in fp32 (an ESTIMATE: the node pass decides).
+__global__ void __launch_bounds__(kSubBlock) beta_sub_kernel(const double* __restrict__ d, int64_t n,
+                                                             const asp_beta_state_t* __restrict__ st,
+                                                             double* __restrict__ scratch, const asp_peer_t P) {
+    extern __shared__ float s_t[];  // [m]
+    __shared__ float s_red[2 * 32];
+    __shared__ float s_sum[2];
+    if (st->phase != 1) return;
+    const int64_t stride = n / kSubSamples > 0 ? n / kSubSamples : 1;
+    const int m = (int)((n + stride - 1) / stride < kSubSamples ? (n + stride - 1) / stride : kSubSamples);
+    const double d_max = st->d_max;
+    float t_max = -INFINITY;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        const float t = (float)(d[(int64_t)i * stride] - d_max);
+        s_t[i] = t;
+        t_max = fmaxf(t_max, t);
+    }
+    // shift by the SAMPLE's maximum: with the global one every sampled weight can underflow in fp32 at the first,
+    // large trial steps (0 >= target * 0 would then read as "ESS large enough")
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t_max = fmaxf(t_max, __shfl_xor_sync(0xffffffffu, t_max, o));
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = t_max;
+    __syncthreads();
+    t_max = s_red[0];
+    for (int w = 1; w < kSubBlock / 32; ++w) t_max = fmaxf(t_max, s_red[w]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < m; i += blockDim.x) s_t[i] -= t_max;  // -inf stays -inf
+    __syncthreads();
+    const float target = (float)st->target_eff * (float)m;
+    float lo = 0.0f, hi = (float)(1.0 - st->beta_prev);  // ESS(lo) >= target > ESS(hi)
+    for (int level = 0; level < kSubLevels; ++level) {
+        const float mid = 0.5f * (lo + hi);
+        if (!(mid > lo && mid < hi)) break;
+        float a = 0.0f, b = 0.0f;
+        const float c = mid * 1.4426950408889634f;
+        for (int i = threadIdx.x; i < m; i += blockDim.x) {
+            const float e = exp2f(c * s_t[i]);  // t <= 0; -inf -> 0
+            a += e;
+            b = fmaf(e, e, b);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            b += __shfl_xor_sync(0xffffffffu, b, o);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            s_red[threadIdx.x >> 5] = a;
+            s_red[32 + (threadIdx.x >> 5)] = b;
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            a = s_red[threadIdx.x];
+            b = s_red[32 + threadIdx.x];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                a += __shfl_xor_sync(0xffffffffu, a, o);
+                b += __shfl_xor_sync(0xffffffffu, b, o);
+            }
+            if (threadIdx.x == 0) {
+                s_sum[0] = a;
+                s_sum[1] = b;
+            }
+        }
+        __syncthreads();
+        if (s_sum[1] > 0.0f && s_sum[0] * s_sum[0] >= target * s_sum[1]) lo = mid;
+        else hi = mid;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        double v[1] = {0.5 * ((double)lo + (double)hi)};
+        bool ok = true;
+        if (P.world > 1) {  // every rank starts Newton from the same point: the mean of the ranks' estimates
+            ok = p2p_allreduce_sum<1>(v, P);
+            v[0] /= (double)P.world;
+        }
+        if (!(v[0] > 0.0)) v[0] = 0.5 * (1.0 - st->beta_prev);
+        scratch[kBsRoot] = ok ? st->beta_prev + v[0] : -1.0;
+        scratch[kBsStep] = 1.0;
+        scratch[kBsTries] = ok ? 0.0 : 3.0;  // a missing peer: skip to the plain bisection (which reports it)
+    }
+}
+
+// S1, S2 and their derivatives at the current root estimate; the last block (after the optional all-reduce) takes
+// the Newton step.  `polish`: skipped when the previous step already left less than a fifth of a tolerance.
+__global__ void __launch_bounds__(kBlock, 4) beta_newton_kernel(const double* __restrict__ d, int64_t n,
+                                                                const asp_beta_state_t* __restrict__ st,
+                                                                double* __restrict__ scratch, int polish, ReduceWs* ws,
+                                                                const asp_peer_t P) {
+    __shared__ double smem[4 * 32];
+    if (st->phase != 1 || scratch[kBsTries] >= 3.0) return;  // uniform across the grid
+    const double delta = scratch[kBsRoot] - st->beta_prev;
+    if (polish && scratch[kBsStep] * scratch[kBsStep] < 0.2 * st->tol * delta) return;
+    const double d_max = st->d_max;
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    auto accumulate = [&](double x) {
+        const double t = x - d_max;
+        const double e = exp(delta * t);
+        const double te = e > 0.0 ? t * e : 0.0;  // d = -inf: zero weight, zero derivative
+        v[0] += e;
+        v[1] = fma(e, e, v[1]);
+        v[2] += te;
+        v[3] = fma(te, e, v[3]);
+    };
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + (kUnroll - 1) * stride < n; i += kUnroll * stride) {
+        double x[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) x[u] = ld_stream(d + i + u * stride);
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) accumulate(x[u]);
+    }
+    for (; i < n; i += stride) accumulate(d[i]);
+    const int ops[4] = {OP_SUM, OP_SUM, OP_SUM, OP_SUM};
+    grid_reduce<4>(v, ops, ws, smem, [&](double(&r)[4]) {
+        if (P.world > 1 && !p2p_allreduce_sum<4>(r, P)) {
+            scratch[kBsTries] = 3.0;
+            return;
+        }
+        beta_newton_update(st, scratch, r[0], r[1], r[2], r[3]);
+    });
+}
+
+// The node pass: sums at a + k h, k = 0..8, of the tree node around the root estimate, weights E r^k as in the
+// three-level pass; the last block decides (beta_node_decide).
+constexpr int kNodeBlocksPerSm = 4;
+__global__ void __launch_bounds__(kBlock, 2) beta_node_kernel(const double* __restrict__ d, int64_t n,
+                                                              asp_beta_state_t* st, double* __restrict__ scratch,
+                                                              ReduceWs* ws, const asp_peer_t P) {
+    __shared__ double smem[2 * kBsNode * 32];
+    if (st->phase != 1 || scratch[kBsTries] >= 3.0 || st->reserved == -1) return;  // uniform across the grid
+    double a, b;
+    int depth;
+    beta_node(st, scratch[kBsRoot], a, b, depth);
+    const double d_max = st->d_max;
+    const double db0 = a - st->beta_prev;
+    const double h = (b - a) * 0.125;
+    double v[2 * kBsNode];
+    int ops[2 * kBsNode];
+#pragma unroll
+    for (int k = 0; k < 2 * kBsNode; ++k) {
+        v[k] = 0.0;
+        ops[k] = OP_SUM;
+    }
+    auto accumulate = [&](double x) {
+        const double t = x - d_max;  // <= 0
+        double e = db0 > 0.0 ? exp(db0 * t) : 1.0;  // db0 == 0: 0 * (-inf) would be NaN for a zero-weight particle
+        const double r = exp(h * t);
+        v[0] += e;
+        v[1] = fma(e, e, v[1]);
+#pragma unroll
+        for (int k = 1; k < kBsNode; ++k) {
+            e *= r;
+            v[2 * k] += e;
+            v[2 * k + 1] = fma(e, e, v[2 * k + 1]);
+        }
+    };
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + (kUnroll - 1) * stride < n; i += kUnroll * stride) {
+        double x[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) x[u] = ld_stream(d + i + u * stride);
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) accumulate(x[u]);
+    }
+    for (; i < n; i += stride) accumulate(d[i]);
+    grid_reduce<2 * kBsNode>(v, ops, ws, smem, [&](double(&r)[2 * kBsNode]) {
+        if (P.world > 1) {  // two mailbox rounds: a slot holds 15 values
+            double lo[14], hi[4];
+#pragma unroll
+            for (int k = 0; k < 14; ++k) lo[k] = r[k];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) hi[k] = r[14 + k];
+            const bool ok = p2p_allreduce_sum<14>(lo, P) && p2p_allreduce_sum<4>(hi, P);
+            if (!ok) {
+                st->reserved = -1;
+                return;
+            }
+#pragma unroll
+            for (int k = 0; k < 14; ++k) r[k] = lo[k];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) r[14 + k] = hi[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 2 * kBsNode; ++k) scratch[k] = r[k];
+        beta_node_decide(st, scratch);
+    });
+}
+
+// ---------------------------------------------------------------------------
 // resampling weights, evidence-variance sum, exact-scan tile statistics
 // one block handles one ASP_CDF_TILE (=2048) tile per iteration
 // ---------------------------------------------------------------------------
@@ -491,6 +689,39 @@ int asp_beta_search_pass3(const double* d_d, int64_t n, asp_beta_state_t* d_stat
     beta_pass3_kernel<<<grid_for(n, kUnroll), kBlock, 0, (cudaStream_t)stream>>>(d_d, n, d_state, d_sums, fused_decide,
                                                                                  (ReduceWs*)ws, none);
     return check_launch("asp_beta_search_pass3");
+}
+
+/* Root-guided search (beta_math.cuh): call after the beta = 1 pass.  d_scratch: asp_beta_search_scratch_words()
+ * doubles.  peer may be NULL (one GPU). */
+int32_t asp_beta_search_scratch_words(void) { return kBsWords; }
+
+int asp_beta_search_root(const double* d_d, int64_t n, asp_beta_state_t* d_state, double* d_scratch,
+                         const asp_peer_t* peer, void* ws, void* stream) {
+    ASP_DEVICE_OR_RETURN();
+    ASP_REQUIRE(d_d && d_state && d_scratch && ws, "null pointer");
+    ASP_REQUIRE(n > 0, "n must be positive");
+    asp_peer_t P = {};
+    if (peer) {
+        int rc = check_peer(peer);
+        if (rc) return rc;
+        P = *peer;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    static bool attr_set = false;
+    const size_t smem = sizeof(float) * kSubSamples;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(beta_sub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return ASP_ERR_CUDA;
+        attr_set = true;
+    }
+    beta_sub_kernel<<<1, kSubBlock, smem, s>>>(d_d, n, d_state, d_scratch, P);
+    const int g = grid_for(n, kUnroll, kBlock, 4);
+    beta_newton_kernel<<<g, kBlock, 0, s>>>(d_d, n, d_state, d_scratch, 0, (ReduceWs*)ws, P);
+    beta_newton_kernel<<<g, kBlock, 0, s>>>(d_d, n, d_state, d_scratch, 1, (ReduceWs*)ws, P);
+    const int gn = grid_for(n, kUnroll, kBlock, kNodeBlocksPerSm);
+    for (int attempt = 0; attempt < 3; ++attempt)
+        beta_node_kernel<<<gn, kBlock, 0, s>>>(d_d, n, d_state, d_scratch, (ReduceWs*)ws, P);
+    return check_launch("asp_beta_search_root");
 }
 
 int asp_beta_search_decide3(asp_beta_state_t* d_state, const double* d_sums, void* stream) {

@@ -120,7 +120,7 @@ _STATE_WORDS = C.sizeof(_lib.BetaState) // 8
 
 
 def beta_search(d, stats, beta_prev: float, target_eff: float, tol: float, n_total: int | None = None,
-                allreduce=None, multi_level: bool = True, peer=None) -> _lib.BetaState:
+                allreduce=None, multi_level: bool = True, peer=None, root_guided: bool | None = None) -> _lib.BetaState:
     """Device-driven bisection of ``determine_beta`` (smc/base.py:166-186).
 
     ``multi_level`` (default) resolves three bisection levels per pass over ``d`` (``asp_beta_search_pass3``),
@@ -129,9 +129,15 @@ def beta_search(d, stats, beta_prev: float, target_eff: float, tol: float, n_tot
     (multi-GPU) is called on the two-element sums tensor between a pass and its
     decision.  ``peer`` (a ``_lib.PeerDesc``, multi-GPU) replaces that with the all-reduce done inside the pass
     kernel over NVLink peer memory (``asp_beta_search_pass_p2p``): one launch per pass and no NCCL call.
+    ``root_guided`` (default: whenever the sums need no host-side all-reduce) estimates the root of ESS/N = target
+    first and evaluates only the tree node of the reference's bisection that contains it
+    (``asp_beta_search_root``): same state, ~2.5x fewer passes over ``d``; the three-level passes launched after
+    it are no-ops unless the node was missed three times.
     Returns the final state (one device->host read)."""
     lib = _lib.load()
     d, stats = _f64(d, "d"), _f64(stats, "stats")
+    if root_guided is None:
+        root_guided = multi_level and (allreduce is None or peer is not None)
     n = d.numel()
     n_total = float(n if n_total is None else n_total)
     state = torch.zeros(_STATE_WORDS, dtype=torch.float64, device=d.device)
@@ -159,6 +165,10 @@ def beta_search(d, stats, beta_prev: float, target_eff: float, tol: float, n_tot
             single_pass()
     else:
         single_pass()  # ESS at beta = 1 (smc/base.py:170-175), then three bisection levels per pass
+        if root_guided:
+            scratch = torch.zeros(lib.asp_beta_search_scratch_words(), dtype=torch.float64, device=d.device)
+            check(lib.asp_beta_search_root(d.data_ptr(), n, state.data_ptr(), scratch.data_ptr(), peer_ref, ws, st),
+                  "asp_beta_search_root")
         for _ in range(lib.asp_beta_search_max_passes3(beta_prev, tol)):
             if peer is not None:
                 check(lib.asp_beta_search_pass_p2p(d.data_ptr(), n, state.data_ptr(), 1, sums.data_ptr(), peer_ref, ws,

@@ -162,6 +162,18 @@ int asp_beta_search_max_passes3(double beta_prev, double tol);
 int asp_beta_search_pass3(const double* d_d, int64_t n, asp_beta_state_t* d_state, double* d_sums, int fused_decide,
                           void* ws, void* stream);
 int asp_beta_search_decide3(asp_beta_state_t* d_state, const double* d_sums, void* stream);
+/* Root-guided search (csrc/beta_math.cuh): ESS(beta) is non-increasing, so every decision of the reference's
+ * bisection is "mid <= beta*".  After the beta = 1 pass: a subsample bisection and up to two Newton passes
+ * estimate the root, the reference's recursion is replayed towards it down to the tree node of width <= 8 tol,
+ * and ONE pass evaluates that node's end points (which prove the root is inside: every earlier decision follows
+ * by monotonicity) and its seven interior candidates (the last three decisions, as asp_beta_search_pass3).
+ * Same beta, bracket, sums and n_evals as the plain search; a miss is retried on the neighbouring node, and
+ * after three misses the state is still that of the beta = 1 pass, so the asp_beta_search_pass3 passes that the
+ * caller launches afterwards (no-ops once the search is done) finish it.  d_scratch:
+ * asp_beta_search_scratch_words() doubles; peer (multi-GPU mailboxes, asp_beta_search_pass_p2p) may be NULL. */
+int32_t asp_beta_search_scratch_words(void);
+int asp_beta_search_root(const double* d_d, int64_t n, asp_beta_state_t* d_state, double* d_scratch,
+                         const asp_peer_t* peer, void* ws, void* stream);
 
 /* ---- resampling weights + evidence bookkeeping (K4/K5 front end) --------
  * p_i = exp(dbeta d_i - c - log S1) (== exp(lw - lse(lw)), src/aspire/samples.py:1277),

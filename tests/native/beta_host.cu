@@ -11,4 +11,14 @@ void beta_host_init(asp_beta_state_t* st, double beta_prev, double target_eff, d
 void beta_host_decide(asp_beta_state_t* st) { asp::beta_decide(st); }
 void beta_host_decide3(asp_beta_state_t* st, const double* sums) { asp::beta_decide3(st, sums); }
 int beta_host_candidates(void) { return asp::kBetaCand; }
+// root-guided search: the node the pass evaluates, the Newton update, the node decision
+void beta_host_node(const asp_beta_state_t* st, double root, double* a, double* b, int* depth) {
+    asp::beta_node(st, root, *a, *b, *depth);
+}
+void beta_host_newton(const asp_beta_state_t* st, double* scratch, double s1, double s2, double d1, double d2) {
+    asp::beta_newton_update(st, scratch, s1, s2, d1, d2);
+}
+int beta_host_node_decide(asp_beta_state_t* st, double* scratch) { return asp::beta_node_decide(st, scratch); }
+int beta_host_scratch_words(void) { return asp::kBsWords; }
+int beta_host_scratch_root(void) { return asp::kBsRoot; }
 }
