@@ -54,7 +54,14 @@ def main():
                                                         peer=eng._peer.desc))
         _, ms_nccl = timed(lambda: ops.beta_search(d, stats, 0.0, 0.5, 1e-6, n_total=n_total,
                                                    allreduce=comm.all_reduce_sum))
-        assert bytes(via_p2p) == bytes(via_nccl), (via_p2p.beta_min, via_nccl.beta_min)
+        # root-guided search over the mailboxes (default) against the plain bisection over NCCL: the same bracket,
+        # evaluation count and sums; the plain bisection over the mailboxes: the same state bit for bit
+        assert (via_p2p.beta_min, via_p2p.beta_max, via_p2p.n_evals, via_p2p.min_valid, via_p2p.eff_beta_max) == (
+            via_nccl.beta_min, via_nccl.beta_max, via_nccl.n_evals, via_nccl.min_valid, via_nccl.eff_beta_max)
+        assert abs(via_p2p.s1_min - via_nccl.s1_min) <= 1e-12 * via_nccl.s1_min
+        assert abs(via_p2p.s2_min - via_nccl.s2_min) <= 1e-12 * via_nccl.s2_min
+        plain_p2p = ops.beta_search(d, stats, 0.0, 0.5, 1e-6, n_total=n_total, peer=eng._peer.desc, root_guided=False)
+        assert bytes(plain_p2p) == bytes(via_nccl), (plain_p2p.beta_min, via_nccl.beta_min)
         p2p_note = f"in-kernel all-reduce over {eng._peer.how}: {ms_p2p:.3f} ms per search, NCCL {ms_nccl:.3f} ms"
     if eng._peer is not None:
         # the exact-CDF carry chain through the mailboxes against send / recv / broadcast: same slice, bit for bit
