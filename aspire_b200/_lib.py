@@ -150,6 +150,7 @@ SIGNATURES = {
     "asp_beta_search_pass3": (C.c_int, [_P, _I64, _P, _P, C.c_int, _P, _P]),
     "asp_beta_search_decide3": (C.c_int, [_P, _P, _P]),
     "asp_beta_search_scratch_words": (_I32, []),
+    "asp_beta_search_run": (C.c_int, [_P, _I64, _P, _D, _D, _D, _D, _P, _P, _P, _P, _P]),
     "asp_beta_search_root": (C.c_int, [_P, _I64, _P, _P, _P, _P, _P]),
     "asp_beta_search_pass_p2p": (C.c_int, [_P, _I64, _P, C.c_int, _P, _P, _P, _P]),
     "asp_smc_weights": (C.c_int, [_P, _I64, _D, _D, _D, _D, _P, _P, _P, _P, _P]),
@@ -180,6 +181,7 @@ SIGNATURES = {
     "asp_gather_rows": (C.c_int, [_P, _I32, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _P]),
     "asp_moments_workspace_bytes": (C.c_size_t, [_I32]),
     "asp_weighted_moments": (C.c_int, [_P, _I32, _P, _P, _I64, _D, _D, _P, _P, _P]),
+    "asp_moments_finish": (C.c_int, [_P, _I32, _D, _P, _P, _P]),
     "asp_pcn_sweep": (
         C.c_int,
         [_P, _P, _P, _P, _P, _I64, _I32, C.POINTER(Density), C.POINTER(Density), C.POINTER(Density),
@@ -238,7 +240,8 @@ KERNELS_PER_CALL = {"asp_importance_weights": 3, "asp_cdf_exact": 6, "asp_cdf_ti
                     "asp_search_multinomial_guided": 4, "asp_select_uniforms": 3, "asp_search_systematic": 3,
                     "asp_search_systematic_workspace_bytes": 0, "asp_pcn_propose_eval_supported": 0, "asp_beta_search_max_passes3": 0,
                     "asp_sorted_tiles": 0, "asp_search_sorted": 2,
-                    "asp_beta_search_root": 6, "asp_beta_search_scratch_words": 0}
+                    "asp_beta_search_run": (C.c_int, [_P, _I64, _P, _D, _D, _D, _D, _P, _P, _P, _P, _P]),
+    "asp_beta_search_root": 6, "asp_beta_search_run": 8, "asp_beta_search_scratch_words": 0}
 launch_count = 0
 
 

@@ -278,6 +278,18 @@ __global__ void __launch_bounds__(kBlock) moments_kernel(const double* __restric
     }
 }
 
+// mean / std of the reference measure from the moment sums {sum w, sum w x_j, sum w x_j^2}
+__global__ void moments_finish_kernel(const double* __restrict__ m, int dims, double floor, double* __restrict__ mu,
+                                      double* __restrict__ sigma) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= dims) return;
+    const double sw = m[0];
+    const double mean = m[1 + j] / sw;
+    const double var = m[1 + dims + j] / sw - mean * mean;  // one-pass form, as oracle/pcn.py::weighted_moments
+    mu[j] = mean;
+    sigma[j] = fmax(sqrt(fmax(var, 0.0)), floor);
+}
+
 }  // namespace asp
 
 using namespace asp;
@@ -465,6 +477,15 @@ int asp_weighted_moments(const double* d_x, int32_t dims, const int64_t* d_idx, 
     ASP_DISPATCH_G(g, (moments_kernel<G><<<grid, kBlock, smem, (cudaStream_t)stream>>>(d_x, dims, d_idx, d_d, n, dbeta, c,
                                                                                       d_moments, (MomentsWs*)ws)));
     return check_launch("asp_weighted_moments");
+}
+
+int asp_moments_finish(const double* d_moments, int32_t dims, double sigma_floor, double* d_mu, double* d_sigma,
+                       void* stream) {
+    ASP_DEVICE_OR_RETURN();
+    ASP_REQUIRE(d_moments && d_mu && d_sigma, "null pointer");
+    ASP_REQUIRE(dims > 0, "dims must be positive");
+    moments_finish_kernel<<<(dims + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_moments, dims, sigma_floor, d_mu, d_sigma);
+    return check_launch("asp_moments_finish");
 }
 
 }  // extern "C"

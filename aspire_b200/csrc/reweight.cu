@@ -724,6 +724,26 @@ int asp_beta_search_root(const double* d_d, int64_t n, asp_beta_state_t* d_state
     return check_launch("asp_beta_search_root");
 }
 
+/* The whole common path in one call: init, the beta = 1 pass, the root-guided search.  The caller reads the state
+ * back and launches asp_beta_search_pass3 passes only if phase != 2 (three missed nodes). */
+int asp_beta_search_run(const double* d_d, int64_t n, const double* d_stats, double beta_prev, double target_eff,
+                        double tol, double n_total, asp_beta_state_t* d_state, double* d_scratch,
+                        const asp_peer_t* peer, void* ws, void* stream) {
+    ASP_DEVICE_OR_RETURN();
+    ASP_REQUIRE(d_d && d_stats && d_state && d_scratch && ws, "null pointer");
+    ASP_REQUIRE(n > 0, "n must be positive");
+    asp_peer_t P = {};
+    if (peer) {
+        int rc = check_peer(peer);
+        if (rc) return rc;
+        P = *peer;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    beta_init_kernel<<<1, 1, 0, s>>>(d_state, beta_prev, target_eff, tol, n_total, d_stats);
+    beta_pass_kernel<<<grid_for(n, kUnroll), kBlock, 0, s>>>(d_d, n, d_state, 1, (ReduceWs*)ws, P);
+    return asp_beta_search_root(d_d, n, d_state, d_scratch, peer, ws, stream);
+}
+
 int asp_beta_search_decide3(asp_beta_state_t* d_state, const double* d_sums, void* stream) {
     ASP_DEVICE_OR_RETURN();
     ASP_REQUIRE(d_state && d_sums, "null pointer");

@@ -81,31 +81,45 @@ __global__ void __launch_bounds__(kSpBlock) spacings_kernel(PhiloxKeys K, uint32
     }
 }
 
-// exclusive prefix of the tile sums and the grand total (one block; integer sums: the order is immaterial)
+// exclusive prefix of the tile sums and the grand total (one block; integer sums: the order is immaterial).
+// Thread t owns the contiguous chunk [t per, (t + 1) per); loads are issued eight at a time so that the chunk's
+// latency is paid once, not per element.
 __global__ void __launch_bounds__(1024) tile_scan_kernel(const unsigned long long* __restrict__ sums, int64_t n_tiles,
                                                          unsigned long long* __restrict__ prefix,
                                                          unsigned long long* __restrict__ total) {
-    __shared__ uint64_t s_part[1024];
+    __shared__ uint64_t s_warp[32];
     const int64_t per = (n_tiles + blockDim.x - 1) / blockDim.x;
     const int64_t a = (int64_t)threadIdx.x * per, b = a + per < n_tiles ? a + per : n_tiles;
     uint64_t s = 0;
-    for (int64_t t = a; t < b; ++t) s += sums[t];
-    s_part[threadIdx.x] = s;
+    for (int64_t t = a; t < b; t += 8) {
+        uint64_t v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = t + i < b ? __ldg(sums + t + i) : 0ull;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += v[i];
+    }
+    // block exclusive scan of the chunk sums
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint64_t incl = warp_scan_incl_u64(s);
+    if (lane == 31) s_warp[wid] = incl;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        uint64_t run = 0;
-        for (int i = 0; i < (int)blockDim.x; ++i) {
-            const uint64_t t = s_part[i];
-            s_part[i] = run;
-            run += t;
-        }
-        *total = run;
+    if (wid == 0) {
+        const uint64_t w = s_warp[lane];
+        const uint64_t wi = warp_scan_incl_u64(w);
+        s_warp[lane] = wi - w;
+        if (lane == 31) *total = wi;
     }
     __syncthreads();
-    uint64_t run = s_part[threadIdx.x];
-    for (int64_t t = a; t < b; ++t) {
-        prefix[t] = run;
-        run += sums[t];
+    uint64_t run = s_warp[wid] + incl - s;
+    for (int64_t t = a; t < b; t += 8) {
+        uint64_t v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = t + i < b ? __ldg(sums + t + i) : 0ull;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (t + i < b) prefix[t + i] = run;
+            run += v[i];
+        }
     }
 }
 

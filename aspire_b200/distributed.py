@@ -207,6 +207,10 @@ class ShardedSMC:
         self._stream = 0
         self._peer = False  # mailboxes of the in-kernel all-reduce: False = not tried yet, None = NCCL
 
+    def reset(self):
+        """Forget the cached particle count (a different particle set is about to be stepped)."""
+        self._n_total = None
+
     def next_stream(self, count=1):
         s = self._stream
         self._stream += count
@@ -220,24 +224,24 @@ class ShardedSMC:
 
     # -- exact CDF over all ranks -------------------------------------------------
     def global_cdf(self, p, tiles, info, n_total, mark=None):
-        """-> (local slice of the global normalised CDF, lo, hi): this rank's slice covers (lo, hi]."""
+        """-> (local slice of the global normalised CDF, chain, gathered): ``chain`` = device
+        [exact running sum in front of this slice, exact total] (this slice covers (chain[0] / chain[1], ...]),
+        ``gathered`` = device [G, 4] {sum p, max p, var-sum, n} of every rank.  No device -> host read."""
         ops, comm = self.ops, self.comm
         r, g = comm.rank, comm.world
         dev = p.device
         gathered = comm.all_gather(info)                     # [G, 4] = {sum p, max p, var-sum, n}
-        host = gathered.cpu()
-        offset = float(host[:r, 0].sum()) if r > 0 else 0.0
-        max_in = float(host[:r, 1].max()) if r > 0 else 0.0
-        carry = torch.tensor([offset, max_in, 0.0, float(n_total)], dtype=torch.float64, device=dev)
+        carry = torch.zeros(4, dtype=torch.float64, device=dev)
+        carry[3] = float(n_total)
+        if r > 0:                                            # approximate offset / running max of the ranks in front
+            carry[0] = gathered[:r, 0].sum()
+            carry[1] = gathered[:r, 1].max()
         ops.cdf_plan_aggregate(p, tiles, carry)
         if mark:
             mark("cdf_local")
         if self._peer:                                       # carry chain + total through the peers' mailboxes
             cdf, chain = ops.cdf_resolve_write_p2p(p, self._peer.desc)
-            c_in, th, c_last = torch.stack([chain[0], chain[1], cdf[-1]]).tolist()   # one device -> host read
-            if not (math.isfinite(th) and math.isfinite(c_in)):
-                raise RuntimeError("exact CDF: a peer GPU did not hand over its running sum within 20 s")
-            return cdf, (c_in / th if r > 0 else 0.0), (1.0 if r == g - 1 else c_last), host
+            return cdf, chain, gathered
         if r > 0:                                            # exact carry chain: rank r-1 -> r
             inc = torch.empty(2, dtype=torch.float64, device=dev)
             comm.recv(inc, r - 1)
@@ -249,36 +253,42 @@ class ShardedSMC:
         total = carry_out[:1].clone()
         comm.broadcast(total, g - 1)
         cdf = ops.cdf_write(p, total)
-        th, c_in, c_last = torch.stack([total[0], carry[2], cdf[-1]]).tolist()   # one device -> host read
-        lo = c_in / th if r > 0 else 0.0                     # == global cdf just before this slice (IEEE division)
-        hi = 1.0 if r == g - 1 else c_last
-        return cdf, lo, hi, host
+        return cdf, torch.stack([carry[2], total[0]]), gathered
+
+    @staticmethod
+    def slice_bounds(chain, cdf, rank, world):
+        """(lo, hi) host floats of the slice (one device -> host read; tests and diagnostics)."""
+        c_in, th, c_last = torch.stack([chain[0], chain[1], cdf[-1]]).tolist()
+        return (c_in / th if rank > 0 else 0.0), (1.0 if rank == world - 1 else c_last)
 
     # -- one tempering step ---------------------------------------------------------
     def step(self, shard: Shard, beta_prev: float, u_all=None, mark=None) -> tuple[Shard, StepRecord]:
+        """Three device -> host reads per step: the search state (beta), the slot boundaries (launch sizes) and the
+        step record at the end."""
         ops, comm = self.ops, self.comm
         mark = mark or (lambda name: None)
         dev = shard.x.device
         n_local = len(shard)
         d, stats_local = ops.reweight(shard.log_l, shard.log_p, shard.log_q)
         stats = self.global_stats(stats_local)
-        counts = torch.tensor([float(n_local)], dtype=torch.float64, device=dev)
-        comm.all_reduce_sum(counts)
-        st = stats.cpu().numpy()
-        n_total = int(round(float(counts[0])))
-        if st[2] > 0 or st[3] > 0:
-            raise ValueError(f"Log weights contain NaN values for beta={beta_prev}")
+        if self.__dict__.get("_n_total") is None:            # rebalanced shards keep their sizes: counted once per
+            counts = torch.tensor([float(n_local)], dtype=torch.float64, device=dev)  # engine (``reset`` recounts);
+            comm.all_reduce_sum(counts)                      # every step re-checks the total in its last read
+            self._n_total = int(round(float(counts[0])))
+        n_total = self._n_total
         if self._peer is False:
             self._peer = PeerMailboxes.create(comm, dev) if dev.type == "cuda" and comm.world > 1 else None
         state = ops.beta_search(d, stats, beta_prev, self.target_efficiency, self.beta_tolerance, n_total=n_total,
                                 allreduce=comm.all_reduce_sum,
                                 **({} if self._peer is None else {"peer": self._peer.desc}))
         mark("beta_search")
+        if state.n_nan > 0 or state.n_inf > 0:               # the all-reduced counters travel with the state
+            raise ValueError(f"Log weights contain NaN values for beta={beta_prev}")
         beta = min(max(state.beta_min, beta_prev), 1.0)
         if beta == beta_prev:
             raise RuntimeError(f"Beta did not increase from previous value {beta:.6g}.")
         dbeta = beta - beta_prev
-        c = dbeta * st[1]
+        c = dbeta * state.d_max
         if state.min_valid:
             s1, s2 = state.s1_min, state.s2_min
         else:  # not reachable with max_beta_step = 1: beta* is always an evaluated beta
@@ -286,9 +296,8 @@ class ShardedSMC:
             comm.all_reduce_sum(sums)
             s1, s2 = float(sums[0]), float(sums[1])
         p, result, tiles = ops.smc_weights(d, dbeta, c, s1, n_total=n_total)
-        info = torch.stack([result[1], tiles[1::2].max(), result[0], counts[0] * 0 + n_local]).contiguous()
-        cdf, lo, hi, host = self.global_cdf(p, tiles, info, n_total, mark)
-        var_sum = float(host[:, 2].sum())
+        info = torch.stack([result[1], tiles[1::2].max(), result[0], result[0] * 0 + n_local]).contiguous()
+        cdf, chain, gathered = self.global_cdf(p, tiles, info, n_total, mark)
         mean_u = s1 / n_total
         mark("cdf")
         # owner-computes multinomial resampling at sorted uniforms
@@ -302,9 +311,11 @@ class ShardedSMC:
         sums = torch.zeros(per, dtype=torch.int64, device=dev)
         sums[:sp.n_tiles] = sp.tile_sums
         sp.scan(comm.all_gather(sums).reshape(-1)[:tiles_total].contiguous() if g > 1 else sp.tile_sums)
-        lo_all = comm.all_gather(torch.tensor([lo], dtype=torch.float64, device=dev)).reshape(-1) if g > 1 else \
-            torch.zeros(1, dtype=torch.float64, device=dev)
+        lo_dev = (chain[0] / chain[1]).reshape(1) if r > 0 else torch.zeros(1, dtype=torch.float64, device=dev)
+        lo_all = comm.all_gather(lo_dev).reshape(-1) if g > 1 else lo_dev
         bounds = ops.sorted_bounds(sp, lo_all, n_total)          # host ints J_0 .. J_G: rank s owns slots [J_s, J_s+1)
+        if bounds is None:
+            raise RuntimeError("exact CDF: a peer GPU did not hand over its running sum within 20 s")
         j_lo, j_hi = bounds[r], bounds[r + 1]
         n_out = j_hi - j_lo
         mark("select")
@@ -320,8 +331,7 @@ class ShardedSMC:
         else:
             mom = torch.zeros(1 + 2 * dims, dtype=torch.float64, device=dev)
         comm.all_reduce_sum(mom)
-        mu, sigma = ops.moments_to_mu_sigma(mom, dims)
-        sigma = torch.clamp_min(sigma, 1e-150)
+        mu, sigma = ops.moments_to_mu_sigma(mom, dims, floor=1e-150)
         mark("moments")
         prm = ops.make_pcn_params(beta, self.rho, mu, sigma, self.n_moves, seed=self.seed,
                                   stream0=self.next_stream(self.n_moves) + 0x40000000, index0=j_lo,
@@ -353,11 +363,16 @@ class ShardedSMC:
         self.exchange(src, src_off, j_lo, j_hi, bufs, margin, bounds, target)
         mark("exchange")
         comm.all_reduce_sum(acc)
+        acc_sum, var_sum, n_seen = torch.stack([acc[0], gathered[:, 2].sum(), gathered[:, 3].sum()]).tolist()  # the step's device -> host read
+        if int(round(n_seen)) != n_total:                    # the same on every rank: everybody raises
+            self._n_total = None
+            raise RuntimeError(f"the shards hold {int(round(n_seen))} particles, the engine counted {n_total}: "
+                               "call reset() before stepping a different particle set")
         rec = StepRecord(
             beta=beta, ess=s1 * s1 / s2, ess_target=state.eff_beta_max * n_total,
             log_norm_ratio=c + math.log(s1) - math.log(n_total),
             log_norm_ratio_var=var_sum / n_total / (n_total * mean_u * mean_u) if mean_u != 0 else math.nan,
-            acceptance=float(acc[0]) / max(self.n_moves * n_total, 1), n_total=n_total, n_local_out=n_out,
+            acceptance=acc_sum / max(self.n_moves * n_total, 1), n_total=n_total, n_local_out=n_out,
             n_beta_evals=state.n_evals)
         x, ll, lp, lq = (t[margin:margin + n_keep] for t in bufs)
         return Shard(x, ll, lp, lq, a_lo), rec
@@ -520,6 +535,7 @@ def _host_buffer_leg(args, comm, engine, shard0, n_total, dev, unit):
         moved[1] += k * row_bytes
 
     steps = max(1, min(args.steps, 3))
+    engine.reset()  # a different particle count than the device-resident leg
     step()
     torch.cuda.synchronize()
     comm.barrier()
@@ -536,6 +552,7 @@ def _host_buffer_leg(args, comm, engine, shard0, n_total, dev, unit):
     tot = torch.tensor([float(m), moved[0] / steps, moved[1] / steps], dtype=torch.float64, device=dev)
     comm.all_reduce_sum(tot)
     ms = float(t[0])
+    engine.reset()
     return {"value": float(tot[0]) / (ms * 1e-3), "unit": unit, "h2d_bytes_per_step": int(tot[1]),
             "d2h_bytes_per_step": int(tot[2]), "particles": int(tot[0]), "ms_per_step": ms, "steps": steps,
             "api": "ShardedSMC.step on pinned host buffers, one PCIe link per rank (H2D + step + D2H timed, max over ranks)"}

@@ -140,14 +140,22 @@ def beta_search(d, stats, beta_prev: float, target_eff: float, tol: float, n_tot
         root_guided = multi_level and (allreduce is None or peer is not None)
     n = d.numel()
     n_total = float(n if n_total is None else n_total)
-    state = torch.zeros(_STATE_WORDS, dtype=torch.float64, device=d.device)
+    words = lib.asp_beta_search_scratch_words()
+    buf = torch.zeros(_STATE_WORDS + words + 4, dtype=torch.float64, device=d.device)
+    state, scratch = buf[:_STATE_WORDS], buf[_STATE_WORDS:_STATE_WORDS + words]
+    buf[_STATE_WORDS + words:] = stats  # read back with the state: min / max / #NaN / #inf of d
     ws = reduce_ws(d.device).data_ptr()
     st = _stream()
-    check(lib.asp_beta_search_init(state.data_ptr(), beta_prev, target_eff, tol, n_total, stats.data_ptr(), st),
-          "asp_beta_search_init")
     sums = torch.zeros(14, dtype=torch.float64, device=d.device)
-
     peer_ref = None if peer is None else C.byref(peer)
+
+    def read_state():
+        host = buf.cpu().numpy()  # the search's one device -> host read
+        out = _lib.BetaState.from_buffer_copy(host[:_STATE_WORDS].tobytes())
+        out.n_nan, out.n_inf = float(host[-2]), float(host[-1])
+        if out.reserved == -1:
+            raise AspireB200Error("beta bisection: a peer GPU did not reach the in-kernel all-reduce within 20 s")
+        return out
 
     def single_pass():
         if peer is not None:
@@ -160,15 +168,7 @@ def beta_search(d, stats, beta_prev: float, target_eff: float, tol: float, n_tot
             allreduce(state[7:9])  # s1, s2
             check(lib.asp_beta_search_decide(state.data_ptr(), st), "asp_beta_search_decide")
 
-    if not multi_level:
-        for _ in range(lib.asp_beta_search_max_passes(beta_prev, tol)):
-            single_pass()
-    else:
-        single_pass()  # ESS at beta = 1 (smc/base.py:170-175), then three bisection levels per pass
-        if root_guided:
-            scratch = torch.zeros(lib.asp_beta_search_scratch_words(), dtype=torch.float64, device=d.device)
-            check(lib.asp_beta_search_root(d.data_ptr(), n, state.data_ptr(), scratch.data_ptr(), peer_ref, ws, st),
-                  "asp_beta_search_root")
+    def three_level_passes():
         for _ in range(lib.asp_beta_search_max_passes3(beta_prev, tol)):
             if peer is not None:
                 check(lib.asp_beta_search_pass_p2p(d.data_ptr(), n, state.data_ptr(), 1, sums.data_ptr(), peer_ref, ws,
@@ -181,10 +181,25 @@ def beta_search(d, stats, beta_prev: float, target_eff: float, tol: float, n_tot
                       "asp_beta_search_pass3")
                 allreduce(sums)
                 check(lib.asp_beta_search_decide3(state.data_ptr(), sums.data_ptr(), st), "asp_beta_search_decide3")
-    host = state.cpu().numpy().tobytes()
-    out = _lib.BetaState.from_buffer_copy(host)
-    if out.reserved == -1:
-        raise AspireB200Error("beta bisection: a peer GPU did not reach the in-kernel all-reduce within 20 s")
+
+    if root_guided:
+        # init, the beta = 1 pass and the root-guided search in one call; the plain passes only after three misses
+        check(lib.asp_beta_search_run(d.data_ptr(), n, stats.data_ptr(), beta_prev, target_eff, tol, n_total,
+                                      state.data_ptr(), scratch.data_ptr(), peer_ref, ws, st), "asp_beta_search_run")
+        out = read_state()
+        if out.phase == 2:
+            return out
+        three_level_passes()
+    else:
+        check(lib.asp_beta_search_init(state.data_ptr(), beta_prev, target_eff, tol, n_total, stats.data_ptr(), st),
+              "asp_beta_search_init")
+        if not multi_level:
+            for _ in range(lib.asp_beta_search_max_passes(beta_prev, tol)):
+                single_pass()
+        else:
+            single_pass()  # ESS at beta = 1 (smc/base.py:170-175), then three bisection levels per pass
+            three_level_passes()
+    out = read_state()
     if out.phase != 2:
         raise AspireB200Error("beta bisection did not converge within the planned number of passes")
     return out
@@ -387,8 +402,11 @@ def sorted_bounds(sp: SortedSpacings, lo_all: torch.Tensor, m: int) -> list:
     """Slot boundaries of the owner-computes partition: ``lo_all[s]`` is the global CDF value in front of rank s's
     slice; rank s owns the slots ``[J_s, J_{s+1})``, ``J_s = #{j : S_j < rint(lo_s total)}``, ``J_G = m``.
     -> host ints [J_0 .. J_G] (one device -> host read)."""
-    thr = torch.round(lo_all.to(torch.float64) * sp.total.to(torch.float64)).to(torch.int64).contiguous()
-    j = sp.lower_bound(thr).cpu().tolist()
+    thr_f = torch.round(lo_all.to(torch.float64) * sp.total.to(torch.float64))
+    j = sp.lower_bound(thr_f.nan_to_num(0.0).to(torch.int64).contiguous())
+    j = torch.where(torch.isfinite(thr_f), j, torch.full_like(j, -1)).cpu().tolist()   # one device -> host read
+    if min(j) < 0:
+        return None  # a non-finite CDF boundary: a peer never handed over its running sum
     j[0] = 0
     return [int(v) for v in j] + [int(m)]
 
@@ -442,12 +460,13 @@ def weighted_moments(x, d=None, dbeta: float = 0.0, c: float = 0.0, idx=None) ->
     return out
 
 
-def moments_to_mu_sigma(m: torch.Tensor, dims: int):
-    """One-pass mean / std from the moment sums (device tensors, no sync)."""
-    sw = m[0]
-    mu = m[1:1 + dims] / sw
-    var = m[1 + dims:1 + 2 * dims] / sw - mu * mu
-    return mu.contiguous(), torch.sqrt(torch.clamp_min(var, 0.0)).contiguous()
+def moments_to_mu_sigma(m: torch.Tensor, dims: int, floor: float = 0.0):
+    """One-pass mean / std (at least ``floor``) from the moment sums: one launch, device tensors, no sync."""
+    m = _f64(m, "moments")
+    out = torch.empty(2, dims, dtype=torch.float64, device=m.device)
+    check(_lib.load().asp_moments_finish(m.data_ptr(), dims, float(floor), out[0].data_ptr(), out[1].data_ptr(),
+                                         _stream()), "asp_moments_finish")
+    return out[0], out[1]
 
 
 def make_pcn_params(beta, rho, mu, sigma, n_moves, seed=0, stream0=0, index0=0, xi=None, log_u=None, slot=None,

@@ -482,8 +482,7 @@ class SMCSampler(Sampler):
             mom = ops.weighted_moments(particles.x, idx=idx)
         else:
             mom = ops.weighted_moments(particles.x)
-        mu, sigma = ops.moments_to_mu_sigma(mom, dims)
-        sigma = torch.clamp_min(sigma, 1e-150)
+        mu, sigma = ops.moments_to_mu_sigma(mom, dims, floor=1e-150)
         tpcn = getattr(self, "step_fn", "pcn") == "tpcn"
         nu = 0.0
         if tpcn:  # Student-t reference measure t_nu(mu, diag sigma^2) fitted to (a sample of) the ensemble

@@ -172,6 +172,10 @@ int asp_beta_search_decide3(asp_beta_state_t* d_state, const double* d_sums, voi
  * caller launches afterwards (no-ops once the search is done) finish it.  d_scratch:
  * asp_beta_search_scratch_words() doubles; peer (multi-GPU mailboxes, asp_beta_search_pass_p2p) may be NULL. */
 int32_t asp_beta_search_scratch_words(void);
+/* asp_beta_search_init + the beta = 1 pass + asp_beta_search_root in one call (one host -> driver round trip). */
+int asp_beta_search_run(const double* d_d, int64_t n, const double* d_stats, double beta_prev, double target_eff,
+                        double tol, double n_total, asp_beta_state_t* d_state, double* d_scratch,
+                        const asp_peer_t* peer, void* ws, void* stream);
 int asp_beta_search_root(const double* d_d, int64_t n, asp_beta_state_t* d_state, double* d_scratch,
                          const asp_peer_t* peer, void* ws, void* stream);
 
@@ -293,6 +297,10 @@ int asp_gather_rows(const double* d_x, int32_t dims, const int64_t* d_idx, int64
 size_t asp_moments_workspace_bytes(int32_t dims);
 int asp_weighted_moments(const double* d_x, int32_t dims, const int64_t* d_idx, const double* d_d, int64_t n,
                          double dbeta, double c, double* d_moments, void* ws, void* stream);
+
+/* mu_j = sum w x_j / sum w,  sigma_j = max(sqrt(max(sum w x_j^2 / sum w - mu_j^2, 0)), sigma_floor) */
+int asp_moments_finish(const double* d_moments, int32_t dims, double sigma_floor, double* d_mu, double* d_sigma,
+                       void* stream);
 
 typedef struct asp_pcn_params {
     double beta;          /* inverse temperature of the target                  */

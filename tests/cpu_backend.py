@@ -42,7 +42,8 @@ def beta_search(d, stats, beta_prev, target_eff, tol, n_total=None, allreduce=No
     dn_, st = _np(d), _np(stats)
     n_total = float(len(dn_) if n_total is None else n_total)
     s = types.SimpleNamespace(beta_min=beta_prev, beta_max=1.0, beta_try=1.0, eff_beta_max=0.0, s1_min=0.0,
-                              s2_min=0.0, min_valid=0, n_evals=0, phase=0)
+                              s2_min=0.0, min_valid=0, n_evals=0, phase=0, d_min=float(st[0]), d_max=float(st[1]),
+                              n_nan=float(st[2]), n_inf=float(st[3]))
     while s.phase != 2:
         db = s.beta_try - beta_prev
         c = db * (st[1] if db >= 0 else st[0])
@@ -175,11 +176,11 @@ def weighted_moments(x, d=None, dbeta=0.0, c=0.0, idx=None):
     return _t(np.concatenate([[float(len(rows))], rows.sum(0), (rows * rows).sum(0)]))
 
 
-def moments_to_mu_sigma(m, dims):
+def moments_to_mu_sigma(m, dims, floor=0.0):
     sw = m[0]
     mu = m[1:1 + dims] / sw
     var = m[1 + dims:1 + 2 * dims] / sw - mu * mu
-    return mu.contiguous(), torch.sqrt(torch.clamp_min(var, 0.0)).contiguous()
+    return mu.contiguous(), torch.clamp_min(torch.sqrt(torch.clamp_min(var, 0.0)), floor).contiguous()
 
 
 def make_pcn_params(beta, rho, mu, sigma, n_moves, seed=0, stream0=0, index0=0, xi=None, log_u=None, slot=None,

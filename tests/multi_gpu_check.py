@@ -68,10 +68,12 @@ def main():
         dbeta = via_nccl.beta_min
         pw, result, tiles = ops.smc_weights(d, dbeta, dbeta * float(stats[1]), via_nccl.s1_min, n_total=n_total)
         info = torch.stack([result[1], tiles[1::2].max(), result[0], result[0] * 0 + len(shard)]).contiguous()
-        cdf_a, lo_a, hi_a, _ = eng.global_cdf(pw, tiles, info, n_total)
+        cdf_a, chain_a, _ = eng.global_cdf(pw, tiles, info, n_total)
         keep, eng._peer = eng._peer, None
-        cdf_b, lo_b, hi_b, _ = eng.global_cdf(pw, tiles, info, n_total)
+        cdf_b, chain_b, _ = eng.global_cdf(pw, tiles, info, n_total)
         eng._peer = keep
+        lo_a, hi_a = eng.slice_bounds(chain_a, cdf_a, r, g)
+        lo_b, hi_b = eng.slice_bounds(chain_b, cdf_b, r, g)
         assert torch.equal(cdf_a, cdf_b) and (lo_a, hi_a) == (lo_b, hi_b), (lo_a, lo_b, hi_a, hi_b)
         _, ms_a = timed(lambda: eng.global_cdf(pw, tiles, info, n_total))
         eng._peer = None

@@ -141,10 +141,10 @@ class Doubles:
         return torch.cat([torch.tensor([float(len(x))], dtype=F64), x.sum(0), (x * x).sum(0)])
 
     @staticmethod
-    def moments_to_mu_sigma(m, dims):
+    def moments_to_mu_sigma(m, dims, floor=0.0):
         mu = m[1:1 + dims] / m[0]
         var = m[1 + dims:1 + 2 * dims] / m[0] - mu * mu
-        return mu.contiguous(), torch.sqrt(torch.clamp_min(var, 0.0)).contiguous()
+        return mu.contiguous(), torch.clamp_min(torch.sqrt(torch.clamp_min(var, 0.0)), floor).contiguous()
 
     # ---- RNG ----------------------------------------------------------------------------
     def philox_uniform(self, seed, stream_id, n, device, index0=0):
