@@ -47,6 +47,9 @@ class Flow:
     def fit(self, samples, **kwargs) -> FlowHistory:
         raise NotImplementedError
 
+    def check_error(self):
+        """Kernels that report failures through a device flag raise here (``CouplingFlow``); a no-op otherwise."""
+
 
 class TransformedFlow(Flow):
     """A flow that lives in the space of a data transform (``flows/torch/flows.py:327-387``: ``rescale`` /
@@ -57,6 +60,9 @@ class TransformedFlow(Flow):
     def __init__(self, inner: Flow, data_transform):
         super().__init__(inner.dims, inner.device, data_transform, None)
         self.inner = inner
+
+    def check_error(self):
+        self.inner.check_error()
 
     def fit(self, samples, **kwargs) -> FlowHistory:
         x = samples.x if hasattr(samples, "x") else samples
@@ -201,11 +207,21 @@ class CouplingFlow(Flow):
             self._struct = s
         return self._struct
 
-    def _check_error(self):
-        if int(self._struct._keep[3].item()) != 0:
+    def check_error(self):
+        """Raise if a tcgen05 flow kernel reported a tensor-core barrier time-out since the last check (the flag
+        is then reset).  One tiny device -> host read: the samplers call it where they synchronise anyway (after
+        the initial draw, after every mutation, after the importance weights), so a time-out can never feed
+        garbage log q into the weights or the accept test unnoticed."""
+        if getattr(self, "_struct", None) is None:
+            return
+        err = self._struct._keep[3]
+        if int(err.item()) != 0:
             from ._lib import AspireB200Error
 
+            err.zero_()
             raise AspireB200Error("tcgen05 flow kernel: a tensor-core barrier timed out")
+
+    _check_error = check_error
 
     # -- hot path ----------------------------------------------------------------
     def log_prob(self, x):

@@ -678,3 +678,64 @@ def transform_apply(x, kind, lower, upper, bounded: int, eps: float, mean=None, 
     check(fn(C.byref(t), x.data_ptr(), n, out.data_ptr(), _ptr(log_j), _stream()),
           "asp_transform_inverse" if inverse else "asp_transform_forward")
     return out, log_j
+
+
+# ---- device guard ------------------------------------------------------------------------------------------
+# Every C entry point launches on the CURRENT device with the current stream of that device.  The wrappers
+# therefore run on the device of their tensors: when that is not the current device (``Aspire(device="cuda:1")``
+# without a ``torch.cuda.set_device``), the call is made under ``torch.cuda.device(...)``, so the stream, the
+# workspaces and the launch all belong to the tensors' GPU; tensors on different GPUs are refused.
+def _tensor_device(args, kwargs):
+    dev = None
+    stack = list(args) + list(kwargs.values())
+    while stack:
+        a = stack.pop()
+        if isinstance(a, torch.Tensor):
+            if a.is_cuda:
+                if dev is None:
+                    dev = a.device
+                elif a.device != dev:
+                    raise AspireB200Error(f"tensors on different devices ({dev} and {a.device}) in one call")
+        elif isinstance(a, (list, tuple)):
+            stack.extend(a)
+        elif isinstance(a, SortedSpacings):
+            stack.append(a.__dict__.get("q"))
+        elif isinstance(a, (str, torch.device)) and not isinstance(a, bool):
+            try:
+                d = torch.device(a)
+            except (RuntimeError, TypeError):
+                continue
+            if d.type == "cuda" and d.index is not None and dev is None:
+                dev = d
+    return dev
+
+
+def _on_tensor_device(fn):
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        dev = _tensor_device(args, kwargs)
+        if dev is None or dev.index is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+
+    return wrapper
+
+
+def _install_device_guard():
+    import types
+
+    g = globals()
+    for name, obj in list(g.items()):
+        if name.startswith("_") or not isinstance(obj, types.FunctionType) or obj.__module__ != __name__:
+            continue
+        g[name] = _on_tensor_device(obj)
+    for cls in (SortedSpacings,):
+        for name, obj in list(vars(cls).items()):
+            if isinstance(obj, types.FunctionType) and name in ("__init__", "scan", "search", "lower_bound", "window"):
+                setattr(cls, name, _on_tensor_device(obj))
+
+
+_install_device_guard()

@@ -71,6 +71,13 @@ class Sampler:
     def log_prior(self, samples) -> torch.Tensor:
         return self._as_vec(self._log_prior(samples), len(samples))
 
+    def _check_flow(self) -> None:
+        """Flow kernels report failures (a tensor-core barrier time-out) through a device flag; the samplers read it
+        where they synchronise anyway and raise ``AspireB200Error`` instead of carrying garbage log q forward."""
+        check = getattr(self.prior_flow, "check_error", None)
+        if check is not None:
+            check()
+
     def _as_vec(self, v, n):
         t = torch.as_tensor(v, dtype=torch.float64, device=self.device).reshape(-1)
         if t.numel() != n:

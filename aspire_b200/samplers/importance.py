@@ -14,4 +14,5 @@ class ImportanceSampler(Sampler):
         samples.log_prior = self.log_prior(samples)          # prior first, then likelihood (importance.py:17-20)
         samples.log_likelihood = self.log_likelihood(samples)
         samples.compute_weights()                            # asp_importance_weights
+        self._check_flow()                                   # a kernel time-out must not reach the weights unnoticed
         return samples

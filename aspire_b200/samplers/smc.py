@@ -102,7 +102,9 @@ class SMCSampler(Sampler):
         while n_drawn < n_samples:
             x, log_q = self.prior_flow.sample_and_log_prob(n_samples)
             log_q = torch.as_tensor(log_q, dtype=torch.float64, device=self.device)
-            if not bool(torch.isfinite(log_q).all()):
+            finite = bool(torch.isfinite(log_q).all())
+            self._check_flow()  # a kernel time-out is reported as such, not as a bad proposal
+            if not finite:
                 raise ValueError(
                     "Proposal returned non-finite log probabilities. aspire assumes the proposal is a valid, "
                     "normalized probability distribution and should therefore only return samples with finite "
@@ -277,6 +279,8 @@ class SMCSampler(Sampler):
 
         samples.log_evidence = float(np.sum(np.asarray(self.history.log_norm_ratio)))
         samples.log_evidence_error = float(np.sqrt(np.sum(np.asarray(self.history.log_norm_ratio_var))))
+        if checkpoint_callback is not None:  # maybe_checkpoint(force=True), smc/base.py:476: the final state is
+            checkpoint_callback(self.build_checkpoint_state(samples, iterations, beta))  # written whatever checkpoint_every
         final = samples.to_standard_samples()
         logger.info(f"Log evidence: {final.log_evidence:.2f} +/- {final.log_evidence_error:.2f}")
         return final
@@ -447,6 +451,7 @@ class SMCSampler(Sampler):
         if mark:
             mark("pcn_sweep")
         acc = float(accepts[:n_moves].sum()) / max(n_moves * n, 1)
+        self._check_flow()
         self.history.mcmc_acceptance.append(acc)
         self.history.rho.append(self.rho)
         if self.sampler_kwargs.get("adapt_rho", True):
@@ -540,6 +545,7 @@ class SMCSampler(Sampler):
                 ops.pcn_accept(x, ll, lp, lq, xp, ll2, lp2, lq2, prm, t, accepts)
             accepts = accepts[:n_moves]
         acc = float(accepts.sum()) / max(n_moves * n, 1)
+        self._check_flow()  # right after the mutation's own device -> host read
         self.history.mcmc_acceptance.append(acc)
         self.history.rho.append(self.rho)
         if self.sampler_kwargs.get("adapt_rho", True):

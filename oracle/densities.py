@@ -76,4 +76,6 @@ def evaluate(desc: dict, x: np.ndarray) -> np.ndarray:
         return gmm(x, desc["means"], desc["inv_sigma"], desc["logc"])
     if kind == KIND_UNIFORM:
         return uniform_box(x, desc["lo"], desc["hi"], desc["const"])
+    if kind == "callable":  # a proposal that only offers log_prob (a flow): desc["fn"](x) -> [n]
+        return np.asarray(desc["fn"](x), dtype=np.float64)
     raise ValueError(f"unknown density kind {kind}")

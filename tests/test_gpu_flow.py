@@ -4,6 +4,8 @@ fp32; against the bf16-emulating oracle log_q agrees to 5e-3 absolute for >= 99 
 particles and to 0.05 for all (an activation that sits on a bf16 rounding boundary may round
 the other way under a different fp32 summation order), against the exact fp64 flow to 0.15
 absolute (mean 0.03) at D = 64 - the bound quoted in DESIGN.md."""
+import math
+
 import numpy as np
 import pytest
 
@@ -97,3 +99,73 @@ def test_flow_as_smc_proposal_importance(cuda):
     logz = dims * (-0.5 * math.log(2 * math.pi * 1.49) - 0.5 * 0.25 / 1.49)
     assert s.efficiency > 0.002
     assert s.log_evidence == pytest.approx(logz, abs=6 * s.log_evidence_error + 0.05)
+
+
+def test_c4_tempering_step_with_the_flow_as_proposal(cuda):
+    """BASELINE configs[3] at reduced N: 64-D, 8-component mixture likelihood, N(0, 4^2) prior, the coupling flow
+    (bf16 tcgen05) as the proposal density inside the tempering step - reweight, beta search, exact resample,
+    pCN moves whose accept test needs log q(x') from the flow kernel - against numpy: oracle/smc_numpy.py +
+    oracle/pcn.py with oracle/flow.py (bf16-emulating) as q, the same numpy Generator call order.
+    Stated bound (bf16 flow): log q agrees to 5e-3 for 99 % of the particles, so beta may differ by a few
+    tolerances and an accept decision may flip where |log u - log a| is inside the flow error."""
+    import torch
+
+    from aspire_b200 import ops
+    from aspire_b200 import targets as tg
+    from aspire_b200.samplers import MiniPCNSMC
+    from aspire_b200.samples import SMCSamples
+    from oracle import densities as dn
+    from oracle import pcn as opcn
+    from oracle import problems
+    from oracle import smc_numpy as sn
+
+    dims, n, moves, rho, seed = 64, 20_000, 5, 0.3, 11
+    f, p = _flow(dims, 3, cuda, seed=2)
+    pg, po = tg.gmm_problem(dims, device=cuda), problems.gmm_problem(dims)
+    u = np.random.default_rng(1).normal(size=(n, dims))
+    x_d, lq_d = ops.flow_sample(f.struct(), _t(u, cuda))
+    x = x_d.cpu().numpy()
+    lq_e = of.forward(p, x, emulate_bf16=True)[1]
+    dq = np.abs(lq_d.cpu().numpy() - lq_e)
+    assert (dq < 5e-3).mean() >= 0.99 and dq.max() < 0.05
+    ll, lp = dn.evaluate(po["like"], x), dn.evaluate(po["prior"], x)
+    np.testing.assert_allclose(pg["like"].log_prob(x_d).cpu().numpy(), ll, rtol=1e-12, atol=1e-10)
+
+    s = MiniPCNSMC(pg["like"], pg["prior"], dims, f, rng=np.random.default_rng(seed))
+    s._configure_kernel(dict(n_steps=moves, rho=rho, adapt_rho=False))
+    s.target_efficiency, s.target_efficiency_rate, s.adaptive, s.adaptive_min_beta_step = 0.5, 1.0, True, False
+    s.max_beta_step, s.resampling = 1.0, "multinomial"
+    from aspire_b200.history import SMCHistory
+
+    s.history = SMCHistory()
+    start = SMCSamples(x_d, log_likelihood=pg["like"].log_prob(x_d), log_prior=pg["prior"].log_prob(x_d), log_q=lq_d,
+                       beta=0.0, device=cuda)
+    assert not s.fused  # the proposal is a flow: semi-fused moves (asp_pcn_propose_eval + flow + asp_pcn_accept_scalar)
+    out, beta, _ = s.tempering_step(start, 0.0, math.nan, 0.0, 1e-6)
+    f.check_error()
+
+    # ---- numpy: the same step with the bf16-emulating flow spec, same generator call order
+    rng = np.random.default_rng(seed)
+    beta_ref, _ = sn.determine_beta(ll, lp, lq_e, 0.0, beta_tolerance=1e-6)
+    assert abs(beta - beta_ref) <= 4e-6                      # a few tolerances: the last decisions see log q +- 5e-3
+    rec, _ = sn.smc_step_reweight(ll, lp, lq_e, 0.0, beta_tolerance=1e-6)
+    assert s.history.ess[-1] == pytest.approx(rec.ess, rel=2e-2)
+    assert s.history.log_norm_ratio[-1] == pytest.approx(rec.log_norm_ratio, abs=2e-2)
+    # resample with the GPU's beta and log q so that the same ancestors are compared move by move
+    lq_g = lq_d.cpu().numpy()
+    pw = sn.resample_weights(ll, lp, lq_g, 0.0, beta)
+    idx = sn.choice_indices(pw, rng.random(n))
+    xi = rng.standard_normal((moves, n, dims))
+    log_u = np.log(1.0 - rng.random((moves, n)))
+    mu, sigma = opcn.weighted_moments(x[idx], np.ones(n))
+    q = dict(kind="callable", fn=lambda y: of.forward(p, y, emulate_bf16=True)[1])
+    ref = opcn.sweep(x[idx], ll[idx], lp[idx], lq_g[idx], like=po["like"], prior=po["prior"], q=q, beta=beta, mu=mu,
+                     sigma=sigma, rho=rho, n_moves=moves, xi=xi, log_u=log_u)
+    got = out.x.cpu().numpy()
+    same = np.isclose(got, ref[0], rtol=1e-9, atol=1e-9).all(axis=1)
+    assert same.mean() > 0.97, same.mean()                   # flips only where |log u - log a| < flow error
+    acc_ref = ref[4].sum() / (moves * n)
+    assert s.history.mcmc_acceptance[-1] == pytest.approx(acc_ref, abs=5e-3)
+    np.testing.assert_allclose(out.log_likelihood.cpu().numpy()[same], ref[1][same], rtol=1e-9, atol=1e-9)
+    dlq = np.abs(out.log_q.cpu().numpy()[same] - ref[3][same])
+    assert (dlq < 5e-3).mean() >= 0.99 and dlq.max() < 0.05

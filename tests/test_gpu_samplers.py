@@ -293,7 +293,10 @@ def test_smc_checkpoint_resume_reproduces_the_run(cuda, tmp_path, source):
     full = make()
     path = tmp_path / "ckpt.pkl"
     ref = full.sample(4000, checkpoint_callback=states.append, **kw)
-    assert len(states) == len(full.history.beta) >= 4
+    # one state per iteration plus the forced final one (maybe_checkpoint(force=True), smc/base.py:476): it carries
+    # the evidence and is written whatever checkpoint_every is
+    assert len(states) == len(full.history.beta) + 1 >= 5
+    assert states[-1]["iteration"] == states[-2]["iteration"] and states[-1]["meta"]["beta"] == 1.0
     st = states[1]
     assert st["sampler"] == "MiniPCNSMC" and st["iteration"] == 2 and st["meta"]["beta"] == full.history.beta[1]
     assert set(st) >= {"samples", "config", "parameters", "history", "rng_state", "sampler_kwargs"}
@@ -437,3 +440,45 @@ def test_readme_quickstart_example_runs(cuda, capsys):
     out = capsys.readouterr().out
     z = float(out.split("log evidence")[1].split()[0])
     assert abs(z - 2 * math.log(math.pi)) < 0.5      # 500 particles: a loose statistical check
+
+
+def test_moment_subsample_step_matches_oracle(cuda):
+    """More particles than ``moment_particles``: the pCN reference measure is fitted to every
+    (n // moment_particles)-th offspring.  One tempering step (host generator, the reference's draw order) against
+    numpy with the same strided subsample: same beta, same ancestors, same particles."""
+    from aspire_b200 import targets as tg
+    from aspire_b200.flows import DiagGaussianFlow
+    from aspire_b200.history import SMCHistory
+    from aspire_b200.samplers import SMCSampler
+    from aspire_b200.samples import SMCSamples
+    from oracle import pcn as opcn
+
+    dims, n, moves, rho, m_use = 8, 20_000, 4, 0.4, 4096
+    po, pg = problems.rosenbrock_problem(dims), tg.rosenbrock_problem(dims, device=cuda)
+    x, ll, lp, lq = problems.draw(po, n, 21)
+    rng = np.random.default_rng(9)
+    flow = DiagGaussianFlow(dims, device=cuda, mean=pg["q"].mean_np, sigma=pg["q"].sigma_np, rng=rng)
+    s = SMCSampler(pg["like"], pg["prior"], dims, flow, rng=rng)
+    s._configure_kernel(dict(n_steps=moves, rho=rho, adapt_rho=False, moment_particles=m_use))
+    s.target_efficiency, s.target_efficiency_rate, s.adaptive, s.adaptive_min_beta_step = 0.5, 1.0, True, False
+    s.max_beta_step, s.resampling, s.history = 1.0, "multinomial", SMCHistory()
+    start = SMCSamples(_t(x, cuda), log_likelihood=_t(ll, cuda), log_prior=_t(lp, cuda), log_q=_t(lq, cuda), beta=0.0,
+                       device=cuda)
+    out, beta, _ = s.tempering_step(start, 0.0, math.nan, 0.0, 1e-6)
+
+    ref_rng = np.random.default_rng(9)
+    beta_ref, _ = sn.determine_beta(ll, lp, lq, 0.0, beta_tolerance=1e-6)
+    assert beta == beta_ref
+    idx = sn.choice_indices(sn.resample_weights(ll, lp, lq, 0.0, beta), ref_rng.random(n))
+    xi = ref_rng.standard_normal((moves, n, dims))
+    log_u = np.log(1.0 - ref_rng.random((moves, n)))
+    stride = n // m_use
+    sub = idx[::stride]
+    mu, sigma = opcn.weighted_moments(x[sub], np.ones(len(sub)))
+    ref = opcn.sweep(x[idx], ll[idx], lp[idx], lq[idx], like=po["like"], prior=po["prior"], q=po["q"], beta=beta, mu=mu,
+                     sigma=sigma, rho=rho, n_moves=moves, xi=xi, log_u=log_u)
+    got = out.x.cpu().numpy()
+    close = np.isclose(got, ref[0], rtol=1e-10, atol=1e-10).all(axis=1)
+    assert close.mean() > 0.999
+    assert s.history.mcmc_acceptance[-1] == pytest.approx(ref[4].sum() / (moves * n), abs=2.0 / n)
+    np.testing.assert_allclose(out.log_likelihood.cpu().numpy()[close], ref[1][close], rtol=1e-9, atol=1e-9)
