@@ -707,13 +707,10 @@ int asp_beta_search_root(const double* d_d, int64_t n, asp_beta_state_t* d_state
         P = *peer;
     }
     cudaStream_t s = (cudaStream_t)stream;
-    static bool attr_set = false;
     const size_t smem = sizeof(float) * kSubSamples;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(beta_sub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return ASP_ERR_CUDA;
-        attr_set = true;
-    }
+    // per device (context) attribute: set on every call rather than cached per process
+    if (cudaFuncSetAttribute(beta_sub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return ASP_ERR_CUDA;
     beta_sub_kernel<<<1, kSubBlock, smem, s>>>(d_d, n, d_state, d_scratch, P);
     const int g = grid_for(n, kUnroll, kBlock, 4);
     beta_newton_kernel<<<g, kBlock, 0, s>>>(d_d, n, d_state, d_scratch, 0, (ReduceWs*)ws, P);

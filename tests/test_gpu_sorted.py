@@ -29,6 +29,7 @@ def _cdf(kind, n, rng):
     elif kind == "zeros30":
         w = np.exp(rng.normal(0, 2.0, n))
         w[rng.random(n) < 0.3] = 0.0
+        w[-1] = max(w[-1], 1e-3)  # never all zero
     else:
         w = np.exp(rng.normal(0, float(kind), n))
     c = np.cumsum(w)
