@@ -255,6 +255,37 @@ class ShardedSMC:
         cdf = ops.cdf_write(p, total)
         return cdf, torch.stack([carry[2], total[0]]), gathered
 
+    # -- owner-computes multinomial resampling at sorted uniforms ----------------------
+    def sorted_ancestors(self, cdf, chain, n_total, mark=None):
+        """-> (idx, bounds): the ancestors (local indices, ascending) of the slots this rank owns, and the slot
+        boundaries J_0 .. J_G of all ranks (host ints; the one device -> host read of the resampling)."""
+        ops, comm = self.ops, self.comm
+        mark = mark or (lambda name: None)
+        r, g = comm.rank, comm.world
+        dev = cdf.device
+        stream_u = self.next_stream()
+        tiles_total = ops.sorted_tiles(n_total)
+        per = -(-tiles_total // g)                               # tiles generated per rank (ceil)
+        t_lo = min(r * per, tiles_total)
+        sp = ops.SortedSpacings(self.seed, stream_u, n_total, dev, j0=t_lo * ops.SPACING_TILE,
+                                n_tiles=min(per, tiles_total - t_lo))
+        if g > 1:
+            sums = torch.zeros(per, dtype=torch.int64, device=dev)
+            sums[:sp.n_tiles] = sp.tile_sums
+            sp.scan(comm.all_gather(sums).reshape(-1)[:tiles_total].contiguous())
+        else:
+            sp.scan()
+        lo_dev = (chain[0] / chain[1]).reshape(1) if r > 0 else torch.zeros(1, dtype=torch.float64, device=dev)
+        lo_all = comm.all_gather(lo_dev).reshape(-1) if g > 1 else lo_dev
+        bounds = ops.sorted_bounds(sp, lo_all, n_total)          # host ints J_0 .. J_G: rank s owns slots [J_s, J_s+1)
+        if bounds is None:
+            raise RuntimeError("exact CDF: a peer GPU did not hand over its running sum within 20 s")
+        mark("select")
+        j_lo, j_hi = bounds[r], bounds[r + 1]
+        idx = sp.window(j_lo, j_hi).search(cdf, j_lo, j_hi)
+        mark("resample")
+        return idx, bounds
+
     @staticmethod
     def slice_bounds(chain, cdf, rank, world):
         """(lo, hi) host floats of the slice (one device -> host read; tests and diagnostics)."""
@@ -300,27 +331,10 @@ class ShardedSMC:
         cdf, chain, gathered = self.global_cdf(p, tiles, info, n_total, mark)
         mean_u = s1 / n_total
         mark("cdf")
-        # owner-computes multinomial resampling at sorted uniforms
+        idx, bounds = self.sorted_ancestors(cdf, chain, n_total, mark)
         r, g = comm.rank, comm.world
-        stream_u = self.next_stream()
-        per = -(-ops.sorted_tiles(n_total) // g)                 # tiles generated per rank (ceil)
-        tiles_total = ops.sorted_tiles(n_total)
-        t_lo = min(r * per, tiles_total)
-        sp = ops.SortedSpacings(self.seed, stream_u, n_total, dev, j0=t_lo * ops.SPACING_TILE,
-                                n_tiles=min(per, tiles_total - t_lo))
-        sums = torch.zeros(per, dtype=torch.int64, device=dev)
-        sums[:sp.n_tiles] = sp.tile_sums
-        sp.scan(comm.all_gather(sums).reshape(-1)[:tiles_total].contiguous() if g > 1 else sp.tile_sums)
-        lo_dev = (chain[0] / chain[1]).reshape(1) if r > 0 else torch.zeros(1, dtype=torch.float64, device=dev)
-        lo_all = comm.all_gather(lo_dev).reshape(-1) if g > 1 else lo_dev
-        bounds = ops.sorted_bounds(sp, lo_all, n_total)          # host ints J_0 .. J_G: rank s owns slots [J_s, J_s+1)
-        if bounds is None:
-            raise RuntimeError("exact CDF: a peer GPU did not hand over its running sum within 20 s")
         j_lo, j_hi = bounds[r], bounds[r + 1]
         n_out = j_hi - j_lo
-        mark("select")
-        idx = sp.window(j_lo, j_hi).search(cdf, j_lo, j_hi)
-        mark("resample")
         dims = shard.x.shape[1]
         # reference measure: moments of every (n_total // moment_particles)-th slot - the same set whatever the
         # sharding, spread over the whole genealogy (the ancestors are ascending)

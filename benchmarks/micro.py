@@ -65,27 +65,150 @@ def flow(args):
                           "particles_per_s": n / ms * 1e3, "tflops": flops / ms / 1e9}))
 
 
+def _numpy_resample(n, sigma=2.0):
+    """The reference's resampling on the host cores: numpy ``Generator.choice`` = cumsum + normalise + searchsorted
+    of n iid uniforms (src/aspire/samples.py:1251-1287), one core (numpy's sort / search are single-threaded)."""
+    import time
+
+    import numpy as np
+
+    rng = np.random.default_rng(7)
+    lw = rng.normal(0.0, sigma, n)
+    p = np.exp(lw - lw.max())
+    p /= p.sum()
+    t0 = time.perf_counter()
+    cdf = np.cumsum(p)
+    cdf /= cdf[-1]
+    idx = cdf.searchsorted(rng.random(n), side="right")
+    t_mult = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    cdf = np.cumsum(p)
+    cdf /= cdf[-1]
+    idx = cdf.searchsorted((np.arange(n) + 0.37) / n, side="right")
+    t_sys = time.perf_counter() - t0
+    del idx
+    return t_mult * 1e3, t_sys * 1e3
+
+
 def resample(args):
+    """C5 (BASELINE.json configs[4]): exact CDF + ancestors for systematic and multinomial resampling, 1e4 .. 1e9
+    particles, log-weights ~ N(0, 2^2), beside numpy on the host cores (n <= --numpy-max).  Under torchrun
+    (``--gpus N``) the particles are sharded: exact CDF with the carry chain over the ranks, owner-computes
+    ancestors at sorted uniforms, device-timed, max over ranks.  Multinomial is timed in both modes: sorted uniforms
+    generated on the device (throughput mode) and supplied iid uniforms through the guide table (parity mode)."""
+    import os
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        return _resample_sharded(args, world)
     dev = torch.device("cuda")
     sizes = [args.n] if args.n else [10**4, 10**5, 10**6, 10**7, 10**8, 10**9]
     for n in sizes:
-        g = torch.Generator(device=dev).manual_seed(7)
-        lw = torch.randn(n, dtype=torch.float64, device=dev, generator=g) * 2.0
+        lw = ops.philox_normal(7, 1, n, 1, dev).reshape(-1) * 2.0
         p = torch.exp(lw - lw.max())
         p /= p.sum()
         del lw
-        u = ops.philox_uniform(7, 0, n, dev)
         iters = args.iters if n <= 10**8 else 3
         t_cdf = timed(lambda: ops.cdf_exact(p), iters)
         cdf = ops.cdf_exact(p)
-        t_mult = timed(lambda: ops.search_multinomial(cdf, u), iters)
+        seq = [0]
+
+        def sorted_mult():
+            seq[0] += 1
+            return ops.search_multinomial_sorted(cdf, 7, seq[0], n)
+
+        t_sorted = timed(sorted_mult, iters)
         t_sys = timed(lambda: ops.search_systematic(cdf, 0.37, n), iters)
-        for name, t in (("multinomial", t_cdf + t_mult), ("systematic", t_cdf + t_sys)):
-            print(json.dumps({"bench": f"resample_{name}", "config": "C5", "particles": n, "ms_cdf": t_cdf,
+        u = ops.philox_uniform(7, 0, n, dev)
+        t_iid = timed(lambda: ops.search_multinomial(cdf, u), iters)
+        del u
+        np_mult = np_sys = None
+        if n <= args.numpy_max:
+            np_mult, np_sys = _numpy_resample(n)
+        for name, t, t_np in (("multinomial_sorted_uniforms", t_cdf + t_sorted, np_mult),
+                              ("multinomial_supplied_iid_uniforms", t_cdf + t_iid, np_mult),
+                              ("systematic", t_cdf + t_sys, np_sys)):
+            print(json.dumps({"bench": f"resample_{name}", "config": "C5", "n_gpus": 1, "particles": n, "ms_cdf": t_cdf,
                               "ms_total": t, "indices_per_s": n / t * 1e3, "algorithmic_gbs": 32 * n / t / 1e6,
                               "hbm_frac": 32 * n / t / 1e6 / PEAKS["hbm_gbs"],
+                              "numpy_host_ms": t_np, "numpy_indices_per_s": None if t_np is None else n / t_np * 1e3,
+                              "numpy_cores": 1, "vs_numpy": None if t_np is None else t_np / t,
                               "note": "inputs L2-resident" if 24 * n < 126e6 else "inputs exceed L2"}))
-        del p, u, cdf
+        del p, cdf
+
+
+def _resample_sharded(args, world):
+    import os
+
+    import torch.distributed as dist
+
+    from aspire_b200.distributed import Comm, PeerMailboxes, ShardedSMC
+
+    local_rank = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist.init_process_group("nccl", device_id=dev)
+    comm = Comm()
+    r = comm.rank
+    eng = ShardedSMC(comm, None, None, None, seed=7)
+    eng._peer = PeerMailboxes.create(comm, dev)
+    sizes = [args.n] if args.n else [10**5, 10**6, 10**7, 10**8, 10**9]
+    for n in sizes:
+        base, rem = divmod(n, world)
+        n_local, start = base + (1 if r < rem else 0), r * base + min(r, rem)
+        lw = ops.philox_normal(7, 1, n_local, 1, dev, index0=start).reshape(-1) * 2.0
+        mx = lw.max().reshape(1)
+        comm.all_reduce_max(mx)
+        p = torch.exp(lw - mx)
+        tot = p.sum().reshape(1)
+        comm.all_reduce_sum(tot)
+        p /= tot
+        del lw
+
+        def cdf_only():
+            info = torch.stack([p.sum(), p.max(), p.sum() * 0, p.sum() * 0 + n_local]).contiguous()
+            return eng.global_cdf(p, None, info, n)
+
+        def multinomial():
+            cdf, chain, _ = cdf_only()
+            return eng.sorted_ancestors(cdf, chain, n)
+
+        def systematic():
+            cdf, chain, _ = cdf_only()
+            lo, hi = eng.slice_bounds(chain, cdf, r, world)
+            # slots whose position (j + u0) / n falls into this rank's CDF slice (lo, hi]
+            j0 = 0 if r == 0 else int(torch.ceil(torch.tensor(lo * n - 0.37)).item())
+            j1 = n if r == world - 1 else int(torch.ceil(torch.tensor(hi * n - 0.37)).item())
+            j0, j1 = max(min(j0, n), 0), max(min(j1, n), 0)
+            return ops.search_systematic(cdf, 0.37, max(j1 - j0, 0), j0=j0, m_total=n)
+
+        iters = args.iters if n <= 10**8 else 3
+        res = {}
+        for name, fn in (("cdf", cdf_only), ("multinomial_sorted_uniforms", multinomial), ("systematic", systematic)):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            comm.barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(iters):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([a.elapsed_time(b) / iters], dtype=torch.float64, device=dev)
+            comm.all_reduce_max(t)
+            res[name] = float(t[0])
+        if r == 0:
+            for name in ("multinomial_sorted_uniforms", "systematic"):
+                t = res[name]
+                print(json.dumps({"bench": f"resample_{name}", "config": "C5", "n_gpus": world, "particles": n,
+                                  "ms_cdf": res["cdf"], "ms_total": t, "indices_per_s": n / t * 1e3,
+                                  "algorithmic_gbs_per_gpu": 32 * n / world / t / 1e6,
+                                  "hbm_frac": 32 * n / world / t / 1e6 / PEAKS["hbm_gbs"],
+                                  "note": "sharded: exact CDF carry chain over " + ("NVLink peer memory" if eng._peer else "NCCL")
+                                          + ", owner-computes ancestors, device-timed, max over ranks"}))
+        del p
+    dist.destroy_process_group()
 
 
 def importance(args):
@@ -340,6 +463,8 @@ if __name__ == "__main__":
     ap.add_argument("--moves", type=int, default=10)
     ap.add_argument("--dims", type=int, default=0)
     ap.add_argument("--sorted-idx", action="store_true")
+    ap.add_argument("--numpy-max", type=int, default=10**7, help="largest n timed with numpy on the host (resample)")
+    ap.add_argument("--gpus", type=int, default=1, help="resample: launch with torch.distributed.run for N > 1")
     ap.add_argument("--only", default="")
     ap.add_argument("--dump", default="")
     a = ap.parse_args()
