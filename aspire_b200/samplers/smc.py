@@ -214,7 +214,11 @@ class SMCSampler(Sampler):
             samples = SMCSamples.from_samples(samples, beta=0.0)
             beta, iterations = 0.0, 0
             self.history = SMCHistory()
-        store_sample_history = store_sample_history and samples.x.numel() <= SAMPLE_HISTORY_MAX_ELEMENTS
+        if store_sample_history and samples.x.numel() > SAMPLE_HISTORY_MAX_ELEMENTS:
+            logger.warning("store_sample_history=True ignored: %d x %d particles per step exceed the %d-element limit of "
+                           "the per-step host copies (history.sample_history stays empty)", samples.x.shape[0],
+                           samples.x.shape[1], SAMPLE_HISTORY_MAX_ELEMENTS)
+            store_sample_history = False
         if store_sample_history:
             self.history.sample_history.append(samples.to_numpy())
 

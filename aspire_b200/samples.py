@@ -32,6 +32,20 @@ def _as_dev(a, device, dtype=torch.float64):
     return t.contiguous()
 
 
+class HostSamples(dict):
+    """numpy copy of a sample set: a dict whose keys are also attributes (``host.x``, ``host["x"]``)."""
+
+    def __getattr__(self, name):
+        try:
+            return self[name]
+        except KeyError:
+            raise AttributeError(name) from None
+
+    def __len__(self):
+        x = self.get("x")
+        return 0 if x is None else len(x)
+
+
 @dataclass
 class BaseSamples:
     """reference ``BaseSamples`` (samples.py:36-413)."""
@@ -112,9 +126,10 @@ class BaseSamples:
                     log_q=cv(self.log_q), parameters=self.parameters)
 
     def to_numpy(self):
-        """Host copy as a plain dict of numpy arrays (the reference returns a
-        numpy-backed dataclass of the same fields)."""
-        return self._numpy_fields()
+        """Host copy (samples.py:281-302: the reference returns a numpy-backed dataclass of the same fields): a
+        ``HostSamples`` - numpy arrays reachable as attributes (``.x``, ``.log_likelihood`` ...) like the reference's
+        object, and as dictionary items (what the checkpoint payload and ``to_dict`` use)."""
+        return HostSamples(self._numpy_fields())
 
     def to_dict(self, flat: bool = True):
         """samples.py:142-181: every field (host copies) plus one key per parameter (``flat``) or a ``"samples"``
