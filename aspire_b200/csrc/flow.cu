@@ -13,8 +13,10 @@
 //   B = the layer's weights, resident in shared memory for the whole kernel, brought in
 //       once by a TMA bulk copy (cp.async.bulk -> UBLKCP) of the host-packed blob;
 //   D = 64 (or D) fp32 TMEM columns, read back with tcgen05.ld.32x32b for the fp32
-//       epilogue (bias + ReLU + bf16 pack, or soft-clip / exp / affine update).
-// Two CTAs are resident per SM so that one CTA's epilogue overlaps the other's MMAs.
+//       epilogue (ReLU + bf16 pack in one cvt.rn.relu.bf16x2, or soft-clip / exp / affine update).
+// The bias rides on the tensor pipe: every GEMM starts with one extra K = 16 step  ones[128 x 16] . bias[16 x N]
+// (bias = bf16 hi + bf16 lo, relative error 2^-17), so the epilogues add nothing.  The chain MMA -> wait -> epilogue
+// is serial per tile, so several warpgroups per SM keep independent tiles in flight over one copy of the weights.
 #include <cuda_bf16.h>
 #include <math.h>
 
@@ -152,9 +154,33 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// relu + round to bf16 + pack: one instruction per two activations
+__device__ __forceinline__ uint32_t pack_relu_bf16(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %2, %1;" : "=r"(r) : "f"(a), "f"(b));  // d = {hi: %2... low half = second source
+    return r;
+}
+__device__ __forceinline__ float fast_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+// 32 bytes of a row in one load: a whole sector per instruction, no reliance on L1 between instructions
+__device__ __forceinline__ void ld_row32(const double* p, double (&v)[4]) {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0, %1, %2, %3}, [%4];"
+                 : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+
+__device__ __forceinline__ void st_row32(double* p, double a, double b, double c, double d) {
+    asm volatile("st.global.L1::no_allocate.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
 // write 8 consecutive K elements (one core-matrix row) of this thread's A-tile row
 __device__ __forceinline__ void a_tile_store8(unsigned char* a_tile, int row, int kchunk, const float* v) {
     uint4 q = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    *reinterpret_cast<uint4*>(a_tile + kchunk * (kFlowM * 16) + (row >> 3) * 128 + (row & 7) * 16) = q;
+}
+
+__device__ __forceinline__ void a_tile_store8_relu(unsigned char* a_tile, int row, int kchunk, const float* v) {
+    uint4 q = make_uint4(pack_relu_bf16(v[0], v[1]), pack_relu_bf16(v[2], v[3]), pack_relu_bf16(v[4], v[5]),
+                         pack_relu_bf16(v[6], v[7]));
     *reinterpret_cast<uint4*>(a_tile + kchunk * (kFlowM * 16) + (row >> 3) * 128 + (row & 7) * 16) = q;
 }
 
@@ -167,19 +193,26 @@ struct FlowSizes {
     static constexpr int kW3 = D * kFlowH * 2;
     static constexpr int kLayer = kW1 + kW2 + kW3;
     static constexpr int kTmemCols = 64;                      // >= max(64, D) accumulators, power of two
+    // bias operands of the extra K = 16 step, built in the prologue: [N x 16] bf16 K-major core matrices
+    static constexpr int kB12 = kFlowH * 16 * 2;              // bias blocks of GEMM 1 / 2 (N = 64)
+    static constexpr int kB3 = D * 16 * 2;                    // GEMM 3 (N = D)
+    static constexpr int kBiasLayer = 2 * kB12 + kB3;
+    static constexpr int kOnes = kFlowM * 16 * 2;             // the constant A operand: columns 0, 1 = 1
 };
 
 // issue one GEMM [128 x K] . [K x N] -> TMEM (thread 0 only), then commit to `bar`
 template <int K, int N>
 __device__ __forceinline__ void issue_gemm(uint32_t tmem, const unsigned char* a_tile, const unsigned char* w,
-                                           uint64_t* bar) {
+                                           const unsigned char* ones, const unsigned char* bias_blk, uint64_t* bar) {
     const uint32_t a0 = smem_u32(a_tile), b0 = smem_u32(w);
     constexpr uint32_t idesc = umma_idesc(N);
+    // D = ones . bias  (the accumulator starts at the bias), then D += A . W
+    umma_f16(tmem, umma_desc(smem_u32(ones), kFlowM * 16, 128), umma_desc(smem_u32(bias_blk), N * 16, 128), idesc, 0u);
 #pragma unroll
     for (int s = 0; s < K / 16; ++s) {
         const uint64_t ad = umma_desc(a0 + s * 2 * (kFlowM * 16), kFlowM * 16, 128);
         const uint64_t bd = umma_desc(b0 + s * 2 * (N * 16), N * 16, 128);
-        umma_f16(tmem, ad, bd, idesc, s > 0 ? 1u : 0u);
+        umma_f16(tmem, ad, bd, idesc, 1u);
     }
     umma_commit(bar);
 }
@@ -191,7 +224,8 @@ __device__ __forceinline__ void wg_sync(int wg) { asm volatile("bar.sync %0, 128
 // (compile time, so z[] keeps static indices and stays in registers).
 template <int D, bool INVERSE, bool ODD>
 __device__ __forceinline__ bool coupling_layer(float (&z)[D], float& ladj, int layer, const unsigned char* s_w,
-                                               unsigned char* s_a, const float* s_bias, uint64_t* mma_bar, uint32_t tmem,
+                                               unsigned char* s_a, const unsigned char* s_ones,
+                                               const unsigned char* s_bb, uint64_t* mma_bar, uint32_t tmem,
                                                uint32_t lane_taddr, uint32_t& phase, int tid, int wg) {
     using S = FlowSizes<D>;
     constexpr int HALF = S::kHalf;
@@ -200,7 +234,9 @@ __device__ __forceinline__ bool coupling_layer(float (&z)[D], float& ladj, int l
     const unsigned char* w1 = s_w + layer * S::kLayer;
     const unsigned char* w2 = w1 + S::kW1;
     const unsigned char* w3 = w2 + S::kW2;
-    const float* b1 = s_bias + layer * 192;
+    const unsigned char* bb1 = s_bb + layer * S::kBiasLayer;
+    const unsigned char* bb2 = bb1 + S::kB12;
+    const unsigned char* bb3 = bb2 + S::kB12;
     // ---- GEMM 1: A = bf16(z_a) ----
 #pragma unroll
     for (int c = 0; c < S::kKA / 8; ++c) {
@@ -218,66 +254,55 @@ __device__ __forceinline__ bool coupling_layer(float (&z)[D], float& ladj, int l
     wg_sync(wg);
     if (tid == 0) {
         tc_fence_after();
-        issue_gemm<S::kKA, kFlowH>(tmem, s_a, w1, mma_bar);
+        issue_gemm<S::kKA, kFlowH>(tmem, s_a, w1, s_ones, bb1, mma_bar);
     }
     ok &= mbar_wait(mma_bar, phase);
     phase ^= 1;
     tc_fence_after();
-    // ---- epilogue 1 -> A = bf16(relu(acc + b1)); GEMM 2 ----
+    // ---- epilogue 1 -> A = bf16(relu(acc)) (the bias is already in the accumulator); GEMM 2 ----
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
         float acc[32];
         tmem_ld32(lane_taddr + half * 32, acc);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            float v[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = fmaxf(acc[c * 8 + k] + b1[half * 32 + c * 8 + k], 0.f);
-            a_tile_store8(s_a, tid, half * 4 + c, v);
-        }
+        for (int c = 0; c < 4; ++c) a_tile_store8_relu(s_a, tid, half * 4 + c, acc + c * 8);
     }
     fence_proxy_async_smem();
     tc_fence_before();
     wg_sync(wg);
     if (tid == 0) {
         tc_fence_after();
-        issue_gemm<kFlowH, kFlowH>(tmem, s_a, w2, mma_bar);
+        issue_gemm<kFlowH, kFlowH>(tmem, s_a, w2, s_ones, bb2, mma_bar);
     }
     ok &= mbar_wait(mma_bar, phase);
     phase ^= 1;
     tc_fence_after();
-    // ---- epilogue 2 -> A = bf16(relu(acc + b2)); GEMM 3 (N = D) ----
+    // ---- epilogue 2 -> A = bf16(relu(acc)); GEMM 3 (N = D) ----
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
         float acc[32];
         tmem_ld32(lane_taddr + half * 32, acc);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            float v[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = fmaxf(acc[c * 8 + k] + b1[64 + half * 32 + c * 8 + k], 0.f);
-            a_tile_store8(s_a, tid, half * 4 + c, v);
-        }
+        for (int c = 0; c < 4; ++c) a_tile_store8_relu(s_a, tid, half * 4 + c, acc + c * 8);
     }
     fence_proxy_async_smem();
     tc_fence_before();
     wg_sync(wg);
     if (tid == 0) {
         tc_fence_after();
-        issue_gemm<kFlowH, D>(tmem, s_a, w3, mma_bar);
+        issue_gemm<kFlowH, D>(tmem, s_a, w3, s_ones, bb3, mma_bar);
     }
     ok &= mbar_wait(mma_bar, phase);
     phase ^= 1;
     tc_fence_after();
     // ---- epilogue 3: columns [0, HALF) = shift, [HALF, D) = raw log-scale ----
-    auto update = [&](int j, float sh_acc, float raw_acc) {
-        const float shift = sh_acc + b1[128 + j];
-        const float r = raw_acc + b1[128 + HALF + j];
-        const float log_s = __fdividef(r, 1.0f + fabsf(r) * (1.0f / kFlowLimit));
+    auto update = [&](int j, float shift, float r) {
+        const float log_s = r * fast_rcp(fmaf(fabsf(r), 1.0f / kFlowLimit, 1.0f));  // soft clip: |log_s| < log(1e3)
         ladj += log_s;
         // z_b is the half NOT fed to the conditioner
         float& zb = odd ? z[j] : z[HALF + j];
-        zb = INVERSE ? (zb - shift) * __expf(-log_s) : fmaf(zb, __expf(log_s), shift);
+        const float t = log_s * 1.4426950408889634f;
+        zb = INVERSE ? (zb - shift) * fast_ex2(-t) : fmaf(zb, fast_ex2(t), shift);
     };
     if constexpr (HALF >= 16) {
 #pragma unroll
@@ -303,22 +328,23 @@ __device__ __forceinline__ bool coupling_layer(float (&z)[D], float& ladj, int l
 // independent warpgroups (own A tile, own 64 TMEM columns, own MMA barrier) over one copy of the weights;
 // D = 32 / 16: three / four single-warpgroup CTAs fit.
 template <int D>
-constexpr int flow_wg() { return D >= 64 ? 3 : 1; }
+constexpr int flow_wg() { return D >= 64 ? 4 : 6; }
 template <int D>
-constexpr int flow_ctas_per_sm() { return D >= 64 ? 1 : (D >= 32 ? 3 : 4); }
+constexpr int flow_ctas_per_sm() { return 1; }
 
 template <int D, bool INVERSE>
 __global__ void __launch_bounds__(kFlowThreads * flow_wg<D>(), flow_ctas_per_sm<D>()) flow_kernel(const FlowArgs A) {
     using S = FlowSizes<D>;
     constexpr int HALF = S::kHalf;
     constexpr int NWG = flow_wg<D>();
-    constexpr int kTmemAll = NWG == 1 ? 64 : (NWG == 2 ? 128 : 256);  // power of two >= 64 NWG
+    constexpr int kTmemAll = NWG == 1 ? 64 : (NWG == 2 ? 128 : (NWG <= 4 ? 256 : 512));  // power of two >= 64 NWG
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* s_w = smem;                                             // weights blob
-    unsigned char* s_a_all = smem + A.n_layers * S::kLayer;                // NWG A tiles (16 KB each)
-    float* s_bias = reinterpret_cast<float*>(s_a_all + NWG * kFlowM * kFlowH * 2);
-    double* s_mean = reinterpret_cast<double*>(s_bias + A.n_layers * 3 * 64);
-    double* s_scale = s_mean + D;
+    unsigned char* s_bb = smem + A.n_layers * S::kLayer;                   // bias blocks (bf16 hi / lo rows)
+    unsigned char* s_ones = s_bb + A.n_layers * S::kBiasLayer;             // constant A operand of the bias step
+    unsigned char* s_a_all = s_ones + S::kOnes;                            // NWG A tiles (16 KB each)
+    double* s_mean = reinterpret_cast<double*>(s_a_all + NWG * kFlowM * kFlowH * 2);
+    float* s_scale = reinterpret_cast<float*>(s_mean + D);                 // log_prob: 1 / std;  sample: std
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_scale + D);           // [0]: weights TMA, [1 + wg]: MMA
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 1 + NWG);
 
@@ -331,11 +357,34 @@ __global__ void __launch_bounds__(kFlowThreads * flow_wg<D>(), flow_ctas_per_sm<
         fence_mbar_init();
     }
     if (threadIdx.x < 32) tmem_alloc(s_tmem, kTmemAll);
-    for (int i = threadIdx.x; i < A.n_layers * 3 * 64; i += blockDim.x) s_bias[i] = A.bias[i];
+    // bias blocks: element (n, k) of an [N x 16] K-major block sits at (k / 8) N 16 + (n / 8) 128 + (n % 8) 16 + (k % 8) 2;
+    // k = 0 holds bf16(b_n), k = 1 holds bf16(b_n - bf16(b_n)), the other K rows are zero
+    for (int i = threadIdx.x; i < A.n_layers * S::kBiasLayer / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(s_bb)[i] = 0u;
+    for (int i = threadIdx.x; i < S::kOnes / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(s_ones)[i] = 0u;
+    __syncthreads();
+    for (int i = threadIdx.x; i < A.n_layers * 3 * 64; i += blockDim.x) {
+        const int l = i / 192, g = (i % 192) / 64, n = i % 64;
+        const int N = g < 2 ? kFlowH : D;
+        if (n < N) {
+            const float b = A.bias[i];
+            const __nv_bfloat16 hi = __float2bfloat16_rn(b);
+            const __nv_bfloat16 lo = __float2bfloat16_rn(b - __bfloat162float(hi));
+            unsigned char* blk = s_bb + l * S::kBiasLayer + (g == 0 ? 0 : (g == 1 ? S::kB12 : 2 * S::kB12));
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(blk + (n >> 3) * 128 + (n & 7) * 16);
+            dst[0] = hi;
+            dst[1] = lo;
+        }
+    }
+    for (int r = threadIdx.x; r < kFlowM; r += blockDim.x) {
+        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(s_ones + (r >> 3) * 128 + (r & 7) * 16);
+        dst[0] = __float2bfloat16_rn(1.0f);
+        dst[1] = __float2bfloat16_rn(1.0f);
+    }
     for (int i = threadIdx.x; i < D; i += blockDim.x) {
         s_mean[i] = A.mean[i];
-        s_scale[i] = A.inv_std[i];
+        s_scale[i] = (float)A.inv_std[i];
     }
+    fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -357,17 +406,16 @@ __global__ void __launch_bounds__(kFlowThreads * flow_wg<D>(), flow_ctas_per_sm<
         const bool live = row < A.n;
         float z[D];
         {
+            // a row is 8 D bytes, read 32 bytes (one sector) per instruction; the centring stays in fp64 (a parameter
+            // can sit far from zero compared with its spread), the scaling is fp32
             const double* src = A.x + (live ? row : A.n - 1) * D;
 #pragma unroll
-            for (int j = 0; j < D; j += 2) {
-                const double2 v = *reinterpret_cast<const double2*>(src + j);
-                if (INVERSE) {
-                    z[j] = (float)v.x;
-                    z[j + 1] = (float)v.y;
-                } else {
-                    z[j] = (float)((v.x - s_mean[j]) * s_scale[j]);
-                    z[j + 1] = (float)((v.y - s_mean[j + 1]) * s_scale[j + 1]);
-                }
+            for (int j = 0; j < D; j += 4) {
+                double v[4];
+                ld_row32(src + j, v);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    z[j + k] = INVERSE ? (float)v[k] : (float)(v[k] - s_mean[j + k]) * s_scale[j + k];
             }
         }
         float base = 0.f;
@@ -379,21 +427,22 @@ __global__ void __launch_bounds__(kFlowThreads * flow_wg<D>(), flow_ctas_per_sm<
         for (int li = 0; li < A.n_layers; ++li) {
             const int layer = INVERSE ? A.n_layers - 1 - li : li;
             if (layer & 1)
-                ok &= coupling_layer<D, INVERSE, true>(z, ladj, layer, s_w, s_a, s_bias, mma_bar, tmem, lane_taddr, phase,
-                                                       tid, wg);
+                ok &= coupling_layer<D, INVERSE, true>(z, ladj, layer, s_w, s_a, s_ones, s_bb, mma_bar, tmem, lane_taddr,
+                                                       phase, tid, wg);
             else
-                ok &= coupling_layer<D, INVERSE, false>(z, ladj, layer, s_w, s_a, s_bias, mma_bar, tmem, lane_taddr, phase,
-                                                        tid, wg);
+                ok &= coupling_layer<D, INVERSE, false>(z, ladj, layer, s_w, s_a, s_ones, s_bb, mma_bar, tmem, lane_taddr,
+                                                        phase, tid, wg);
         }
         // ---- outputs ----
         if (live) {
             if (INVERSE) {
                 double* dst = A.x_out + row * D;
 #pragma unroll
-                for (int j = 0; j < D; j += 2) {
-                    const double a = (double)z[j] * s_scale[j] + s_mean[j];
-                    const double b = (double)z[j + 1] * s_scale[j + 1] + s_mean[j + 1];
-                    *reinterpret_cast<double2*>(dst + j) = make_double2(a, b);
+                for (int j = 0; j < D; j += 4) {  // 32 bytes (one sector) per store
+                    double o[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) o[k] = fma((double)z[j + k], (double)s_scale[j + k], s_mean[j + k]);
+                    st_row32(dst + j, o[0], o[1], o[2], o[3]);
                 }
                 A.logq[row] = (double)(-0.5f * base - 0.5f * D * kLog2Pi + ladj) + A.log_det0;
             } else {
@@ -404,7 +453,7 @@ __global__ void __launch_bounds__(kFlowThreads * flow_wg<D>(), flow_ctas_per_sm<
                 if (A.x_out) {
                     double* dst = A.x_out + row * D;
 #pragma unroll
-                    for (int j = 0; j < D; j += 2) *reinterpret_cast<double2*>(dst + j) = make_double2(z[j], z[j + 1]);
+                    for (int j = 0; j < D; j += 4) st_row32(dst + j, z[j], z[j + 1], z[j + 2], z[j + 3]);
                 }
             }
         }
@@ -418,8 +467,8 @@ __global__ void __launch_bounds__(kFlowThreads * flow_wg<D>(), flow_ctas_per_sm<
 template <int D>
 static size_t flow_smem_bytes(int n_layers) {
     using S = FlowSizes<D>;
-    return (size_t)n_layers * S::kLayer + (size_t)flow_wg<D>() * kFlowM * kFlowH * 2 + (size_t)n_layers * 3 * 64 * 4 +
-           2 * D * 8 + (1 + flow_wg<D>()) * 8 + 16 + 128;
+    return (size_t)n_layers * (S::kLayer + S::kBiasLayer) + S::kOnes + (size_t)flow_wg<D>() * kFlowM * kFlowH * 2 +
+           D * 8 + D * 4 + (1 + flow_wg<D>()) * 8 + 16 + 128;
 }
 
 template <int D, bool INV>
