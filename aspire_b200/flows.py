@@ -149,6 +149,12 @@ class CouplingFlow(Flow):
 
     ``log_prob`` / ``sample_and_log_prob`` run on tcgen05 (``asp_flow_*_bf16``); ``fit`` trains the
     same weight tensors with torch autograd (scaffolding - SURVEY 8f-1 - not part of the hot path).
+
+    The kernels are built for 16, 32 and 64 dimensions; any ``2 <= dims <= 64`` runs on the next kernel size with
+    PADDING coordinates: the real coordinates are spread over both halves of the mask, a padding coordinate has
+    mean 0 / std 1, enters as 0 and - its rows of every ``W3`` / ``b3`` being held at zero - leaves every layer as 0
+    with zero log-scale, so it contributes exactly ``-1/2 log 2 pi`` to the base density, which is added back.
+    (The reference's default flow works for any D: ``flows/torch/flows.py:140,164``.)
     """
 
     hidden = 64
@@ -156,8 +162,16 @@ class CouplingFlow(Flow):
     def __init__(self, dims: int, device=None, data_transform=None, dtype=None, n_layers: int = 3, rng=None,
                  seed: int = 0):
         super().__init__(dims, device, data_transform, dtype)
-        if dims not in (16, 32, 64):
-            raise ValueError("CouplingFlow kernels are built for dims in {16, 32, 64}")
+        if not 2 <= dims <= 64:
+            raise ValueError("CouplingFlow kernels cover 2 <= dims <= 64")
+        kdims = 16 if dims <= 16 else (32 if dims <= 32 else 64)
+        n_first = (dims + 1) // 2  # real coordinates in the first half of the mask; the rest go to the second half
+        pos = list(range(n_first)) + [kdims // 2 + j for j in range(dims - n_first)]
+        self._pos = torch.tensor(pos, dtype=torch.int64, device=self.device)
+        self._pad = kdims - dims
+        self._real = torch.zeros(kdims, dtype=torch.bool, device=self.device)
+        self._real[self._pos] = True
+        self.kdims = dims = kdims  # the weights, mean / std and the kernels work in the kernel's dimension
         self.n_layers = int(n_layers)
         self.rng = as_uniform_source(rng)
         g = torch.Generator().manual_seed(seed)
@@ -170,6 +184,38 @@ class CouplingFlow(Flow):
         self.mean = torch.zeros(dims, dtype=torch.float64, device=self.device)
         self.std = torch.ones(dims, dtype=torch.float64, device=self.device)
         self._struct = None
+        self._hold_padding()
+
+    # -- padding ---------------------------------------------------------------
+    def _out_mask(self, t: int) -> torch.Tensor:
+        """Rows of layer t's W3 / b3 (shift rows then log-scale rows) that belong to real coordinates."""
+        half = self.kdims // 2
+        b = self._real[half:] if t % 2 == 0 else self._real[:half]  # the half this layer transforms
+        return torch.cat([b, b])
+
+    def _hold_padding(self):
+        """Padding coordinates are never shifted or scaled: their W3 rows and b3 entries stay zero."""
+        if not self._pad:
+            return
+        with torch.no_grad():
+            for t, layer in enumerate(self.layers):
+                m = self._out_mask(t).to(layer["W3"].dtype)
+                layer["W3"].mul_(m[:, None])
+                layer["b3"].mul_(m)
+
+    def _embed(self, x: torch.Tensor) -> torch.Tensor:
+        if not self._pad:
+            return x.contiguous()
+        out = torch.zeros(x.shape[0], self.kdims, dtype=x.dtype, device=x.device)
+        out[:, self._pos] = x
+        return out
+
+    def _extract(self, xp: torch.Tensor) -> torch.Tensor:
+        return xp if not self._pad else xp[:, self._pos].contiguous()
+
+    @property
+    def _pad_const(self) -> float:
+        return 0.5 * self._pad * math.log(2.0 * math.pi)
 
     # -- parameters ------------------------------------------------------------
     def set_params(self, params: dict):
@@ -180,25 +226,26 @@ class CouplingFlow(Flow):
         self.mean = torch.as_tensor(np.asarray(params["mean"]), dtype=torch.float64).to(self.device)
         self.std = torch.as_tensor(np.asarray(params["std"]), dtype=torch.float64).to(self.device)
         self._struct = None
+        self._hold_padding()
 
     def struct(self):
         if self._struct is None:
             from . import _lib
 
-            half = self.dims // 2
+            half = self.kdims // 2
             ka = max(16, half)
             blobs, bias = [], torch.zeros(self.n_layers, 3, 64, dtype=torch.float32, device=self.device)
             for i, layer in enumerate(self.layers):
                 blobs += [pack_umma_kmajor(layer["W1"], ka), pack_umma_kmajor(layer["W2"]), pack_umma_kmajor(layer["W3"])]
                 bias[i, 0, :self.hidden] = layer["b1"]
                 bias[i, 1, :self.hidden] = layer["b2"]
-                bias[i, 2, :self.dims] = layer["b3"]
+                bias[i, 2, :self.kdims] = layer["b3"]
             weights = torch.cat(blobs).contiguous()
-            assert weights.numel() * 2 == _lib.load().asp_flow_weights_bytes(self.dims, self.n_layers)
+            assert weights.numel() * 2 == _lib.load().asp_flow_weights_bytes(self.kdims, self.n_layers)
             inv_std = (1.0 / self.std).contiguous()
             err = torch.zeros(1, dtype=torch.int32, device=self.device)
             s = _lib.Flow()
-            s.dims, s.hidden, s.n_layers = self.dims, self.hidden, self.n_layers
+            s.dims, s.hidden, s.n_layers = self.kdims, self.hidden, self.n_layers
             s.d_weights, s.d_bias = weights.data_ptr(), bias.data_ptr()
             s.d_mean, s.d_inv_std, s.d_std = self.mean.data_ptr(), inv_std.data_ptr(), self.std.data_ptr()
             s.log_det0 = -float(torch.log(self.std).sum())
@@ -225,26 +272,28 @@ class CouplingFlow(Flow):
 
     # -- hot path ----------------------------------------------------------------
     def log_prob(self, x):
-        x = torch.as_tensor(x, dtype=torch.float64, device=self.device)
-        return ops.flow_logprob(self.struct(), x)
+        x = self._embed(torch.as_tensor(x, dtype=torch.float64, device=self.device))
+        logq = ops.flow_logprob(self.struct(), x)
+        return logq + self._pad_const if self._pad else logq
 
     def forward(self, x):
-        x = torch.as_tensor(x, dtype=torch.float64, device=self.device)
+        x = self._embed(torch.as_tensor(x, dtype=torch.float64, device=self.device))
         logq, z = ops.flow_logprob(self.struct(), x, want_z=True)
-        return z, logq
+        return self._extract(z), (logq + self._pad_const if self._pad else logq)
 
     def sample_and_log_prob(self, n_samples):
-        u = self.rng.normal(n_samples, self.dims, self.device)
-        return ops.flow_sample(self.struct(), u)
+        u = self._embed(self.rng.normal(n_samples, self.dims, self.device))  # padding base coordinates: 0
+        x, logq = ops.flow_sample(self.struct(), u)
+        return self._extract(x), (logq + self._pad_const if self._pad else logq)
 
     # -- training scaffolding (torch autograd over the same tensors) -------------------
     def _torch_forward(self, x32, layers):
-        half = self.dims // 2
+        half = self.kdims // 2
         z = (x32 - self.mean.float()) / self.std.float()
         ladj = -torch.log(self.std.float()).sum().expand(z.shape[0])
         for t, layer in enumerate(layers):
-            a = slice(0, half) if t % 2 == 0 else slice(half, self.dims)
-            b = slice(half, self.dims) if t % 2 == 0 else slice(0, half)
+            a = slice(0, half) if t % 2 == 0 else slice(half, self.kdims)
+            b = slice(half, self.kdims) if t % 2 == 0 else slice(0, half)
             hdn = torch.relu(z[:, a] @ layer["W1"].T + layer["b1"])
             hdn = torch.relu(hdn @ layer["W2"].T + layer["b2"])
             o = hdn @ layer["W3"].T + layer["b3"]
@@ -253,7 +302,7 @@ class CouplingFlow(Flow):
             zb = z[:, b] * torch.exp(log_s) + shift
             z = torch.cat([z[:, a], zb], dim=1) if t % 2 == 0 else torch.cat([zb, z[:, a]], dim=1)
             ladj = ladj + log_s.sum(dim=1)
-        return -0.5 * (z * z).sum(dim=1) - 0.5 * self.dims * math.log(2 * math.pi) + ladj
+        return -0.5 * (z * z).sum(dim=1) - 0.5 * self.kdims * math.log(2 * math.pi) + ladj
 
     def fit(self, samples, n_epochs: int = 100, lr: float = 1e-3, batch_size: int = 500,
             validation_fraction: float = 0.2, clip_grad: float | None = None, lr_annealing: bool = False,
@@ -271,8 +320,12 @@ class CouplingFlow(Flow):
         if not bool(torch.isfinite(x).all()):
             bad = (~torch.isfinite(x)).any(dim=0).nonzero(as_tuple=True)[0].tolist()
             raise ValueError(f"Training data contains infinite values in dimensions: {bad}")
+        x = self._embed(x)
         self.mean = x.mean(dim=0)
         self.std = x.std(dim=0).clamp_min(1e-12)
+        if self._pad:
+            self.mean = torch.where(self._real, self.mean, torch.zeros_like(self.mean))
+            self.std = torch.where(self._real, self.std, torch.ones_like(self.std))
         n = x.shape[0]
         g = torch.Generator(device="cpu").manual_seed(int(kwargs.get("seed", 0)))
         x32 = x[torch.randperm(n, generator=g).to(self.device)].float()
@@ -294,6 +347,7 @@ class CouplingFlow(Flow):
                 if clip_grad is not None:
                     torch.nn.utils.clip_grad_norm_(params, clip_grad)
                 opt.step()
+                self._hold_padding()
                 tot += float(loss.detach())
                 nb += 1
             if sched is not None:
@@ -318,4 +372,5 @@ class CouplingFlow(Flow):
         else:
             self.layers = [{k: v.detach() for k, v in layer.items()} for layer in self.layers]
         self._struct = None
+        self._hold_padding()
         return hist

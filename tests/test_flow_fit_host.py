@@ -48,3 +48,50 @@ def test_fit_rejects_non_finite_data():
     x[3, 5] = np.inf
     with pytest.raises(ValueError, match="infinite"):
         _flow().fit(x, n_epochs=1)
+
+
+@pytest.mark.parametrize("dims", [2, 4, 5, 16, 23, 40])
+def test_padding_coordinates_are_inert(dims):
+    """Any 2 <= D <= 64 runs on the 16 / 32 / 64-dimensional kernels: after a fit, the padding coordinates enter as 0,
+    leave every layer as 0 with zero log-scale (their W3 rows / b3 entries stay zero), and the density of the real
+    coordinates is the padded density + (#padding) / 2 log 2 pi - checked on the torch restatement of the kernel."""
+    import math
+
+    from aspire_b200.flows import CouplingFlow
+
+    rng = np.random.default_rng(dims)
+    x = rng.normal(size=(800, dims)) * np.linspace(0.5, 2.0, dims) + 1.0
+    x[:, -1] += 0.5 * x[:, 0]
+    f = CouplingFlow(dims, device="cpu", n_layers=3, seed=1)
+    k = f.kdims
+    assert k in (16, 32, 64) and k >= dims and f._pad == k - dims and f.dims == dims
+    assert len(set(f._pos.tolist())) == dims and int((f._pos < k // 2).sum()) == (dims + 1) // 2  # both halves used
+    h = f.fit(x, n_epochs=3, batch_size=200, lr=5e-3)
+    assert np.isfinite(h.training_loss).all() and min(h.training_loss) < h.training_loss[0] + 0.1
+    for t, layer in enumerate(f.layers):
+        dead = ~f._out_mask(t)
+        assert float(layer["W3"][dead].abs().sum()) == 0.0 and float(layer["b3"][dead].abs().sum()) == 0.0
+        if f._pad:
+            assert float(layer["W3"][~dead].abs().sum()) > 0.0
+    np.testing.assert_allclose(f.mean[f._pos].numpy(), x.mean(axis=0), rtol=1e-12)
+    assert float(f.std[~f._real].sub(1).abs().sum()) == 0.0 and float(f.mean[~f._real].abs().sum()) == 0.0
+    # density of the real coordinates: integrates like a D-dimensional density (compare with a Gaussian at the data
+    # scale through importance sampling is overkill here) - check the padding bookkeeping exactly instead:
+    xp = f._embed(torch.as_tensor(x, dtype=torch.float64)).float()
+    lq_pad = f._torch_forward(xp, f.layers)
+    # recompute with the padding coordinates removed from the base density by hand
+    half = k // 2
+    z = (xp - f.mean.float()) / f.std.float()
+    for t, layer in enumerate(f.layers):
+        a = slice(0, half) if t % 2 == 0 else slice(half, k)
+        b = slice(half, k) if t % 2 == 0 else slice(0, half)
+        hdn = torch.relu(torch.relu(z[:, a] @ layer["W1"].T + layer["b1"]) @ layer["W2"].T + layer["b2"])
+        o = hdn @ layer["W3"].T + layer["b3"]
+        log_s = o[:, half:] / (1.0 + torch.abs(o[:, half:] / 6.907755278982137))
+        zb = z[:, b] * torch.exp(log_s) + o[:, :half]
+        z = torch.cat([z[:, a], zb], dim=1) if t % 2 == 0 else torch.cat([zb, z[:, a]], dim=1)
+        assert float(zb[:, ~f._real[b]].abs().max()) == 0.0 if f._pad else True      # padding stays 0
+        assert float(log_s[:, ~f._real[b]].abs().max()) == 0.0 if f._pad else True   # and is never scaled
+    assert float(z[:, ~f._real].abs().max()) == 0.0 if f._pad else True
+    assert f._pad_const == pytest.approx(0.5 * (k - dims) * math.log(2 * math.pi))
+    assert torch.isfinite(lq_pad).all()

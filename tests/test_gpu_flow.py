@@ -169,3 +169,60 @@ def test_c4_tempering_step_with_the_flow_as_proposal(cuda):
     np.testing.assert_allclose(out.log_likelihood.cpu().numpy()[same], ref[1][same], rtol=1e-9, atol=1e-9)
     dlq = np.abs(out.log_q.cpu().numpy()[same] - ref[3][same])
     assert (dlq < 5e-3).mean() >= 0.99 and dlq.max() < 0.05
+
+
+@pytest.mark.parametrize("dims", [4, 11, 20, 48])
+def test_any_dimension_runs_on_padded_kernels(cuda, dims):
+    """2 <= D <= 64 on the 16 / 32 / 64-dimensional tcgen05 kernels with inert padding coordinates: log_prob equals
+    the torch restatement of the same (fitted) flow, samples come back in D dimensions with the log density
+    log_prob gives them, and the density is normalised (importance estimate of its integral)."""
+    import torch
+
+    from aspire_b200.flows import CouplingFlow
+    from aspire_b200.rng import PhiloxRNG
+
+    rng = np.random.default_rng(dims)
+    x = rng.normal(size=(3000, dims)) * np.linspace(0.6, 1.8, dims) + 0.5
+    x[:, -1] += 0.6 * x[:, 0]
+    torch.manual_seed(0)
+    f = CouplingFlow(dims, device=cuda, rng=PhiloxRNG(4))
+    f.fit(_t(x, cuda), n_epochs=6, batch_size=500, lr=3e-3)
+    lq = f.log_prob(_t(x, cuda))
+    f.check_error()
+    ref = f._torch_forward(f._embed(_t(x, cuda)).float(), f.layers).double() + f._pad_const
+    err = (lq - ref).abs()
+    assert float(err.max()) < 0.15 and float(err.mean()) < 0.03           # the stated bf16 bound
+    xs, lqs = f.sample_and_log_prob(50_000)
+    assert xs.shape == (50_000, dims) and bool(lqs.isfinite().all())
+    back = f.log_prob(xs)
+    assert float((back - lqs).abs().max()) < 0.05
+    z, lq2 = f.forward(_t(x[:100], cuda))
+    assert z.shape == (100, dims) and float((lq2 - lq[:100]).abs().max()) == 0.0
+    # normalisation: E_q[N(x; m, s) / q(x)] = 1 for any normalised density N
+    m, s = torch.as_tensor(x.mean(0), device=cuda), torch.as_tensor(x.std(0) * 0.8, device=cuda)
+    log_n = (-0.5 * ((xs - m) / s) ** 2 - torch.log(s) - 0.5 * math.log(2 * math.pi)).sum(dim=1)
+    w = torch.exp(log_n - lqs)
+    assert float(w.mean()) == pytest.approx(1.0, abs=6 * float(w.std()) / math.sqrt(len(w)) + 0.02)
+
+
+def test_quickstart_with_a_learned_coupling_flow(cuda):
+    """The reference's README quickstart shape (4-D, README.md:42-77) with a LEARNED flow as the proposal, like the
+    reference's default: fit the coupling flow to initial samples, then SMC; posterior N(0, 1/2 I), log Z = 2 ln pi."""
+    import torch
+
+    from aspire_b200 import targets as tg
+    from aspire_b200.aspire import Aspire
+    from aspire_b200.rng import PhiloxRNG
+
+    dims = 4
+    like = tg.GaussianDensity(0.0, 1.0, dims, normalised=False, device=cuda)
+    prior = tg.GaussianDensity(0.0, 1.0, dims, normalised=False, device=cuda)
+    torch.manual_seed(1)
+    a = Aspire(log_likelihood=like, log_prior=prior, dims=dims, flow_class="coupling", device=cuda)
+    init = PhiloxRNG(3).normal(2000, dims, cuda) * 1.2
+    a.fit(init, n_epochs=20)
+    s = a.sample_posterior(20_000, sampler="smc", sampler_kwargs=dict(n_steps=20), rng=5)
+    x = s.x.cpu().numpy()
+    assert np.abs(x.mean(axis=0)).max() < 0.05
+    np.testing.assert_allclose(x.var(axis=0), 0.5, rtol=0.08)
+    assert s.log_evidence == pytest.approx(2 * math.log(math.pi), abs=0.1)
