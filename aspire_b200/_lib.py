@@ -126,6 +126,13 @@ class Flow(C.Structure):
     ]
 
 
+class FlowTrain(C.Structure):
+    """``asp_flow_train_t`` (include/aspire_b200.h)."""
+    _fields_ = [("kdims", C.c_int32), ("hidden", C.c_int32), ("n_layers", C.c_int32), ("batch_cap", C.c_int32),
+                ("d_w", C.c_void_p), ("d_m", C.c_void_p), ("d_v", C.c_void_p), ("d_g", C.c_void_p),
+                ("d_out_mask", C.c_void_p), ("d_mean", C.c_void_p), ("d_inv_std", C.c_void_p), ("d_ws", C.c_void_p)]
+
+
 _P = C.c_void_p
 _I64 = C.c_int64
 _I32 = C.c_int32
@@ -194,6 +201,7 @@ SIGNATURES = {
     ),
     "asp_tpcn_scales": (C.c_int, [_P, _I64, _I32, C.POINTER(PcnParams), _I32, _P, _P]),
     "asp_pcn_propose_eval_supported": (_I32, [_I32, _I32, _I32]),
+    "asp_pcn_sweep_tpcn_supported": (_I32, [_I32]),
     "asp_pcn_propose_eval": (C.c_int, [_P, _I64, _I32, C.POINTER(Density), C.POINTER(Density), C.POINTER(PcnParams), _I32,
                                        _P, _P, _P, _P, _P]),
     "asp_pcn_accept_scalar": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, C.POINTER(PcnParams), _I32, _P,
@@ -201,6 +209,11 @@ SIGNATURES = {
     "asp_flow_weights_bytes": (C.c_size_t, [_I32, _I32]),
     "asp_flow_logprob_bf16": (C.c_int, [C.POINTER(Flow), _P, _I64, _P, _P, _P]),
     "asp_flow_sample_bf16": (C.c_int, [C.POINTER(Flow), _P, _I64, _P, _P, _P]),
+    "asp_flow_fit_params": (C.c_size_t, [_I32, _I32]),
+    "asp_flow_fit_workspace_floats": (C.c_size_t, [_I32, _I32, _I32]),
+    "asp_flow_fit_step": (C.c_int, [C.POINTER(FlowTrain), _P, _I32, C.c_float, C.c_float, C.c_float, C.c_float, _I32,
+                                    C.c_float, C.c_float, _P, _P]),
+    "asp_flow_fit_loss": (C.c_int, [C.POINTER(FlowTrain), _P, _I32, C.c_float, _P, _P]),
     "asp_select_workspace_bytes": (C.c_size_t, []),
     "asp_select_uniforms": (C.c_int, [C.c_uint64, C.c_uint32, _P, _I64, _D, _D, _I64, _P, _P, _P, _P, _P]),
     "asp_philox_uniform": (C.c_int, [C.c_uint64, C.c_uint32, _I64, _I64, _P, _P]),
@@ -239,9 +252,8 @@ KERNELS_PER_CALL = {"asp_importance_weights": 3, "asp_cdf_exact": 6, "asp_cdf_ti
                     "asp_cdf_set_tile_stats": 2, "asp_cdf_info": 0, "asp_device_check": 0,
                     "asp_search_multinomial_guided": 4, "asp_select_uniforms": 3, "asp_search_systematic": 3,
                     "asp_search_systematic_workspace_bytes": 0, "asp_pcn_propose_eval_supported": 0, "asp_beta_search_max_passes3": 0,
-                    "asp_sorted_tiles": 0, "asp_search_sorted": 2,
-                    "asp_beta_search_run": (C.c_int, [_P, _I64, _P, _D, _D, _D, _D, _P, _P, _P, _P, _P]),
-    "asp_beta_search_root": 6, "asp_beta_search_run": 8, "asp_beta_search_scratch_words": 0}
+                    "asp_sorted_tiles": 0, "asp_search_sorted": 2, "asp_pcn_sweep_tpcn_supported": 0,
+                    "asp_beta_search_root": 6, "asp_beta_search_run": 8, "asp_beta_search_scratch_words": 0}
 launch_count = 0
 
 

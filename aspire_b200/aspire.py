@@ -5,8 +5,8 @@
 Only the dispatch that sits on the SMC / importance hot path is mirrored
 (``init_flow`` :175-205, ``get_sampler_class`` :272-305, ``init_sampler`` :307-381, ``sample_posterior``
 :383-570, ``sample_flow`` :891-907), including the bounded / periodic / affine preconditioning transforms
-(``aspire_b200.transforms``); the HDF5 config / flow files and flow-based preconditioning are not
-built.
+(``aspire_b200.transforms``) and flow preconditioning (a coupling flow refitted on the device at every SMC step);
+the HDF5 config / flow files are not built.
 """
 
 from __future__ import annotations
@@ -99,7 +99,11 @@ class Aspire:
     # ---- flow ---------------------------------------------------------------
     def init_flow(self):
         kw = dict(self.flow_kwargs)
-        flow_class = kw.pop("flow_class", "diag_gaussian")
+        # the reference's default is a learned flow for any D (flows/torch/flows.py:140,164): here the coupling flow
+        # (tcgen05 evaluation, device fit) where its kernels cover D; flow_class="diag_gaussian" selects the
+        # analytic proposal of the benchmark configs, which keeps the SMC mutation on the fused sweep
+        default_class = "coupling" if 2 <= self.dims <= 64 and self.device.type == "cuda" else "diag_gaussian"
+        flow_class = kw.pop("flow_class", default_class)
         if isinstance(flow_class, str):
             if flow_class not in _FLOW_CLASSES:
                 raise ValueError(f"Unknown flow class {flow_class!r}; available: {sorted(_FLOW_CLASSES)}")
@@ -146,7 +150,7 @@ class Aspire:
     def init_sampler(self, sampler_type: str, preconditioning=None, preconditioning_kwargs=None, **kwargs):
         """aspire.py:307-381: ``preconditioning`` None / "none" -> no transform; "default" / "standard" -> a
         ``CompositeTransform`` over the prior bounds and periodic parameters (by default without the bounded and
-        affine stages, :338-341); "flow" is not built (row 8f-1)."""
+        affine stages, :338-341); "flow" -> ``FlowPreconditioningTransform`` (:351-366)."""
         cls = self.get_sampler_class(sampler_type)
         if sampler_type != "importance" and preconditioning is None:
             preconditioning = "default"
@@ -165,7 +169,15 @@ class Aspire:
                 if transform.is_identity:
                     transform = None
         elif preconditioning == "flow":
-            raise NotImplementedError("flow preconditioning needs the device flow fit (scope row 8f-1, SURVEY.md)")
+            from .transforms import FlowPreconditioningTransform
+
+            kw = dict(preconditioning_kwargs or {})
+            kw.setdefault("affine_transform", False)
+            parameters = self.parameters or [f"x_{i}" for i in range(self.dims)]
+            transform = FlowPreconditioningTransform(
+                parameters=parameters, flow_backend=self.flow_backend, flow_kwargs=self.flow_kwargs,
+                periodic_parameters=self.periodic_parameters, bounded_to_unbounded=self.bounded_to_unbounded,
+                prior_bounds=self.prior_bounds, device=self.device, **kw)
         elif preconditioning not in (None, "none", "identity"):
             raise ValueError(f"Unknown preconditioning: {preconditioning}")
         if transform is not None:

@@ -133,12 +133,8 @@ __device__ __forceinline__ double gamma_mt(uint64_t seed, uint32_t stream, uint6
     for (uint32_t it = 0; it < 64; ++it) {
         const uint4 r = philox4x32<kNoiseRounds>((uint32_t)index, (uint32_t)(index >> 32), stream, kGammaBlock0 + it,
                                                  (uint32_t)seed, (uint32_t)(seed >> 32));
-        float z, z1;
-        box_muller_f32(r.x, r.y, z, z1);
-        const float u = u01_f32(r.z);
-        const float t = 1.0f + c * z;
-        const float v = t * t * t;
-        if (t > 0.0f && sfu_log(u) < 0.5f * z * z + d - d * v + d * sfu_log(fmaxf(v, 1e-30f))) return (double)(d * v);
+        double g;
+        if (gamma_mt_try(r, d, c, g)) return g;
     }
     return (double)d;
 }
@@ -372,7 +368,8 @@ int asp_pcn_sweep(const double* d_x, const double* d_log_l, const double* d_log_
     ASP_REQUIRE(params->d_mu && params->d_sigma, "reference measure missing");
     ASP_REQUIRE(params->noise_mode == 0 || (params->d_xi && params->d_log_u), "noise arrays missing");
     ASP_REQUIRE(d_x != d_x_out || !d_idx, "in-place sweep cannot gather");
-    ASP_REQUIRE(!(params->nu > 0.0), "the fused sweep is pCN only: tpCN (nu > 0) runs through asp_tpcn_scales + the unfused pair");
+    const bool tpcn = params->nu > 0.0;
+    ASP_REQUIRE(!tpcn || params->noise_mode == 0 || params->d_gamma, "gamma variates missing (tpCN, supplied noise)");
     int rc;
     if ((rc = check_density(like, dims, "likelihood"))) return rc;
     if ((rc = check_density(prior, dims, "prior"))) return rc;
@@ -392,16 +389,18 @@ int asp_pcn_sweep(const double* d_x, const double* d_log_l, const double* d_log_
     const bool aligned = ((reinterpret_cast<uintptr_t>(d_x) | reinterpret_cast<uintptr_t>(d_x_out) |
                            reinterpret_cast<uintptr_t>(params->d_xi)) & 15) == 0;
     static const bool legacy = [] { const char* e = getenv("ASP_SWEEP_LEGACY"); return e && e[0] == '1'; }();
-    if (!legacy && aligned && params->rho < 1.0 && tpp_shape(dims, like->kind, dl, gt)) {
+    if ((!legacy || tpcn) && aligned && params->rho < 1.0 && tpp_shape(dims, like->kind, dl, gt)) {
         switch (like->kind) {
-            case ASP_DENSITY_GAUSSIAN: rc = launch_tpp_gaussian(A, s); break;
-            case ASP_DENSITY_ROSENBROCK: rc = launch_tpp_rosenbrock(A, s); break;
-            case ASP_DENSITY_GMM: rc = launch_tpp_gmm(A, s); break;
-            default: rc = launch_tpp_uniform(A, s); break;
+            case ASP_DENSITY_GAUSSIAN: rc = tpcn ? launch_tpp_t_gaussian(A, s) : launch_tpp_gaussian(A, s); break;
+            case ASP_DENSITY_ROSENBROCK: rc = tpcn ? launch_tpp_t_rosenbrock(A, s) : launch_tpp_rosenbrock(A, s); break;
+            case ASP_DENSITY_GMM: rc = tpcn ? launch_tpp_t_gmm(A, s) : launch_tpp_gmm(A, s); break;
+            default: rc = tpcn ? launch_tpp_t_uniform(A, s) : launch_tpp_uniform(A, s); break;
         }
         if (rc) { set_error("asp_pcn_sweep: unsupported density combination"); return rc; }
         return check_launch("asp_pcn_sweep");
     }
+    // the Student-t step is built into the particle-per-thread kernel only (asp_pcn_sweep_tpcn_supported)
+    ASP_REQUIRE(!tpcn, "fused tpCN needs dims in {4, 8, 16, 32, 64}, 16-byte aligned rows and rho < 1: use asp_tpcn_scales + the unfused pair");
     const int g = group_size_for(dims);
     const int grid = grid_for(n * g, 1);
     switch (like->kind) {
@@ -412,6 +411,11 @@ int asp_pcn_sweep(const double* d_x, const double* d_log_l, const double* d_log_
     }
     if (rc) { set_error("asp_pcn_sweep: unsupported density combination"); return rc; }
     return check_launch("asp_pcn_sweep");
+}
+
+int32_t asp_pcn_sweep_tpcn_supported(int32_t dims) {
+    int dl = 0, g = 0;
+    return tpp_shape(dims, ASP_DENSITY_GAUSSIAN, dl, g) ? 1 : 0;
 }
 
 int asp_tpcn_scales(const double* d_x, int64_t n, int32_t dims, const asp_pcn_params_t* params, int32_t move,

@@ -98,7 +98,26 @@ __device__ __forceinline__ double tpp_gmm(const double (&v)[DL], MuOf mu_of, int
     return m + log(acc);
 }
 
-template <int DL, int G, int LIKE, int PRIOR, bool PHILOX>
+// Marsaglia & Tsang (2000) gamma variate of the tpCN scale, fp32, counter-based: the same draws as
+// asp_tpcn_scales (pcn.cu::gamma_mt; spec oracle/pcn.py::gamma_mt_f32) from the precomputed round keys
+constexpr uint32_t kTppGammaBlock0 = 0xFFFFFF00u;
+__device__ __forceinline__ double tpp_gamma_mt(const PhiloxKeys& K, uint32_t stream, uint64_t index, float a) {
+    const float d = a - (1.0f / 3.0f);
+    const float c = 1.0f / sqrtf(9.0f * d);
+    for (uint32_t it = 0; it < 64; ++it) {
+        const uint4 r = philox4x32<kNoiseRounds>((uint32_t)index, (uint32_t)(index >> 32), stream, kTppGammaBlock0 + it, K);
+        double g;
+        if (gamma_mt_try(r, d, c, g)) return g;
+    }
+    return (double)d;
+}
+
+// TPCN: the Student-t preconditioned step (the reference's default step_fn, smc/minipcn.py:48; spec
+// oracle/pcn.py::tpcn_sweep).  Per move and particle: g ~ Gamma((D + nu)/2, 1), proposal scale
+// sqrt((nu + r2(x)) / (2 g)) on the noise term, and the reference term of the accept test becomes
+// (nu + D)/2 log1p(r2 / nu) instead of r2 / 2 - so r2 = |(x - mu)/sigma|^2 is carried beside the folded
+// quadratic (3 more fp64 instructions per dimension and move than pCN).
+template <int DL, int G, int LIKE, int PRIOR, bool PHILOX, bool TPCN>
 __global__ void __launch_bounds__(kTppBlock, tpp_min_blocks<DL>()) pcn_sweep_tpp_kernel(const SweepArgs A) {
     constexpr int DT = DL * G;  // == dims
     constexpr int NQ = DL / 4;
@@ -113,6 +132,7 @@ __global__ void __launch_bounds__(kTppBlock, tpp_min_blocks<DL>()) pcn_sweep_tpp
     __shared__ double2 s_c01[DT];  // {rho sigma_k, mu_k}
     __shared__ double2 s_c23[DT];  // {a2_k, a1_k}: folded quadratic of the accept test
     __shared__ double2 s_pbox[kPBox ? DT : 1], s_lbox[kLBox ? DT : 1];
+    __shared__ double s_isr[TPCN ? DT : 1];  // 1 / sigma_k (tpCN: r2 is needed by itself)
     // final logs: a Gaussian density at x = mu + y is  s0 - 1/2 sum_k (is_k y_k + is_k (mu_k - m_k))^2
     __shared__ double2 s_fq[DT], s_fp[kPriorQuad ? DT : 1], s_fl[kLikeQuad ? DT : 1];  // {is_k, is_k (mu_k - m_k)}
     __shared__ unsigned int s_acc[kMaxMovesSmem];
@@ -123,6 +143,8 @@ __global__ void __launch_bounds__(kTppBlock, tpp_min_blocks<DL>()) pcn_sweep_tpp
     const double ninf = identity(OP_MAX);
     const double rho = A.prm.rho, beta = A.prm.beta;
     const double ca = sqrt(1.0 - rho * rho);
+    const double nu = TPCN ? A.prm.nu : 1.0, t_half = 0.5 * (nu + (double)DT), inv_nu = 1.0 / nu;
+    const float gamma_a = (float)t_half;
     const double ros_w = kRosen ? -beta / A.like.s2 : 0.0;  // beta and the scale folded
     const double ros_wa = ros_w * A.like.s0;
     const int n_comp = kGmm ? A.like.n_comp : 0;
@@ -136,7 +158,8 @@ __global__ void __launch_bounds__(kTppBlock, tpp_min_blocks<DL>()) pcn_sweep_tpp
         // Rosenbrock's (b - x_j)^2 are per-dimension quadratics in y = x - mu and fold into a2 y^2 + a1 y
         const double sg = __ldg(A.prm.d_sigma + j), mu = __ldg(A.prm.d_mu + j);
         const double isr = 1.0 / sg;
-        double c2 = 0.5 * isr * isr, c1 = 0.0;
+        double c2 = TPCN ? 0.0 : 0.5 * isr * isr, c1 = 0.0;  // tpCN: the reference term is not a quadratic
+        if constexpr (TPCN) s_isr[j] = isr;
         const double isq = __ldg(A.q.p1 + j), wq = -0.5 * (1.0 - beta) * isq * isq;
         c2 += wq;
         c1 += 2.0 * wq * (mu - __ldg(A.q.p0 + j));
@@ -186,9 +209,11 @@ __global__ void __launch_bounds__(kTppBlock, tpp_min_blocks<DL>()) pcn_sweep_tpp
     // A plain shared-memory read of a constant is loop-invariant: the compiler hoists all 4 DL of them out of
     // the move loop into registers and spills the state.  lds2 (volatile) keeps each read next to its use.
     double2 rc01[kRC ? DL : 1] = {}, rc23[kRC ? DL : 1] = {}, rpb[kRC && kPBox ? DL : 1] = {}, rlb[kRC && kLBox ? DL : 1] = {};
+    double risr[kRC && TPCN ? DL : 1] = {};
     if constexpr (kRC) {
 #pragma unroll
         for (int k = 0; k < DL; ++k) {
+            if constexpr (TPCN) risr[k] = s_isr[lane * DL + k];
             rc01[k] = s_c01[lane * DL + k];
             rc23[k] = s_c23[lane * DL + k];
             if constexpr (kPBox) rpb[k] = s_pbox[lane * DL + k];
@@ -199,6 +224,14 @@ __global__ void __launch_bounds__(kTppBlock, tpp_min_blocks<DL>()) pcn_sweep_tpp
     auto C23 = [&](int k) -> double2 { if constexpr (kRC) return rc23[k]; else return lds2(&s_c23[lane * DL + k]); };
     auto PBOX = [&](int k) -> double2 { if constexpr (kRC) return rpb[kPBox ? k : 0]; else return lds2(&s_pbox[kPBox ? lane * DL + k : 0]); };
     auto LBOX = [&](int k) -> double2 { if constexpr (kRC) return rlb[kLBox ? k : 0]; else return lds2(&s_lbox[kLBox ? lane * DL + k : 0]); };
+    auto ISR = [&](int k) -> double {
+        if constexpr (kRC) return risr[TPCN ? k : 0];
+        else {
+            double r;
+            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(r) : "r"((uint32_t)__cvta_generic_to_shared(&s_isr[TPCN ? lane * DL + k : 0])));
+            return r;
+        }
+    };
     auto MU = [&](int k) -> double { return C01(k).y; };
     constexpr int kPerWarp = 32 / G;
     const int sub = (threadIdx.x & 31) / G;
@@ -208,8 +241,17 @@ __global__ void __launch_bounds__(kTppBlock, tpp_min_blocks<DL>()) pcn_sweep_tpp
     unsigned int n_acc = 0;
 
     // separable part of T at centred state v (+ Rosenbrock's coupling term), group-reduced
-    auto target = [&](const double(&v)[DL]) -> double {
+    auto target = [&](const double(&v)[DL], double& r2_out) -> double {
         double sq[4] = {0.0, 0.0, 0.0, 0.0}, rr[4] = {0.0, 0.0, 0.0, 0.0};
+        if constexpr (TPCN) {
+            double r2 = 0.0;
+#pragma unroll
+            for (int k = 0; k < DL; ++k) {
+                const double zz = v[k] * ISR(k);
+                r2 = fma(zz, zz, r2);
+            }
+            r2_out = group_sum<G>(r2);
+        }
         double xprev = 0.0, xfirst = 0.0;
         bool bad = false;
 #pragma unroll
@@ -245,6 +287,7 @@ __global__ void __launch_bounds__(kTppBlock, tpp_min_blocks<DL>()) pcn_sweep_tpp
         }
         double T = group_sum<G>(s);
         if constexpr (kGmm) T = fma(beta, tpp_gmm<DL, G>(v, MU, lane, s_gm, s_gw, n_comp, ncp), T);
+        if constexpr (TPCN) T = fma(t_half, log1p(r2_out * inv_nu), T);
         return T;
     };
 
@@ -307,7 +350,8 @@ __global__ void __launch_bounds__(kTppBlock, tpp_min_blocks<DL>()) pcn_sweep_tpp
             y[k] = v.x - C01(k).y;
             y[k + 1] = v.y - C01(k + 1).y;
         }
-        double cur = target(y);
+        double r2c = 0.0;  // tpCN: |(x - mu)/sigma|^2 of the current state
+        double cur = target(y, r2c);
         if (!active) cur = identity(OP_MIN);  // +inf: a padding particle never accepts
         // from here on y holds ca * (x - mu): the proposal is then one DFMA per dimension and accepting a
         // move is one DMUL per dimension (instead of a DMUL + DFMA and two register moves)
@@ -323,9 +367,16 @@ __global__ void __launch_bounds__(kTppBlock, tpp_min_blocks<DL>()) pcn_sweep_tpp
             } else {
                 log_u = A.prm.d_log_u[(size_t)t * A.n + i];
             }
-            double stot = 0.0, rtot = 0.0;
+            double stot = 0.0, rtot = 0.0, r2p = 0.0;
             double xprev = 0.0, xfirst = 0.0;
             bool bad = false;
+            double sc = 1.0;
+            if constexpr (TPCN) {
+                double g;
+                if constexpr (PHILOX) g = tpp_gamma_mt(A.keys, stream0 + (uint32_t)t, pidx, gamma_a);
+                else g = A.prm.d_gamma[(size_t)t * A.n + i];
+                sc = sqrt((nu + r2c) / (2.0 * g));
+            }
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
                 double xi[4];
@@ -344,10 +395,14 @@ __global__ void __launch_bounds__(kTppBlock, tpp_min_blocks<DL>()) pcn_sweep_tpp
                 for (int j = 0; j < 4; ++j) {
                     const int k = q * 4 + j;
                     const double2 c = C01(k);
-                    const double v = fma(c.x, xi[j], y[k]);
+                    const double v = TPCN ? fma(c.x * sc, xi[j], y[k]) : fma(c.x, xi[j], y[k]);
                     yp[k] = v;
                     const double2 e = C23(k);
                     sq = fma(v, fma(e.x, v, e.y), sq);
+                    if constexpr (TPCN) {
+                        const double zz = v * ISR(k);
+                        r2p = fma(zz, zz, r2p);
+                    }
                     if constexpr (kNeedX) {
                         const double xk = c.y + v;
                         if constexpr (kRosen) {
@@ -380,11 +435,16 @@ __global__ void __launch_bounds__(kTppBlock, tpp_min_blocks<DL>()) pcn_sweep_tpp
             }
             double nw = group_sum<G>(s);
             if constexpr (kGmm) nw = fma(beta, tpp_gmm<DL, G>(yp, MU, lane, s_gm, s_gw, n_comp, ncp), nw);
+            if constexpr (TPCN) {
+                r2p = group_sum<G>(r2p);
+                nw = fma(t_half, log1p(r2p * inv_nu), nw);
+            }
             const bool acc = log_u < nw - cur;  // NaN -> reject, like the reference's NaN -> -inf
             if (acc) {
 #pragma unroll
                 for (int k = 0; k < DL; ++k) y[k] = ca * yp[k];
                 cur = nw;
+                if constexpr (TPCN) r2c = r2p;
                 moved = true;
             }
             if (per_move) {
@@ -506,7 +566,7 @@ inline size_t tpp_dyn_smem(const SweepArgs& A) {
     return tpp_gmm_bytes(A.dims, A.like.kind == ASP_DENSITY_GMM ? A.like.n_comp : 0) + stage;
 }
 
-template <int DL, int G, int LIKE, int PRIOR>
+template <int DL, int G, int LIKE, int PRIOR, bool TPCN>
 inline int launch_tpp_n(const SweepArgs& A, cudaStream_t s) {
     const int64_t per_block = (int64_t)kTppBlock / G;
     const int64_t need = (A.n + per_block - 1) / per_block;
@@ -519,25 +579,25 @@ inline int launch_tpp_n(const SweepArgs& A, cudaStream_t s) {
         kernel<<<grid, kTppBlock, smem, s>>>(A);
         return ASP_OK;
     };
-    if (A.prm.noise_mode == 0) return launch(pcn_sweep_tpp_kernel<DL, G, LIKE, PRIOR, true>);
-    return launch(pcn_sweep_tpp_kernel<DL, G, LIKE, PRIOR, false>);
+    if (A.prm.noise_mode == 0) return launch(pcn_sweep_tpp_kernel<DL, G, LIKE, PRIOR, true, TPCN>);
+    return launch(pcn_sweep_tpp_kernel<DL, G, LIKE, PRIOR, false, TPCN>);
 }
 
-template <int LIKE, int PRIOR>
+template <int LIKE, int PRIOR, bool TPCN>
 inline int launch_tpp_shape(const SweepArgs& A, cudaStream_t s) {
     int dl = 0, g = 0;
     if (!tpp_shape(A.dims, LIKE, dl, g)) return ASP_ERR_ARG;
-    if (g == 2) return launch_tpp_n<32, 2, LIKE, PRIOR>(A, s);
-    if (dl == 32) return launch_tpp_n<32, 1, LIKE, PRIOR>(A, s);
-    if (dl == 16) return launch_tpp_n<16, 1, LIKE, PRIOR>(A, s);
-    if (dl == 8) return launch_tpp_n<8, 1, LIKE, PRIOR>(A, s);
-    return launch_tpp_n<4, 1, LIKE, PRIOR>(A, s);
+    if (g == 2) return launch_tpp_n<32, 2, LIKE, PRIOR, TPCN>(A, s);
+    if (dl == 32) return launch_tpp_n<32, 1, LIKE, PRIOR, TPCN>(A, s);
+    if (dl == 16) return launch_tpp_n<16, 1, LIKE, PRIOR, TPCN>(A, s);
+    if (dl == 8) return launch_tpp_n<8, 1, LIKE, PRIOR, TPCN>(A, s);
+    return launch_tpp_n<4, 1, LIKE, PRIOR, TPCN>(A, s);
 }
 
-template <int LIKE>
+template <int LIKE, bool TPCN = false>
 inline int launch_tpp_like(const SweepArgs& A, cudaStream_t s) {
-    if (A.prior.kind == ASP_DENSITY_GAUSSIAN) return launch_tpp_shape<LIKE, ASP_DENSITY_GAUSSIAN>(A, s);
-    if (A.prior.kind == ASP_DENSITY_UNIFORM) return launch_tpp_shape<LIKE, ASP_DENSITY_UNIFORM>(A, s);
+    if (A.prior.kind == ASP_DENSITY_GAUSSIAN) return launch_tpp_shape<LIKE, ASP_DENSITY_GAUSSIAN, TPCN>(A, s);
+    if (A.prior.kind == ASP_DENSITY_UNIFORM) return launch_tpp_shape<LIKE, ASP_DENSITY_UNIFORM, TPCN>(A, s);
     return ASP_ERR_ARG;
 }
 
@@ -545,5 +605,10 @@ int launch_tpp_gaussian(const SweepArgs& A, cudaStream_t s);
 int launch_tpp_rosenbrock(const SweepArgs& A, cudaStream_t s);
 int launch_tpp_gmm(const SweepArgs& A, cudaStream_t s);
 int launch_tpp_uniform(const SweepArgs& A, cudaStream_t s);
+// tpCN (params->nu > 0) instantiations: pcn_tpp_t_*.cu
+int launch_tpp_t_gaussian(const SweepArgs& A, cudaStream_t s);
+int launch_tpp_t_rosenbrock(const SweepArgs& A, cudaStream_t s);
+int launch_tpp_t_gmm(const SweepArgs& A, cudaStream_t s);
+int launch_tpp_t_uniform(const SweepArgs& A, cudaStream_t s);
 
 }  // namespace asp

@@ -1,0 +1,5 @@
+// particle-per-thread tpCN sweep instantiations for the uniform likelihood (see pcn_sweep_tpp.cuh)
+#include "pcn_sweep_tpp.cuh"
+namespace asp {
+int launch_tpp_t_uniform(const SweepArgs& A, cudaStream_t s) { return launch_tpp_like<ASP_DENSITY_UNIFORM, true>(A, s); }
+}  // namespace asp

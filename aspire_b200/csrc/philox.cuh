@@ -118,6 +118,19 @@ __device__ __forceinline__ void philox_normal4(const PhiloxKeys& K, uint32_t str
     box_muller_f32(r.z, r.w, z[2], z[3]);
 }
 
+// One iteration of Marsaglia & Tsang's (2000) Gamma(a, 1) sampler, a >= 1, in fp32 from one Philox block (words 0, 1
+// -> the first Box-Muller normal, word 2 -> the uniform); d = a - 1/3, c = 1 / sqrt(9 d).  Spec:
+// oracle/pcn.py::gamma_mt_f32.  Shared by asp_tpcn_scales and the fused tpCN sweep so both draw the same variates.
+__device__ __forceinline__ bool gamma_mt_try(const uint4& r, float d, float c, double& g) {
+    float z, z1;
+    box_muller_f32(r.x, r.y, z, z1);
+    const float u = u01_f32(r.z);
+    const float t = 1.0f + c * z;
+    const float v = t * t * t;
+    g = (double)(d * v);
+    return t > 0.0f && sfu_log(u) < 0.5f * z * z + d - d * v + d * sfu_log(fmaxf(v, 1e-30f));
+}
+
 __device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
     return (double)((((uint64_t)hi << 32) | lo) >> 11) * 0x1p-53;
 }

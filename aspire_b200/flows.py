@@ -143,12 +143,75 @@ def pack_umma_kmajor(w: torch.Tensor, k_pad: int | None = None) -> torch.Tensor:
     return out
 
 
+class _NativeTrainer:
+    """State of ``asp_flow_fit_step``: flat fp32 master weights, Adam moments, gradient and workspace buffers."""
+
+    def __init__(self, flow: "CouplingFlow", batch_cap: int):
+        import ctypes as C
+
+        from . import _lib
+
+        lib = _lib.load()
+        self.flow, self.lib, self.C = flow, lib, C
+        k, n_layers, dev = flow.kdims, flow.n_layers, flow.device
+        n = lib.asp_flow_fit_params(k, n_layers)
+        self.w = torch.cat([torch.cat([layer[name].detach().float().reshape(-1)
+                                       for name in ("W1", "b1", "W2", "b2", "W3", "b3")]) for layer in flow.layers]).contiguous()
+        assert self.w.numel() == n
+        self.m, self.v, self.g = (torch.zeros_like(self.w) for _ in range(3))
+        self.ws = torch.zeros(lib.asp_flow_fit_workspace_floats(k, n_layers, batch_cap), dtype=torch.float32, device=dev)
+        half = k // 2
+        mask = torch.stack([flow._out_mask(t)[:half] for t in range(n_layers)]).to(torch.uint8).contiguous()
+        self.mask = mask
+        self.mean32, self.inv_std32 = flow.mean.float().contiguous(), (1.0 / flow.std).float().contiguous()
+        self.log_const = 0.5 * k * math.log(2.0 * math.pi) + float(torch.log(flow.std).sum())
+        t = _lib.FlowTrain()
+        t.kdims, t.hidden, t.n_layers, t.batch_cap = k, flow.hidden, n_layers, int(batch_cap)
+        t.d_w, t.d_m, t.d_v, t.d_g = (x.data_ptr() for x in (self.w, self.m, self.v, self.g))
+        t.d_out_mask = mask.data_ptr() if flow._pad else None
+        t.d_mean, t.d_inv_std, t.d_ws = self.mean32.data_ptr(), self.inv_std32.data_ptr(), self.ws.data_ptr()
+        self.t, self.steps = t, 0
+
+    def step(self, x32: torch.Tensor, lr: float, clip_grad) -> torch.Tensor:
+        from ._lib import check
+
+        x32 = x32.contiguous()
+        loss = torch.empty(1, dtype=torch.float32, device=x32.device)
+        self.steps += 1
+        check(self.lib.asp_flow_fit_step(self.C.byref(self.t), x32.data_ptr(), x32.shape[0], lr, 0.9, 0.999, 1e-8,
+                                         self.steps, float(clip_grad or 0.0), self.log_const, loss.data_ptr(),
+                                         ops._stream()), "asp_flow_fit_step")
+        return loss
+
+    def loss(self, x32: torch.Tensor) -> torch.Tensor:
+        from ._lib import check
+
+        x32 = x32.contiguous()
+        loss = torch.empty(1, dtype=torch.float32, device=x32.device)
+        check(self.lib.asp_flow_fit_loss(self.C.byref(self.t), x32.data_ptr(), x32.shape[0], self.log_const,
+                                         loss.data_ptr(), ops._stream()), "asp_flow_fit_loss")
+        return loss
+
+    def unflatten(self, w: torch.Tensor):
+        k, h, half = self.flow.kdims, self.flow.hidden, self.flow.kdims // 2
+        shapes = [("W1", (h, half)), ("b1", (h,)), ("W2", (h, h)), ("b2", (h,)), ("W3", (k, h)), ("b3", (k,))]
+        layers, off = [], 0
+        for _ in range(self.flow.n_layers):
+            layer = {}
+            for name, shape in shapes:
+                n = int(np.prod(shape))
+                layer[name] = w[off:off + n].reshape(shape).clone()
+                off += n
+            layers.append(layer)
+        return layers
+
+
 class CouplingFlow(Flow):
     """T affine-coupling layers (alternating half masks), conditioner MLP(D/2 -> 64 -> 64 -> D)
     with ReLU, soft-clipped log-scale, standard-normal base, input standardisation.
 
-    ``log_prob`` / ``sample_and_log_prob`` run on tcgen05 (``asp_flow_*_bf16``); ``fit`` trains the
-    same weight tensors with torch autograd (scaffolding - SURVEY 8f-1 - not part of the hot path).
+    ``log_prob`` / ``sample_and_log_prob`` run on tcgen05 (``asp_flow_*_bf16``); ``fit`` trains the fp32 master
+    weights with the library's forward / backward / Adam kernels (``asp_flow_fit_step``).
 
     The kernels are built for 16, 32 and 64 dimensions; any ``2 <= dims <= 64`` runs on the next kernel size with
     PADDING coordinates: the real coordinates are spread over both halves of the mask, a padding coordinate has
@@ -202,6 +265,18 @@ class CouplingFlow(Flow):
                 m = self._out_mask(t).to(layer["W3"].dtype)
                 layer["W3"].mul_(m[:, None])
                 layer["b3"].mul_(m)
+
+    def _mask_padding_grads(self, layers):
+        """Gradients of the padding rows are dropped before clipping / the optimiser step (the kernels never form
+        them: ``asp_flow_fit_step`` zeroes dO on those rows)."""
+        if not self._pad:
+            return
+        for t, layer in enumerate(layers):
+            m = self._out_mask(t).to(layer["W3"].dtype)
+            if layer["W3"].grad is not None:
+                layer["W3"].grad.mul_(m[:, None])
+            if layer["b3"].grad is not None:
+                layer["b3"].grad.mul_(m)
 
     def _embed(self, x: torch.Tensor) -> torch.Tensor:
         if not self._pad:
@@ -281,6 +356,12 @@ class CouplingFlow(Flow):
         logq, z = ops.flow_logprob(self.struct(), x, want_z=True)
         return self._extract(z), (logq + self._pad_const if self._pad else logq)
 
+    def inverse(self, z):
+        """Base-space points -> (x, log q(x)): the sampling direction on given z (``asp_flow_sample_bf16``)."""
+        u = self._embed(torch.as_tensor(z, dtype=torch.float64, device=self.device))
+        x, logq = ops.flow_sample(self.struct(), u)
+        return self._extract(x), (logq + self._pad_const if self._pad else logq)
+
     def sample_and_log_prob(self, n_samples):
         u = self._embed(self.rng.normal(n_samples, self.dims, self.device))  # padding base coordinates: 0
         x, logq = ops.flow_sample(self.struct(), u)
@@ -311,7 +392,10 @@ class CouplingFlow(Flow):
         flows/torch/flows.py:170-325): affine data transform from the samples (mean, unbiased std -
         ``transforms.py:618-621``), random permutation, train / validation split, Adam, optional gradient
         clipping, cosine annealing and early stopping, best-validation weights restored at the end.
-        The optimiser is torch autograd over the kernel's own weight tensors (scaffolding: SURVEY 8f-1)."""
+        On a CUDA device the optimisation itself - forward, backward, Adam - runs in the library's own kernels over
+        the flow's fp32 master weights (``asp_flow_fit_step``, csrc/flow_fit.cu); ``native=False`` (and
+        the CPU, where only the host logic can be tested) uses torch autograd over the same tensors, which is also
+        the reference the kernels' gradients are tested against."""
         x = samples.x if hasattr(samples, "x") else samples
         x = torch.as_tensor(x, dtype=torch.float64, device=self.device).clone()
         if bool(torch.isnan(x).any()):
@@ -332,40 +416,65 @@ class CouplingFlow(Flow):
         n_val = int(validation_fraction * n)
         x_train, x_val = (x32[:-n_val], x32[-n_val:]) if n_val > 0 else (x32, x32[:0])
         logger.info(f"Training on {x_train.shape[0]} samples, validating on {x_val.shape[0]} samples.")
-        params = [p.requires_grad_(True) for layer in self.layers for p in layer.values()]
-        opt = torch.optim.Adam(params, lr=lr)
-        sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, n_epochs) if lr_annealing else None
+        native = bool(kwargs.get("native", self.device.type == "cuda"))
         hist = FlowHistory()
         best_val, best_state, best_epoch = float("inf"), None, 0
+        if native:
+            trainer = _NativeTrainer(self, batch_size)
+        else:
+            params = [p.requires_grad_(True) for layer in self.layers for p in layer.values()]
+            opt = torch.optim.Adam(params, lr=lr)
+            sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, n_epochs) if lr_annealing else None
         for epoch in range(n_epochs):
             perm = torch.randperm(x_train.shape[0], generator=g).to(self.device)
-            tot, nb = 0.0, 0
-            for i in range(0, x_train.shape[0], batch_size):
-                loss = -self._torch_forward(x_train[perm[i:i + batch_size]], self.layers).mean()
-                opt.zero_grad()
-                loss.backward()
-                if clip_grad is not None:
-                    torch.nn.utils.clip_grad_norm_(params, clip_grad)
-                opt.step()
-                self._hold_padding()
-                tot += float(loss.detach())
-                nb += 1
-            if sched is not None:
-                sched.step()
+            nb = 0
+            if native:
+                lr_e = 0.5 * lr * (1.0 + math.cos(math.pi * epoch / n_epochs)) if lr_annealing else lr
+                tot_d = torch.zeros(1, dtype=torch.float32, device=self.device)
+                for i in range(0, x_train.shape[0], batch_size):
+                    tot_d += trainer.step(x_train[perm[i:i + batch_size]], lr_e, clip_grad)
+                    nb += 1
+                tot = float(tot_d)  # one device -> host read per epoch
+            else:
+                tot = 0.0
+                for i in range(0, x_train.shape[0], batch_size):
+                    loss = -self._torch_forward(x_train[perm[i:i + batch_size]], self.layers).mean()
+                    opt.zero_grad()
+                    loss.backward()
+                    self._mask_padding_grads(self.layers)
+                    if clip_grad is not None:
+                        torch.nn.utils.clip_grad_norm_(params, clip_grad)
+                    opt.step()
+                    self._hold_padding()
+                    tot += float(loss.detach())
+                    nb += 1
+                if sched is not None:
+                    sched.step()
             hist.training_loss.append(tot / max(nb, 1))
             val, nv = 0.0, 0
-            with torch.no_grad():
+            if native:
+                val_d = torch.zeros(1, dtype=torch.float32, device=self.device)
                 for i in range(0, x_val.shape[0], batch_size):
-                    val += float(-self._torch_forward(x_val[i:i + batch_size], self.layers).mean())
+                    val_d += trainer.loss(x_val[i:i + batch_size])
                     nv += 1
+                val = float(val_d) if nv else 0.0
+            else:
+                with torch.no_grad():
+                    for i in range(0, x_val.shape[0], batch_size):
+                        val += float(-self._torch_forward(x_val[i:i + batch_size], self.layers).mean())
+                        nv += 1
             avg_val = val / nv if nv else hist.training_loss[-1]
             hist.validation_loss.append(avg_val)
             if avg_val < best_val:
                 best_val, best_epoch = avg_val, epoch
-                best_state = [{k: v.detach().clone() for k, v in layer.items()} for layer in self.layers]
+                best_state = (trainer.w.clone() if native else
+                              [{k: v.detach().clone() for k, v in layer.items()} for layer in self.layers])
             if patience is not None and epoch - best_epoch >= patience:
                 logger.info(f"Early stopping triggered after {patience} epochs")
                 break
+        if native:
+            self.layers = trainer.unflatten(best_state if best_state is not None else trainer.w)
+            best_state = None if best_state is None else self.layers
         if best_state is not None:
             self.layers = best_state
             logger.info(f"Loaded best model from epoch {best_epoch} with val loss {best_val:.4f}")

@@ -484,7 +484,7 @@ def make_pcn_params(beta, rho, mu, sigma, n_moves, seed=0, stream0=0, index0=0, 
     prm.d_xi = None if xi is None else _f64(xi, "xi").data_ptr()
     prm.d_log_u = None if log_u is None else _f64(log_u, "log_u").data_ptr()
     prm.d_slot = None if slot is None else _i64(slot, "slot").data_ptr()
-    prm.nu = float(nu)  # > 0: tpCN (Student-t reference measure), unfused moves only
+    prm.nu = float(nu)  # > 0: tpCN (Student-t reference measure)
     prm.d_scale = None
     prm.d_gamma = None if gamma is None else _f64(gamma, "gamma").data_ptr()
     prm._keep = (mu, sigma, xi, log_u, slot, gamma)  # keep the tensors alive
@@ -506,6 +506,11 @@ def pcn_sweep(x, log_l, log_p, log_q, idx, like, prior, q, prm, out=None):
                                     C.byref(prm), out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
                                     out[3].data_ptr(), accepts.data_ptr(), _stream()), "asp_pcn_sweep")
     return (*out, accepts[:1] if prm.reserved else accepts[:prm.n_moves])
+
+
+def pcn_sweep_tpcn_supported(dims: int) -> bool:
+    """Whether ``pcn_sweep`` runs tpCN moves (``prm.nu > 0``) in the fused kernel for this dimension."""
+    return bool(_lib.load().asp_pcn_sweep_tpcn_supported(int(dims)))
 
 
 def tpcn_scales(x, prm, move: int) -> torch.Tensor:

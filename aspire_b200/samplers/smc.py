@@ -382,8 +382,8 @@ class SMCSampler(Sampler):
         kw.setdefault("moment_particles", 1 << 22)
         if kw["step_fn"] not in ("pcn", "tpcn"):
             raise ValueError(f"step_fn={kw['step_fn']!r}: expected 'pcn' or 'tpcn'")
-        # 'pcn' (default here) runs the fused sweep; 'tpcn' (the reference's default, smc/minipcn.py:48) fits a
-        # Student-t reference measure by EM and runs unfused moves (asp_tpcn_scales + propose / accept)
+        # both run the fused sweep with built-in densities; 'tpcn' (the reference's default, smc/minipcn.py:48)
+        # first fits a Student-t reference measure by EM; other dims / callables: unfused moves
         self.step_fn = kw["step_fn"]
         self.sampler_kwargs = kw
         self.rho = float(kw["rho"])
@@ -510,8 +510,12 @@ class SMCSampler(Sampler):
         else:
             prm = ops.make_pcn_params(beta, self.rho, mu, sigma, n_moves, seed=self.rng.seed,
                                       stream0=self.rng.next_stream(n_moves), index0=getattr(self, "index0", 0),
-                                      total_accepts_only=not tpcn, nu=nu)
-        if self.fused and not tpcn:
+                                      total_accepts_only=True, nu=nu)
+        fused = self.fused and (not tpcn or (ops.pcn_sweep_tpcn_supported(dims) and self.rho < 1.0
+                                             and particles.x.data_ptr() % 16 == 0))
+        if not fused and not self.rng.is_host:
+            prm.reserved = 0  # the unfused kernels count accepts per move
+        if fused:
             x, ll, lp, lq, accepts = ops.pcn_sweep(particles.x, particles.log_likelihood, particles.log_prior,
                                                    particles.log_q, idx, self._log_likelihood, self._log_prior,
                                                    self.prior_flow.density, prm, out=out)

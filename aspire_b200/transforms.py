@@ -7,8 +7,9 @@ Same classes, constructor arguments and method contracts as the reference's ``sr
 array-API updates.  Tensors are fp64 CUDA tensors; there is no CPU path.  Spec: ``oracle/transforms.py``, pinned
 against the reference's own classes.
 
-Not built here: ``FlowPreconditioningTransform`` (``transforms.py:649-748``: a flow fitted per SMC step, row
-8f-1) and the HDF5 ``save`` / ``load`` (``h5py`` absent; ``state_dict`` carries the same content)."""
+``FlowPreconditioningTransform`` (``transforms.py:649-748``) refits a coupling flow to the ensemble at every SMC
+step with the device fit (``asp_flow_fit_step``, row 8f-1) and maps through it on tcgen05.  Not built here: the
+HDF5 ``save`` / ``load`` (``h5py`` absent; ``state_dict`` carries the same content)."""
 
 from __future__ import annotations
 
@@ -289,3 +290,92 @@ class FlowTransform(CompositeTransform):
         cfg = super().config_dict()
         cfg.pop("periodic_parameters", None)
         return cfg
+
+
+class FlowPreconditioningTransform(BaseTransform):
+    """``transforms.py:649-748``: preconditioning by a normalising flow that is refitted to the ensemble at every
+    SMC step - ``fit(x)`` builds and trains a new flow on x and returns the base-space points, ``forward`` /
+    ``inverse`` map through it with the log-Jacobian of the whole chain (bounded / periodic data transform, then the
+    flow).  The flow is the library's ``CouplingFlow``: trained by the device kernels (``asp_flow_fit_step``),
+    evaluated on tcgen05 (``asp_flow_logprob_bf16`` gives z and log q(x), ``asp_flow_sample_bf16`` the way back);
+    ``log|det J| = log q(x) - log N(z)`` in either direction.  The coupling MLPs run in bf16 / fp32, so the
+    round trip x -> z -> x closes to ~1e-6, like the reference's fp32 flows."""
+
+    name = "flow_preconditioning"
+
+    def __init__(self, parameters, flow_backend: str = "b200", prior_bounds=None, bounded_to_unbounded: bool = True,
+                 bounded_transform: str = "probit", affine_transform: bool = True, periodic_parameters=None,
+                 device=None, xp=None, eps: float = 1e-6, dtype: Any = None, flow_matching: bool = False,
+                 flow_kwargs: dict | None = None, fit_kwargs: dict | None = None):
+        super().__init__(xp, dtype, device)
+        if flow_matching:
+            raise NotImplementedError("flow matching is out of scope")
+        self.parameters = list(parameters)
+        self.periodic_parameters = list(periodic_parameters or [])
+        self.prior_bounds = prior_bounds
+        self.bounded_to_unbounded = bounded_to_unbounded
+        self.bounded_transform = bounded_transform
+        self.affine_transform = affine_transform
+        self.eps = eps
+        self.flow_backend = flow_backend
+        self.flow_matching = flow_matching
+        self.flow_kwargs = {k: v for k, v in dict(flow_kwargs or {}).items() if k not in ("flow_class", "dtype")}
+        self.fit_kwargs = dict(fit_kwargs or {})
+        # the flow standardises its input itself, so the data transform keeps its affine stage only when asked
+        self._data_transform = CompositeTransform(
+            parameters=self.parameters, periodic_parameters=self.periodic_parameters, prior_bounds=prior_bounds,
+            bounded_to_unbounded=bounded_to_unbounded, bounded_transform=bounded_transform,
+            affine_transform=affine_transform, device=self.device, eps=eps)
+        self.flow = None
+        self.history = None
+
+    def _log_normal(self, z: torch.Tensor) -> torch.Tensor:
+        return -0.5 * (z * z).sum(dim=1) - 0.5 * z.shape[1] * math.log(2.0 * math.pi)
+
+    def fit(self, x):
+        from .flows import CouplingFlow
+
+        x = self._rows(x)
+        self.flow = CouplingFlow(dims=len(self.parameters), device=self.device, **self.flow_kwargs)
+        y = x if self._data_transform.is_identity else self._data_transform.fit(x)
+        self.history = self.flow.fit(y, **self.fit_kwargs)
+        return self.forward(x)[0]
+
+    def _require(self):
+        if self.flow is None:
+            raise RuntimeError("FlowPreconditioningTransform must be fitted first")
+
+    def forward(self, x):
+        self._require()
+        x = self._rows(x)
+        y, lj = (x, 0.0) if self._data_transform.is_identity else self._data_transform.forward(x)
+        z, log_q = self.flow.forward(y)
+        return z, lj + (log_q - self._log_normal(z))
+
+    def inverse(self, z):
+        self._require()
+        z = self._rows(z)
+        y, log_q = self.flow.inverse(z)
+        lj_flow = self._log_normal(z) - log_q
+        if self._data_transform.is_identity:
+            return y, lj_flow
+        x, lj = self._data_transform.inverse(y)
+        return x, lj + lj_flow
+
+    def new_instance(self, xp=None, dtype: Any = None):
+        return self.__class__(parameters=self.parameters, periodic_parameters=self.periodic_parameters,
+                              prior_bounds=self.prior_bounds, bounded_to_unbounded=self.bounded_to_unbounded,
+                              bounded_transform=self.bounded_transform, affine_transform=self.affine_transform,
+                              device=self.device, eps=self.eps, flow_backend=self.flow_backend,
+                              flow_matching=self.flow_matching, flow_kwargs=self.flow_kwargs, fit_kwargs=self.fit_kwargs)
+
+    def config_dict(self):
+        return BaseTransform.config_dict(self) | {
+            "parameters": self.parameters, "periodic_parameters": self.periodic_parameters,
+            "prior_bounds": self.prior_bounds, "bounded_to_unbounded": self.bounded_to_unbounded,
+            "bounded_transform": self.bounded_transform, "affine_transform": self.affine_transform,
+            "eps": self.eps, "device": str(self.device), "flow_backend": self.flow_backend,
+            "flow_kwargs": self.flow_kwargs, "fit_kwargs": self.fit_kwargs}
+
+    def save(self, h5_file, path="data_transform"):
+        raise NotImplementedError("FlowPreconditioningTransform does not support save method yet.")  # transforms.py:745-748

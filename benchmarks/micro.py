@@ -276,7 +276,8 @@ def sweep(args):
             idx = torch.sort(idx).values
         mom = ops.weighted_moments(x[: 1 << 20])
         mu, sigma = ops.moments_to_mu_sigma(mom, dims)
-        prm = ops.make_pcn_params(0.1, 0.3, mu, sigma, args.moves, seed=99, stream0=3, total_accepts_only=True)
+        prm = ops.make_pcn_params(0.1, 0.3, mu, sigma, args.moves, seed=99, stream0=3, total_accepts_only=True,
+                                  nu=args.nu)  # --nu > 0: tpCN moves (Student-t reference) in the same fused kernel
         out = tuple(torch.empty_like(t) for t in (x, ll, lp, lq))
         res = {}
 
@@ -286,7 +287,7 @@ def sweep(args):
         ms = timed(run, args.iters)
         acc = float(res["o"][4].sum()) / (n * args.moves)
         w = (16 * dims + 48) * n
-        print(json.dumps({"bench": "pcn_sweep", "problem": name, "particles": n, "dims": dims, "moves": args.moves,
+        print(json.dumps({"bench": "tpcn_sweep" if args.nu > 0 else "pcn_sweep", "nu": args.nu, "problem": name, "particles": n, "dims": dims, "moves": args.moves,
                           "ms": ms, "particle_moves_per_s": n * args.moves / ms * 1e3, "normals_per_s":
                           n * args.moves * dims / ms * 1e3, "algorithmic_gbs": w / ms / 1e6,
                           "hbm_frac": w / ms / 1e6 / PEAKS["hbm_gbs"], "acceptance": acc,
@@ -463,6 +464,7 @@ if __name__ == "__main__":
     ap.add_argument("--moves", type=int, default=10)
     ap.add_argument("--dims", type=int, default=0)
     ap.add_argument("--sorted-idx", action="store_true")
+    ap.add_argument("--nu", type=float, default=0.0, help="sweep: > 0 runs tpCN moves with this many degrees of freedom")
     ap.add_argument("--numpy-max", type=int, default=10**7, help="largest n timed with numpy on the host (resample)")
     ap.add_argument("--gpus", type=int, default=1, help="resample: launch with torch.distributed.run for N > 1")
     ap.add_argument("--only", default="")

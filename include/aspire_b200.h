@@ -317,7 +317,7 @@ typedef struct asp_pcn_params {
     const double* d_log_u;/* [n_moves, n] log-uniforms   (noise_mode 1)         */
     const int64_t* d_slot;/* optional per-particle Philox counter (global output
                              slot); NULL: index0 + i                            */
-    /* tpCN (Student-t preconditioned CN, the reference's default step_fn): unfused moves only */
+    /* tpCN (Student-t preconditioned CN, the reference's default step_fn, smc/minipcn.py:48) */
     double nu;            /* 0: pCN (Gaussian reference); > 0: degrees of freedom of the
                              Student-t reference t_nu(mu, diag sigma^2)          */
     const double* d_scale;/* [n] per-particle proposal scale sqrt(s_i) of the current
@@ -328,7 +328,11 @@ typedef struct asp_pcn_params {
 /* Fused sweep: particle i starts from row d_idx[i] of the inputs (d_idx NULL
  * = identity, i.e. no resampling gather), runs n_moves accept/reject moves
  * with built-in densities and writes the final state.  d_accepts[n_moves]
- * (uint64) is incremented by the per-move accept counts (caller zeroes it). */
+ * (uint64) is incremented by the per-move accept counts (caller zeroes it).
+ * params->nu > 0 runs tpCN moves in the same kernel (gamma variates drawn in-kernel, or params->d_gamma with
+ * supplied noise; d_scale is ignored): same trajectory as asp_tpcn_scales + asp_pcn_propose + asp_pcn_accept.
+ * Built for the dims asp_pcn_sweep_tpcn_supported reports (4, 8, 16, 32, 64); other dims return ASP_ERR_ARG. */
+int32_t asp_pcn_sweep_tpcn_supported(int32_t dims);
 int asp_pcn_sweep(const double* d_x, const double* d_log_l, const double* d_log_p, const double* d_log_q,
                   const int64_t* d_idx, int64_t n, int32_t dims, const asp_density_t* like,
                   const asp_density_t* prior, const asp_density_t* q, const asp_pcn_params_t* params,
@@ -393,6 +397,31 @@ size_t asp_flow_weights_bytes(int32_t dims, int32_t n_layers);
 int asp_flow_logprob_bf16(const asp_flow_t* flow, const double* d_x, int64_t n, double* d_logq, double* d_z, void* stream);
 /* d_u: base normals [n, dims] -> d_x [n, dims], d_logq[i] = log q(x_i). */
 int asp_flow_sample_bf16(const asp_flow_t* flow, const double* d_u, int64_t n, double* d_x, double* d_logq, void* stream);
+
+/* ---- coupling-flow fit on the device (8f-1) ----------------------------------
+ * The optimisation loop of ZukoFlow.fit (src/aspire/flows/torch/flows.py:170-325: Adam on the mean negative
+ * log-likelihood of mini-batches): forward, backward and Adam kernels over the flow's fp32 master weights.
+ * One layer's parameters are laid out  W1[64, K/2] | b1[64] | W2[64, 64] | b2[64] | W3[K, 64] | b3[K]  (row-major,
+ * K = kdims); d_w / d_m / d_v / d_g hold n_layers such blocks (asp_flow_fit_params floats each).  d_out_mask
+ * (optional) is [n_layers][K/2] bytes: 0 marks a padding coordinate of the half the layer transforms - its
+ * shift / log-scale rows get zero gradient, so they stay zero.  d_ws: asp_flow_fit_workspace_floats floats.
+ * asp_flow_fit_step: d_loss[0] = mean_s(-log q(x_s)) of the batch BEFORE the update (log_const = K/2 log 2 pi +
+ * sum log std is added), then one Adam step (torch.optim.Adam semantics; step = 1, 2, ... for the bias correction;
+ * clip_grad > 0: global-norm clipping as torch.nn.utils.clip_grad_norm_).  asp_flow_fit_loss: forward only. */
+typedef struct asp_flow_train {
+    int32_t kdims, hidden, n_layers, batch_cap;
+    float *d_w, *d_m, *d_v, *d_g;
+    const unsigned char* d_out_mask;
+    const float* d_mean;
+    const float* d_inv_std;
+    float* d_ws;
+} asp_flow_train_t;
+size_t asp_flow_fit_params(int32_t kdims, int32_t n_layers);
+size_t asp_flow_fit_workspace_floats(int32_t kdims, int32_t n_layers, int32_t batch_cap);
+int asp_flow_fit_step(const asp_flow_train_t* t, const float* d_x, int32_t b, float lr, float beta1, float beta2,
+                      float eps, int32_t step, float clip_grad, float log_const, float* d_loss, void* stream);
+int asp_flow_fit_loss(const asp_flow_train_t* t, const float* d_x, int32_t b, float log_const, float* d_loss,
+                      void* stream);
 
 /* ---- owner-computes multinomial resampling across GPUs (K12) ---------------
  * (no reference site: the reference is single-process.)  Every rank walks the same

@@ -217,6 +217,8 @@ class Doubles:
         x, ll, lp, lq = (t.clone().contiguous() for t in (x, ll, lp, lq))
         accepts = torch.zeros(max(prm.n_moves, 1), dtype=torch.int64)
         for t in range(prm.n_moves):
+            if prm.nu > 0:
+                self.tpcn_scales(x, prm, t)
             xp = self.pcn_propose(x, prm, t)
             self.pcn_accept(x, ll, lp, lq, xp, self.logdensity(like, xp), self.logdensity(prior, xp),
                             self.logdensity(q, xp), prm, t, accepts)
@@ -225,6 +227,10 @@ class Doubles:
     @staticmethod
     def pcn_propose_eval_supported(dims, like, prior):
         return False
+
+    @staticmethod
+    def pcn_sweep_tpcn_supported(dims):
+        return dims in (4, 8, 16, 32, 64)
 
     @staticmethod
     def logdensity(dens, x):
@@ -248,7 +254,8 @@ class Doubles:
 NAMES = ["_f64", "_i64", "_stream", "device_check", "reweight", "ess_sums", "beta_search", "smc_weights",
          "importance_weights", "cdf_exact", "search_multinomial", "search_multinomial_sorted", "search_systematic", "gather_rows",
          "weighted_moments", "moments_to_mu_sigma", "philox_uniform", "philox_normal", "pcg64_uniform", "make_pcn_params",
-         "tpcn_scales", "pcn_propose", "pcn_accept", "pcn_sweep", "pcn_propose_eval_supported", "logdensity",
+         "tpcn_scales", "pcn_propose", "pcn_accept", "pcn_sweep", "pcn_propose_eval_supported", "pcn_sweep_tpcn_supported",
+         "logdensity",
          "transform_apply"]
 
 

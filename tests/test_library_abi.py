@@ -64,7 +64,8 @@ def test_struct_layouts_match_the_header(tmp_path):
     if gcc is None:
         pytest.skip("gcc not found")
     pairs = {"asp_density_t": _lib.Density, "asp_beta_state_t": _lib.BetaState, "asp_peer_t": _lib.PeerDesc,
-             "asp_pcn_params_t": _lib.PcnParams, "asp_flow_t": _lib.Flow, "asp_transform_t": _lib.TransformDesc}
+             "asp_pcn_params_t": _lib.PcnParams, "asp_flow_t": _lib.Flow, "asp_transform_t": _lib.TransformDesc,
+             "asp_flow_train_t": _lib.FlowTrain}
     text = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "aspire_b200.h")).read(), flags=re.S)
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "aspire_b200.h"', "int main(void) {"]
     fields = {}

@@ -91,8 +91,12 @@ def test_init_sampler_preconditioning_selection():
                        ).preconditioning_transform
     assert t._kind_host == [T.BOUNDED, T.PERIODIC] and t.affine_transform and t.bounded_transform == "logit"
     assert a.init_sampler("smc", preconditioning="none").preconditioning_transform is None
-    with pytest.raises(NotImplementedError):
-        a.init_sampler("smc", preconditioning="flow")
+    t = a.init_sampler("smc", preconditioning="flow", preconditioning_kwargs={"fit_kwargs": {"n_epochs": 3}}
+                       ).preconditioning_transform                            # aspire.py:351-366
+    assert isinstance(t, T.FlowPreconditioningTransform) and not t.affine_transform and t.fit_kwargs == {"n_epochs": 3}
+    assert t._data_transform._kind_host == [T.BOUNDED, T.PERIODIC] and t.flow is None
+    with pytest.raises(RuntimeError, match="fitted"):
+        t.forward(torch.zeros(3, 2, dtype=torch.float64))
     with pytest.raises(ValueError, match="Unknown preconditioning"):
         a.init_sampler("smc", preconditioning="whitening")
 
