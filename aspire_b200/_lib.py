@@ -209,6 +209,10 @@ SIGNATURES = {
     "asp_flow_weights_bytes": (C.c_size_t, [_I32, _I32]),
     "asp_flow_logprob_bf16": (C.c_int, [C.POINTER(Flow), _P, _I64, _P, _P, _P]),
     "asp_flow_sample_bf16": (C.c_int, [C.POINTER(Flow), _P, _I64, _P, _P, _P]),
+    "asp_pcn_sweep_flow_supported": (_I32, [_I32, _I32, _I32]),
+    "asp_pcn_sweep_flow_workspace_bytes": (C.c_size_t, [_I32]),
+    "asp_pcn_sweep_flow": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, C.POINTER(Density), C.POINTER(Density),
+                                     C.POINTER(Flow), C.POINTER(PcnParams), _P, _P, _P, _P, _P, _P, _P]),
     "asp_flow_fit_params": (C.c_size_t, [_I32, _I32]),
     "asp_flow_fit_workspace_floats": (C.c_size_t, [_I32, _I32, _I32]),
     "asp_flow_fit_step": (C.c_int, [C.POINTER(FlowTrain), _P, _I32, C.c_float, C.c_float, C.c_float, C.c_float, _I32,
@@ -252,7 +256,8 @@ KERNELS_PER_CALL = {"asp_importance_weights": 3, "asp_cdf_exact": 6, "asp_cdf_ti
                     "asp_cdf_set_tile_stats": 2, "asp_cdf_info": 0, "asp_device_check": 0,
                     "asp_search_multinomial_guided": 4, "asp_select_uniforms": 3, "asp_search_systematic": 3,
                     "asp_search_systematic_workspace_bytes": 0, "asp_pcn_propose_eval_supported": 0, "asp_beta_search_max_passes3": 0,
-                    "asp_sorted_tiles": 0, "asp_search_sorted": 2, "asp_pcn_sweep_tpcn_supported": 0,
+                    "asp_sorted_tiles": 0, "asp_search_sorted": 2, "asp_pcn_sweep_tpcn_supported": 0, "asp_pcn_sweep_flow_supported": 0,
+                    "asp_pcn_sweep_flow_workspace_bytes": 0, "asp_flow_fit_params": 0, "asp_flow_fit_workspace_floats": 0,
                     "asp_beta_search_root": 6, "asp_beta_search_run": 8, "asp_beta_search_scratch_words": 0}
 launch_count = 0
 

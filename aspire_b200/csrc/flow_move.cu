@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(kFlowThreads* kMoveWG, 1) flow_move_kernel(con
                     const int d = q * 4 + j;
                     const double2 rf = lds2(&s_ref[d]), ip = lds2(&s_ip[d]), pf = lds2(&s_pf[d]);
                     const double y = xc[j] - rf.x;
-                    const double v = rf.x + fma(rf.y, xi[j], ca * y);  // oracle/pcn.py::propose
+                    const double v = rf.x + (ca * y + rf.y * xi[j]);  // oracle/pcn.py::propose (same expression as pcn_eval.cu)
                     xn[j] = v;
                     const double z1 = (v - rf.x) * ip.x;
                     r1 = fma(z1, z1, r1);

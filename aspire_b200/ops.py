@@ -513,6 +513,30 @@ def pcn_sweep_tpcn_supported(dims: int) -> bool:
     return bool(_lib.load().asp_pcn_sweep_tpcn_supported(int(dims)))
 
 
+def pcn_sweep_flow_supported(dims: int, like, prior) -> bool:
+    return bool(_lib.load().asp_pcn_sweep_flow_supported(int(dims), int(like.kind), int(prior.kind)))
+
+
+def pcn_sweep_flow(x, log_l, log_p, log_q, idx, like, prior, flow_struct, prm, out=None):
+    """Fused gather + ``n_moves`` pCN moves whose proposal density is a coupling flow (log q(x') on tcgen05 inside
+    the move).  -> (x, log_l, log_p, log_q, accepts)."""
+    x, log_l, log_p, log_q = _f64(x, "x"), _f64(log_l, "log_l"), _f64(log_p, "log_p"), _f64(log_q, "log_q")
+    dims = x.shape[1]
+    n = x.shape[0] if idx is None else idx.numel()
+    idx = None if idx is None else _i64(idx, "idx")
+    if out is None:
+        out = (torch.empty(n, dims, dtype=torch.float64, device=x.device),
+               *(torch.empty(n, dtype=torch.float64, device=x.device) for _ in range(3)))
+    lib = _lib.load()
+    ws = _sized_ws("flow_sweep", lib.asp_pcn_sweep_flow_workspace_bytes(dims), x.device)
+    accepts = torch.zeros(max(prm.n_moves, 1), dtype=torch.int64, device=x.device)
+    check(lib.asp_pcn_sweep_flow(x.data_ptr(), log_l.data_ptr(), log_p.data_ptr(), log_q.data_ptr(), _ptr(idx), n, dims,
+                                 C.byref(like.struct()), C.byref(prior.struct()), C.byref(flow_struct), C.byref(prm),
+                                 out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), out[3].data_ptr(),
+                                 accepts.data_ptr(), ws.data_ptr(), _stream()), "asp_pcn_sweep_flow")
+    return (*out, accepts[:1] if prm.reserved else accepts[:prm.n_moves])
+
+
 def tpcn_scales(x, prm, move: int) -> torch.Tensor:
     """tpCN: per-particle proposal scale sqrt(s_i) of move ``move`` (``oracle/pcn.py::tpcn_scale``); the
     result is attached to ``prm`` (``d_scale``) for the following ``pcn_propose``."""

@@ -411,6 +411,17 @@ class SMCSampler(Sampler):
                                    stream0=self.rng.next_stream(n_moves), index0=getattr(self, "index0", 0),
                                    total_accepts_only=False, nu=nu)
 
+    def _flow_sweep_ok(self, particles, n_moves: int, tpcn: bool) -> bool:
+        """Whether the mutation can run in ``asp_pcn_sweep_flow``: pCN, built-in Gaussian prior and Gaussian /
+        mixture likelihood, an unpadded ``CouplingFlow`` (16 / 32 / 64 dimensions) as ``prior_flow``."""
+        from ..flows import CouplingFlow
+
+        f = self.prior_flow
+        return (not tpcn and self.sampler_kwargs.get("flow_sweep", True) and type(f) is CouplingFlow and not f._pad
+                and isinstance(self._log_likelihood, Density) and isinstance(self._log_prior, Density)
+                and self.rho < 1.0 and n_moves <= 256 and particles.x.data_ptr() % 32 == 0
+                and ops.pcn_sweep_flow_supported(self.dims, self._log_likelihood, self._log_prior))
+
     def _mutate_preconditioned(self, particles: SMCSamples, beta: float, n_moves: int, idx, mark) -> SMCSamples:
         """Mutation in the space of the preconditioning transform (smc/minipcn.py:102-131): z = T.fit(x), pCN / tpCN
         moves on z against ``log_prob(z) = log_p_t(T^-1(z)) + log|det J|`` (smc/base.py:507-519), x = T^-1(z_last),
@@ -519,6 +530,16 @@ class SMCSampler(Sampler):
             x, ll, lp, lq, accepts = ops.pcn_sweep(particles.x, particles.log_likelihood, particles.log_prior,
                                                    particles.log_q, idx, self._log_likelihood, self._log_prior,
                                                    self.prior_flow.density, prm, out=out)
+            if mark:
+                mark("pcn_sweep")
+            self.n_likelihood_evaluations += n * n_moves
+        elif self._flow_sweep_ok(particles, n_moves, tpcn):
+            # built-in prior / likelihood, coupling flow as the proposal density (C4): gather, all moves with
+            # log q(x') on tcgen05 inside the move, and the final store in one kernel (csrc/flow_move.cu)
+            prm.reserved = 1
+            x, ll, lp, lq, accepts = ops.pcn_sweep_flow(particles.x, particles.log_likelihood, particles.log_prior,
+                                                        particles.log_q, idx, self._log_likelihood, self._log_prior,
+                                                        self.prior_flow.struct(), prm, out=out)
             if mark:
                 mark("pcn_sweep")
             self.n_likelihood_evaluations += n * n_moves

@@ -398,6 +398,24 @@ int asp_flow_logprob_bf16(const asp_flow_t* flow, const double* d_x, int64_t n, 
 /* d_u: base normals [n, dims] -> d_x [n, dims], d_logq[i] = log q(x_i). */
 int asp_flow_sample_bf16(const asp_flow_t* flow, const double* d_u, int64_t n, double* d_x, double* d_logq, void* stream);
 
+/* ---- pCN sweep with the coupling flow as proposal density (C4) -----------------
+ * MiniPCNSMC.mutate (src/aspire/samplers/smc/minipcn.py:89-117) with a learned flow as prior_flow: the resampling
+ * gather, n_moves x (propose, built-in prior / likelihood at x', log q(x') through the flow on tcgen05, accept)
+ * and the final store in ONE kernel - a particle is read once and written once per sweep instead of three passes
+ * over the particle set per move (asp_pcn_propose_eval + asp_flow_logprob_bf16 + asp_pcn_accept_scalar, which walk
+ * the same trajectory).  Arguments as asp_pcn_sweep, with the flow descriptor in place of the proposal density;
+ * n_moves <= 256; rows 32-byte aligned; d_ws: asp_pcn_sweep_flow_workspace_bytes(dims) bytes of scratch (the
+ * current points and proposals of the tiles in flight; L2-resident).  Built for dims 16, 32, 64, a Gaussian prior
+ * and a Gaussian or mixture likelihood (asp_pcn_sweep_flow_supported); a tensor-core barrier time-out sets
+ * flow->d_error bit 0. */
+int32_t asp_pcn_sweep_flow_supported(int32_t dims, int32_t like_kind, int32_t prior_kind);
+size_t asp_pcn_sweep_flow_workspace_bytes(int32_t dims);
+int asp_pcn_sweep_flow(const double* d_x, const double* d_log_l, const double* d_log_p, const double* d_log_q,
+                       const int64_t* d_idx, int64_t n, int32_t dims, const asp_density_t* like,
+                       const asp_density_t* prior, const asp_flow_t* flow, const asp_pcn_params_t* params,
+                       double* d_x_out, double* d_log_l_out, double* d_log_p_out, double* d_log_q_out,
+                       unsigned long long* d_accepts, void* d_ws, void* stream);
+
 /* ---- coupling-flow fit on the device (8f-1) ----------------------------------
  * The optimisation loop of ZukoFlow.fit (src/aspire/flows/torch/flows.py:170-325: Adam on the mean negative
  * log-likelihood of mini-batches): forward, backward and Adam kernels over the flow's fp32 master weights.

@@ -229,6 +229,10 @@ class Doubles:
         return False
 
     @staticmethod
+    def pcn_sweep_flow_supported(dims, like, prior):
+        return False
+
+    @staticmethod
     def pcn_sweep_tpcn_supported(dims):
         return dims in (4, 8, 16, 32, 64)
 
@@ -254,7 +258,7 @@ class Doubles:
 NAMES = ["_f64", "_i64", "_stream", "device_check", "reweight", "ess_sums", "beta_search", "smc_weights",
          "importance_weights", "cdf_exact", "search_multinomial", "search_multinomial_sorted", "search_systematic", "gather_rows",
          "weighted_moments", "moments_to_mu_sigma", "philox_uniform", "philox_normal", "pcg64_uniform", "make_pcn_params",
-         "tpcn_scales", "pcn_propose", "pcn_accept", "pcn_sweep", "pcn_propose_eval_supported", "pcn_sweep_tpcn_supported",
+         "tpcn_scales", "pcn_propose", "pcn_accept", "pcn_sweep", "pcn_propose_eval_supported", "pcn_sweep_tpcn_supported", "pcn_sweep_flow_supported",
          "logdensity",
          "transform_apply"]
 

@@ -339,3 +339,102 @@ def test_native_fit_trains_and_follows_the_protocol(cuda):
     # the tcgen05 evaluation of the re-packed bf16 weights reproduces the trained fp32 model (these rows are mostly
     # training rows, so the value sits between the last training loss and the validation loss)
     assert ha.training_loss[-1] - 0.3 < float(-lq.mean()) < min(ha.validation_loss) + 0.1
+
+
+# ---------------------------------------------------------------- the sweep with the flow inside (csrc/flow_move.cu)
+@pytest.mark.parametrize("dims,like,n,n_comp,philox", [(64, "gmm", 6000, 8, False), (64, "gmm", 4097, 8, True),
+                                                       (32, "gauss", 5000, 0, False), (16, "gmm", 3001, 11, True),
+                                                       (32, "gmm", 130, 3, True), (64, "gauss", 1, 0, True)])
+def test_flow_sweep_equals_the_semi_fused_moves(cuda, dims, like, n, n_comp, philox):
+    """asp_pcn_sweep_flow (gather + all moves, log q(x') on tcgen05 inside the move, one kernel) against the per-move
+    chain asp_pcn_propose_eval -> asp_flow_logprob_bf16 -> asp_pcn_accept_scalar on the same ancestors and the same
+    noise (supplied arrays or the Philox streams): the same trajectory.  The two routes evaluate the same fp32 flow
+    chain; the proposal's fp64 rounding may differ in the last bit, which can move log q by ~1e-6 and flip an accept
+    decision that sits inside that margin - allowed for at most 0.1 % of the particles."""
+    import torch
+
+    from aspire_b200 import ops
+    from aspire_b200 import targets as tg
+
+    rng = np.random.default_rng(dims + n)
+    f, _ = _flow(dims, 3, cuda, seed=4)
+    f.mean = _t(rng.normal(0.0, 0.3, dims), cuda)
+    f.std = _t(rng.uniform(1.5, 2.5, dims), cuda)
+    f._struct = None
+    prior = tg.GaussianDensity(0.0, 4.0, dims, device=cuda)
+    if like == "gmm":
+        means = rng.choice([-2.0, 2.0], size=(n_comp, dims))
+        L = tg.GaussianMixtureDensity(means, 0.7, device=cuda)
+    else:
+        L = tg.GaussianDensity(rng.normal(0.5, 0.2, dims), rng.uniform(0.8, 1.2, dims), dims, device=cuda)
+    moves, beta, rho = 6, 0.35, 0.3
+    x = _t(rng.normal(0.0, 2.0, (n, dims)), cuda)
+    ll, lp, lq = L.log_prob(x), prior.log_prob(x), f.log_prob(x)
+    m = n + 17
+    idx = _t(np.sort(rng.integers(0, n, size=m)), cuda)
+    mu, sigma = _t(rng.normal(0.0, 0.2, dims), cuda), _t(rng.uniform(1.5, 2.2, dims), cuda)
+    if philox:
+        mk = lambda: ops.make_pcn_params(beta, rho, mu, sigma, moves, seed=17, stream0=3, index0=500)  # noqa: E731
+    else:
+        xi = _t(rng.standard_normal((moves, m, dims)), cuda)
+        log_u = _t(np.log(1.0 - rng.random((moves, m))), cuda)
+        mk = lambda: ops.make_pcn_params(beta, rho, mu, sigma, moves, xi=xi, log_u=log_u)  # noqa: E731
+    assert ops.pcn_sweep_flow_supported(dims, L, prior)
+    out = ops.pcn_sweep_flow(x, ll, lp, lq, idx, L, prior, f.struct(), mk())
+    f.check_error()
+    prm = mk()
+    st = list(ops.gather_rows(x, idx, ll, lp, lq))
+    acc = torch.zeros(moves, dtype=torch.int64, device=cuda)
+    for t in range(moves):
+        xp, ll2, lp2, dr = ops.pcn_propose_eval(st[0], L, prior, prm, t)
+        ops.pcn_accept_scalar(st[0], st[1], st[2], st[3], xp, ll2, lp2, f.log_prob(xp), dr, prm, t, acc)
+    f.check_error()
+    got, ref = out[0].cpu().numpy(), st[0].cpu().numpy()
+    same = np.isclose(got, ref, rtol=1e-12, atol=1e-12).all(axis=1)
+    assert same.mean() >= 0.999, same.mean()
+    assert abs(int(out[4].sum()) - int(acc.sum())) <= max(2, moves * m // 1000)
+    if not philox:
+        np.testing.assert_array_equal(out[4].cpu().numpy()[:1], acc.cpu().numpy()[:1])  # move 0 starts from equal bits
+    for k in (1, 2):
+        np.testing.assert_allclose(out[k].cpu().numpy()[same], st[k].cpu().numpy()[same], rtol=1e-11, atol=1e-10)
+    np.testing.assert_allclose(out[3].cpu().numpy()[same], st[3].cpu().numpy()[same], rtol=0, atol=2e-5)
+    rate = int(acc.sum()) / (moves * m)
+    assert 0.02 < rate < 0.98 or n < 10
+
+
+def test_flow_sweep_is_the_route_of_the_c4_mutation(cuda):
+    """A sampler with built-in densities and an unpadded CouplingFlow proposal mutates through asp_pcn_sweep_flow; the
+    ``flow_sweep=False`` kernel option keeps the per-move chain, and both give the same ensemble."""
+    import torch
+
+    from aspire_b200 import _lib
+    from aspire_b200 import targets as tg
+    from aspire_b200.rng import PhiloxRNG
+    from aspire_b200.samplers import MiniPCNSMC
+    from aspire_b200.samples import SMCSamples
+
+    dims, n = 64, 9000
+    f, _ = _flow(dims, 3, cuda, seed=5)
+    f.std = torch.full((dims,), 2.5, dtype=torch.float64, device=cuda)
+    f._struct = None
+    pg = tg.gmm_problem(dims, device=cuda)
+    x0, lq0 = f.sample_and_log_prob(n)
+    res = []
+    for flag in (True, False):
+        s = MiniPCNSMC(pg["like"], pg["prior"], dims, f, rng=PhiloxRNG(9))
+        s._configure_kernel(dict(n_steps=4, rho=0.3, adapt_rho=False, flow_sweep=flag))
+        from aspire_b200.history import SMCHistory
+
+        s.history = SMCHistory()
+        p0 = SMCSamples(x0, log_likelihood=pg["like"].log_prob(x0), log_prior=pg["prior"].log_prob(x0), log_q=lq0,
+                        beta=0.0, device=cuda)
+        assert s._flow_sweep_ok(p0, 4, False) is flag
+        before = _lib.launch_count
+        out = s.mutate(p0, 0.2)
+        res.append((out, s.history.mcmc_acceptance[-1], _lib.launch_count - before))
+    (a, acc_a, launches_a), (b, acc_b, launches_b) = res
+    assert launches_a < launches_b
+    same = torch.isclose(a.x, b.x, rtol=1e-12, atol=1e-12).all(dim=1)
+    assert float(same.double().mean()) >= 0.999
+    assert acc_a == pytest.approx(acc_b, abs=2e-3)
+    f.check_error()
