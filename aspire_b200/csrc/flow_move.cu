@@ -10,9 +10,13 @@
 //
 // One warpgroup = one tile of 128 particles, thread i owns particle i (its TMEM lane, its fp32 flow state in
 // registers).  The fp64 state does not fit in registers beside the flow state (512 threads per SM: 128 registers
-// each), so the current point and the proposal live in two per-warpgroup scratch tiles in global memory, chunk-major
-// ([D / 4][128][4] doubles: a warp's 32-byte accesses are contiguous) - 75 MB for the whole grid at D = 64, resident
-// in the 126 MB L2: the move loop never goes to HBM.  Accepting a move swaps the two tiles' roles for that particle.
+// each), so the current point lives in a per-warpgroup scratch tile in global memory, chunk-major ([D / 4][128][4]
+// doubles: a warp's 32-byte accesses are contiguous) - 38 MB for the whole grid at D = 64, resident in the L2: the
+// move loop does not go to HBM (a first version kept the proposal in a second tile: 75 MB of scratch thrashed the L2,
+// 17x the algorithmic DRAM traffic - profiles/r2_ncu_flow_move.md).  The proposal is never stored: it is formed chunk
+// by chunk in a rolled loop (densities accumulated on the fly), its standardised image is parked in the thread's own
+// TMEM lane (tcgen05.st into the idle accumulator columns, read back with tcgen05.ld as the flow state), and an
+// accepted proposal is formed again from the same Philox counters and written over the current point.
 // Four warpgroups per SM share one copy of the weights; while one waits on its MMAs the others run their fp64
 // proposal / density phase, so the tensor pipe, the XU (Philox / Box-Muller) and the fp64 pipe overlap.
 #include "density.cuh"
@@ -53,7 +57,15 @@ __device__ __forceinline__ void st_g32(double* p, const double (&v)[4]) {
 }
 
 template <int D>
-__host__ __device__ constexpr size_t move_scratch_doubles_per_wg() { return (size_t)2 * kFlowM * D; }
+__host__ __device__ constexpr size_t move_scratch_doubles_per_wg() { return (size_t)kFlowM * D; }
+
+// four fp32 values -> columns [taddr, taddr + 4) of this thread's TMEM lane
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const float (&v)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(__float_as_uint(v[0])),
+                 "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3]))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // bytes of the per-dimension constants behind the A tiles
 template <int D>
@@ -160,9 +172,26 @@ __global__ void __launch_bounds__(kFlowThreads* kMoveWG, 1) flow_move_kernel(con
     uint64_t* mma_bar = &s_bar[1 + wg];
     const uint32_t lane_taddr = tmem + ((uint32_t)(warp * 32) << 16);
     const uint32_t stream0 = A.prm.stream0;
-    double* buf0 = A.scratch + ((size_t)blockIdx.x * NWG + wg) * move_scratch_doubles_per_wg<D>() + (size_t)tid * 4;
-    double* buf1 = buf0 + (size_t)kFlowM * D;  // element (chunk q, thread): + q * 128 * 4
+    // this thread's slots of the warpgroup's scratch tile: element (chunk q, thread) at q * 128 * 4 doubles
+    double* cur = A.scratch + ((size_t)blockIdx.x * NWG + wg) * move_scratch_doubles_per_wg<D>() + (size_t)tid * 4;
+    constexpr size_t kChunk = (size_t)kFlowM * 4;
     unsigned int n_acc = 0;
+
+    // x' = mu + (ca (x - mu) + rho sigma xi) with fixed roundings: the proposal is formed twice (for the densities,
+    // and again when it is accepted) and both must give the same bits
+    auto propose = [&](double xc, double xi, const double2& rf) -> double {
+        return __dadd_rn(rf.x, __fma_rn(ca, __dsub_rn(xc, rf.x), __dmul_rn(rf.y, xi)));
+    };
+    auto noise4 = [&](int t, int64_t row, uint64_t pidx, int q, double (&xi)[4]) {
+        if constexpr (PHILOX) {
+            float zn[4];
+            philox_normal4(A.keys, stream0 + (uint32_t)t, pidx, (uint32_t)q, zn);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) xi[j] = (double)zn[j];
+        } else {
+            ld_row32(A.prm.d_xi + ((size_t)t * A.n + row) * D + q * 4, xi);
+        }
+    };
 
     const int64_t n_tiles = (A.n + kFlowM - 1) / kFlowM;
     for (int64_t tile = (int64_t)blockIdx.x * NWG + wg; tile < n_tiles; tile += (int64_t)gridDim.x * NWG) {
@@ -172,17 +201,15 @@ __global__ void __launch_bounds__(kFlowThreads* kMoveWG, 1) flow_move_kernel(con
         const int64_t src = A.idx ? A.idx[row] : row;
         const uint64_t pidx = (uint64_t)(A.prm.d_slot ? A.prm.d_slot[row] : A.prm.index0 + row);
         double ll = A.ll[src], lp = A.lp[src], lq = A.lq[src];
-        double* cur = buf0;
-        double* oth = buf1;
         // the ancestor's row -> scratch; r = |(x - mu) / sigma|^2 of the current point is carried along
         double r_cur = 0.0;
         {
             const double* xs = A.x + src * D;
-#pragma unroll
+#pragma unroll 4
             for (int q = 0; q < NQ; ++q) {
                 double v[4];
                 ld_row32(xs + q * 4, v);
-                st_g32(cur + (size_t)q * kFlowM * 4, v);
+                st_g32(cur + q * kChunk, v);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const double z0 = (v[j] - lds2(&s_ref[q * 4 + j]).x) * lds2(&s_ip[q * 4 + j]).x;
@@ -199,31 +226,25 @@ __global__ void __launch_bounds__(kFlowThreads* kMoveWG, 1) flow_move_kernel(con
             } else {
                 log_u = A.prm.d_log_u[(size_t)t * A.n + row];
             }
-            // ---- proposal, prior, likelihood, reference term; the standardised point goes to the flow state ----
-            float z[D];
+            // ---- proposal, prior, likelihood, reference term, chunk by chunk (rolled: small code, few registers);
+            //      the standardised point is parked in this thread's TMEM lane (the accumulator columns are idle) ----
             double r1 = 0.0, sp = 0.0, sl = 0.0;
             double d2[kMoveComp];
 #pragma unroll
             for (int c = 0; c < kMoveComp; ++c) d2[c] = 0.0;
-#pragma unroll
+            double xc[4];
+            ld_g32(cur, xc);
+#pragma unroll 1
             for (int q = 0; q < NQ; ++q) {
-                double xi[4], xc[4], xn[4];
-                if constexpr (PHILOX) {
-                    float zn[4];
-                    philox_normal4(A.keys, stream0 + (uint32_t)t, pidx, (uint32_t)q, zn);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) xi[j] = (double)zn[j];
-                } else {
-                    ld_row32(A.prm.d_xi + ((size_t)t * A.n + row) * D + q * 4, xi);
-                }
-                ld_g32(cur + (size_t)q * kFlowM * 4, xc);
+                double xi[4], nxt[4];
+                ld_g32(cur + (q + 1 < NQ ? q + 1 : q) * kChunk, nxt);  // the next chunk is in flight during this one
+                noise4(t, row, pidx, q, xi);
+                float zf[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int d = q * 4 + j;
                     const double2 rf = lds2(&s_ref[d]), ip = lds2(&s_ip[d]), pf = lds2(&s_pf[d]);
-                    const double y = xc[j] - rf.x;
-                    const double v = rf.x + (ca * y + rf.y * xi[j]);  // oracle/pcn.py::propose (same expression as pcn_eval.cu)
-                    xn[j] = v;
+                    const double v = propose(xc[j], xi[j], rf);
                     const double z1 = (v - rf.x) * ip.x;
                     r1 = fma(z1, z1, r1);
                     const double zp = (v - ip.y) * pf.x;
@@ -242,9 +263,11 @@ __global__ void __launch_bounds__(kFlowThreads* kMoveWG, 1) flow_move_kernel(con
                         const double zl = (v - lk.x) * lk.y;
                         sl = fma(zl, zl, sl);
                     }
-                    z[d] = (float)(v - pf.y) * s_scale[d];
+                    zf[j] = (float)(v - pf.y) * s_scale[d];
                 }
-                st_g32(oth + (size_t)q * kFlowM * 4, xn);
+                tmem_st4(lane_taddr + (uint32_t)(q * 4), zf);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) xc[j] = nxt[j];
             }
             const double lp2 = A.prior.s0 - 0.5 * sp;
             double ll2;
@@ -257,20 +280,22 @@ __global__ void __launch_bounds__(kFlowThreads* kMoveWG, 1) flow_move_kernel(con
                         lse_push(m, acc, fma(-w.x, d2[c], w.y));
                     }
                 }
-                for (int c0 = kMoveComp; c0 < n_comp; c0 += kMoveComp) {  // further components: the proposal is re-read
+                for (int c0 = kMoveComp; c0 < n_comp; c0 += kMoveComp) {  // further components: the proposal is re-formed
 #pragma unroll
                     for (int c = 0; c < kMoveComp; ++c) d2[c] = 0.0;
 #pragma unroll 1
                     for (int q = 0; q < NQ; ++q) {
-                        double xn[4];
-                        ld_g32(oth + (size_t)q * kFlowM * 4, xn);
+                        double xi[4];
+                        ld_g32(cur + q * kChunk, xc);
+                        noise4(t, row, pidx, q, xi);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
+                            const double v = propose(xc[j], xi[j], lds2(&s_ref[q * 4 + j]));
                             const double* mrow = s_gm + (size_t)(q * 4 + j) * ncp + c0;
 #pragma unroll
                             for (int c = 0; c < kMoveComp; c += 2) {
                                 const double2 mm = lds2(reinterpret_cast<const double2*>(mrow + c));
-                                const double e0 = xn[j] - mm.x, e1 = xn[j] - mm.y;
+                                const double e0 = v - mm.x, e1 = v - mm.y;
                                 d2[c] = fma(e0, e0, d2[c]);
                                 d2[c + 1] = fma(e1, e1, d2[c + 1]);
                             }
@@ -289,6 +314,15 @@ __global__ void __launch_bounds__(kFlowThreads* kMoveWG, 1) flow_move_kernel(con
                 ll2 = A.like.s0 - 0.5 * sl;
             }
             // ---- log q(x') : the coupling layers on the tensor cores (same chain as flow_kernel's log_prob) ----
+            float z[D];
+            tmem_wait_st();
+#pragma unroll
+            for (int h = 0; h < D / 16; ++h) {
+                float v16[16];
+                tmem_ld16(lane_taddr + h * 16, v16);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) z[h * 16 + k] = v16[k];
+            }
             float ladj = 0.f;
             for (int layer = 0; layer < A.n_layers; ++layer) {
                 if (layer & 1)
@@ -302,18 +336,24 @@ __global__ void __launch_bounds__(kFlowThreads* kMoveWG, 1) flow_move_kernel(con
 #pragma unroll
             for (int j = 0; j < D; ++j) qq = fmaf(z[j], z[j], qq);
             const double lq2 = (double)(-0.5f * qq - 0.5f * D * kLog2Pi + ladj) + A.log_det0;
-            // ---- accept / reject (asp_pcn_accept_scalar) ----
+            // ---- accept / reject (asp_pcn_accept_scalar); an accepted proposal is formed again, in place ----
             const double t_cur = tempered(ll, lp, lq, beta), t_new = tempered(ll2, lp2, lq2, beta);
             const double dr = 0.5 * r1 - 0.5 * r_cur;
             const bool acc = live && (log_u < (t_new - t_cur) + dr);
             if (acc) {
-                double* tmp = cur;
-                cur = oth;
-                oth = tmp;
                 ll = ll2;
                 lp = lp2;
                 lq = lq2;
                 r_cur = r1;
+#pragma unroll 1
+                for (int q = 0; q < NQ; ++q) {
+                    double xi[4], xo[4];
+                    ld_g32(cur + q * kChunk, xo);
+                    noise4(t, row, pidx, q, xi);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) xo[j] = propose(xo[j], xi[j], lds2(&s_ref[q * 4 + j]));
+                    st_g32(cur + q * kChunk, xo);
+                }
             }
             if (per_move) {
                 const unsigned int votes = __ballot_sync(0xffffffffu, acc);
@@ -324,10 +364,10 @@ __global__ void __launch_bounds__(kFlowThreads* kMoveWG, 1) flow_move_kernel(con
         }
         if (live) {
             double* dst = A.xo + row * D;
-#pragma unroll
+#pragma unroll 4
             for (int q = 0; q < NQ; ++q) {
                 double v[4];
-                ld_g32(cur + (size_t)q * kFlowM * 4, v);
+                ld_g32(cur + q * kChunk, v);
                 st_row32(dst + q * 4, v[0], v[1], v[2], v[3]);
             }
             A.llo[row] = ll;
@@ -397,7 +437,7 @@ int32_t asp_pcn_sweep_flow_supported(int32_t dims, int32_t like_kind, int32_t pr
 }
 
 size_t asp_pcn_sweep_flow_workspace_bytes(int32_t dims) {
-    return (size_t)kNumSMs * kMoveWG * 2 * kFlowM * (size_t)dims * sizeof(double);
+    return (size_t)kNumSMs * kMoveWG * kFlowM * (size_t)dims * sizeof(double);
 }
 
 int asp_pcn_sweep_flow(const double* d_x, const double* d_log_l, const double* d_log_p, const double* d_log_q,

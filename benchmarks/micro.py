@@ -343,6 +343,39 @@ def c4(args):
                       "beta": s.history.beta[-1], "acceptance": s.history.mcmc_acceptance[-1]}))
 
 
+def flowsweep(args):
+    """asp_pcn_sweep_flow alone (C4 shape: 64-D, 8-component mixture, coupling-flow proposal): gather + `moves` pCN
+    moves with log q(x') on tcgen05 inside the move, Philox noise, sorted ancestors."""
+    from aspire_b200.flows import CouplingFlow
+    from aspire_b200.rng import PhiloxRNG
+
+    dev = torch.device("cuda")
+    n, dims, moves = args.n or 10_000_000, args.dims or 64, args.moves
+    prob = tg.gmm_problem(dims, device=dev) if not args.only else tg.gaussian_problem(dims, device=dev)
+    flow = CouplingFlow(dims, device=dev, n_layers=3, rng=PhiloxRNG(3), seed=1)
+    flow.std = torch.full((dims,), 2.5, dtype=torch.float64, device=dev)
+    flow._struct = None
+    x, lq = flow.sample_and_log_prob(n)
+    ll, lp = prob["like"].log_prob(x), prob["prior"].log_prob(x)
+    idx = torch.sort((ops.philox_uniform(6, 0, n, dev) * n).to(torch.int64).clamp_(0, n - 1)).values
+    mu, sigma = ops.moments_to_mu_sigma(ops.weighted_moments(x[: 1 << 20]), dims)
+    prm = ops.make_pcn_params(0.01, 0.3, mu, sigma, moves, seed=99, stream0=3, total_accepts_only=True)
+    out = tuple(torch.empty_like(t) for t in (x, ll, lp, lq))
+    res = {}
+
+    def run():
+        res["o"] = ops.pcn_sweep_flow(x, ll, lp, lq, idx, prob["like"], prob["prior"], flow.struct(), prm, out=out)
+
+    ms = timed(run, args.iters)
+    flow._check_error()
+    half, h = dims // 2, 64
+    flops = 3 * 2 * (half * h + h * h + h * dims) * n * moves
+    print(json.dumps({"bench": "pcn_sweep_flow", "particles": n, "dims": dims, "moves": moves, "ms": ms,
+                      "particle_moves_per_s": n * moves / ms * 1e3, "flow_tflops": flops / ms / 1e9,
+                      "algorithmic_gbs": (16 * dims + 48) * n / ms / 1e6,
+                      "acceptance": float(res["o"][4].sum()) / (n * moves), "lib": os.environ.get("ASPIRE_B200_LIB", "")}))
+
+
 def full(args):
     """A whole ``Aspire.sample_posterior(sampler="smc")`` run (all tempering steps to beta = 1) through the
     drop-in API: 32-D Rosenbrock, N particles, 10 pCN moves per step, adaptive beta at efficiency 0.5."""
@@ -458,7 +491,7 @@ def transform(args):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["flow", "resample", "importance", "sweep", "c4", "full", "transform", "precond"])
+    ap.add_argument("what", choices=["flow", "resample", "importance", "sweep", "c4", "flowsweep", "full", "transform", "precond"])
     ap.add_argument("--n", type=int, default=0)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--moves", type=int, default=10)
@@ -471,4 +504,4 @@ if __name__ == "__main__":
     ap.add_argument("--dump", default="")
     a = ap.parse_args()
     ops.device_check()
-    {"flow": flow, "resample": resample, "importance": importance, "sweep": sweep, "c4": c4, "full": full, "transform": transform, "precond": precond}[a.what](a)
+    {"flow": flow, "resample": resample, "importance": importance, "sweep": sweep, "c4": c4, "flowsweep": flowsweep, "full": full, "transform": transform, "precond": precond}[a.what](a)
