@@ -66,12 +66,20 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, const float (&v)[4]) {
                  : "memory");
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
+    uint32_t r[4];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
 
 // bytes of the per-dimension constants behind the A tiles
 template <int D>
 __host__ __device__ inline size_t move_const_bytes(int like_kind, int n_comp) {
     const int ncp = (n_comp + kMoveComp - 1) / kMoveComp * kMoveComp;
-    size_t b = (size_t)D * 16 * 3;                                               // s_ref, s_ip, s_pf
+    size_t b = (size_t)D * 16 * 3;                                               // s_ref, s_q, s_pr
     b += like_kind == ASP_DENSITY_GMM ? (size_t)D * ncp * 8 + (size_t)ncp * 16  // means [D][ncp], {1/2 is^2, logc}[ncp]
                                       : (size_t)D * 16;                         // Gaussian likelihood {mean, 1/sigma}
     return b;
@@ -82,7 +90,7 @@ __global__ void __launch_bounds__(kFlowThreads* kMoveWG, 1) flow_move_kernel(con
     using S = FlowSizes<D>;
     constexpr int NWG = kMoveWG;
     constexpr int NQ = D / 4;
-    constexpr int kTmemAll = 256;  // 4 warpgroups x 64 columns
+    constexpr int kTmemAll = 512;  // per warpgroup 64 accumulator columns (+ the parked flow input) and 64 for the noise
     constexpr bool kGmm = LIKE == ASP_DENSITY_GMM;
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* s_w = smem;
@@ -90,15 +98,16 @@ __global__ void __launch_bounds__(kFlowThreads* kMoveWG, 1) flow_move_kernel(con
     unsigned char* s_ones = s_bb + A.n_layers * S::kBiasLayer;
     unsigned char* s_a_all = s_ones + S::kOnes;
     double2* s_ref = reinterpret_cast<double2*>(s_a_all + NWG * kFlowM * kFlowH * 2);  // {mu_k, rho sigma_k}
-    double2* s_ip = s_ref + D;                                                         // {1 / sigma_k, prior mean_k}
-    double2* s_pf = s_ip + D;                                                          // {prior 1/sigma_k, flow mean_k}
+    double2* s_q = s_ref + D;   // {a2_k, a1_k}: the Gaussian terms of the accept test folded into one quadratic
+    double2* s_pf = s_q + D;    // {prior mean_k, prior 1/sigma_k}: the final log prior
     const int n_comp = kGmm ? A.like.n_comp : 0;
     const int ncp = (n_comp + kMoveComp - 1) / kMoveComp * kMoveComp;
     double* s_gm = reinterpret_cast<double*>(s_pf + D);                                // mixture means [D][ncp]
-    double2* s_gw = reinterpret_cast<double2*>(s_gm + (size_t)D * ncp);                // {1/2 is^2, logc}[ncp]
+    double2* s_gw = reinterpret_cast<double2*>(s_gm + (size_t)D * ncp);                // {is^2, logc - 1/2 is^2 |m|^2}[ncp]
     double2* s_lk = reinterpret_cast<double2*>(s_pf + D);                              // Gaussian likelihood {mean, 1/sigma}
     unsigned char* tail = reinterpret_cast<unsigned char*>(s_pf + D) + (move_const_bytes<D>(LIKE, n_comp) - (size_t)D * 48);
-    float* s_scale = reinterpret_cast<float*>(tail);                                    // flow 1 / std (fp32, as flow_kernel)
+    double* s_fmean = reinterpret_cast<double*>(tail);                                  // flow mean
+    float* s_scale = reinterpret_cast<float*>(s_fmean + D);                             // flow 1 / std (fp32, as flow_kernel)
     unsigned int* s_acc = reinterpret_cast<unsigned int*>(s_scale + D);
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_acc + kMoveMaxMoves);
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 1 + NWG);
@@ -140,11 +149,27 @@ __global__ void __launch_bounds__(kFlowThreads* kMoveWG, 1) flow_move_kernel(con
     }
     for (int j = threadIdx.x; j < D; j += blockDim.x) {
         const double mu = A.prm.d_mu[j], sg = A.prm.d_sigma[j];
+        // T(x) = (1-beta) log q + beta (logL + logP) + r,  r = 1/2 |(x - mu)/sigma|^2: the Gaussian prior, a Gaussian
+        // likelihood and r are per-dimension quadratics in y = x - mu and fold into a2 y^2 + a1 y (constants cancel
+        // in the accept difference) - as in the particle-per-thread sweep (pcn_sweep_tpp.cuh)
+        const double isr = 1.0 / sg;
+        double c2 = 0.5 * isr * isr, c1 = 0.0;
+        {
+            const double is = A.prior.p1[j], w = -0.5 * beta * is * is;
+            c2 += w;
+            c1 += 2.0 * w * (mu - A.prior.p0[j]);
+        }
+        if constexpr (!kGmm) {
+            const double is = A.like.p1[j], w = -0.5 * beta * is * is;
+            c2 += w;
+            c1 += 2.0 * w * (mu - A.like.p0[j]);
+            s_lk[j] = make_double2(A.like.p0[j], A.like.p1[j]);
+        }
         s_ref[j] = make_double2(mu, rho * sg);
-        s_ip[j] = make_double2(1.0 / sg, A.prior.p0[j]);
-        s_pf[j] = make_double2(A.prior.p1[j], A.mean[j]);
+        s_q[j] = make_double2(c2, c1);
+        s_pf[j] = make_double2(A.prior.p0[j], A.prior.p1[j]);
+        s_fmean[j] = A.mean[j];
         s_scale[j] = (float)A.inv_std[j];
-        if constexpr (!kGmm) s_lk[j] = make_double2(A.like.p0[j], A.like.p1[j]);
     }
     if constexpr (kGmm) {
         for (int e = threadIdx.x; e < D * ncp; e += blockDim.x) {
@@ -153,7 +178,13 @@ __global__ void __launch_bounds__(kFlowThreads* kMoveWG, 1) flow_move_kernel(con
         }
         for (int c = threadIdx.x; c < ncp; c += blockDim.x) {
             const double is = c < n_comp ? A.like.p1[c] : 0.0;
-            s_gw[c] = make_double2(0.5 * is * is, c < n_comp ? A.like.p2[c] : ninf);
+            // log w_c N(v; m_c, s_c^2) = logc - 1/2 is^2 |v - m_c|^2 = (logc - 1/2 is^2 |m_c|^2) + is^2 (v.m_c - 1/2 |v|^2)
+            double mm = 0.0;
+            for (int k = 0; k < D; ++k) {
+                const double mk = c < n_comp ? A.like.p0[(size_t)c * D + k] : 0.0;
+                mm = fma(mk, mk, mm);
+            }
+            s_gw[c] = make_double2(is * is, c < n_comp ? fma(-0.5 * is * is, mm, A.like.p2[c]) : ninf);
         }
     }
     fence_proxy_async_smem();
@@ -171,6 +202,7 @@ __global__ void __launch_bounds__(kFlowThreads* kMoveWG, 1) flow_move_kernel(con
     uint32_t phase = 0;
     uint64_t* mma_bar = &s_bar[1 + wg];
     const uint32_t lane_taddr = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t xi_taddr = lane_taddr + (uint32_t)(NWG * S::kTmemCols);  // this thread's 64 noise columns
     const uint32_t stream0 = A.prm.stream0;
     // this thread's slots of the warpgroup's scratch tile: element (chunk q, thread) at q * 128 * 4 doubles
     double* cur = A.scratch + ((size_t)blockIdx.x * NWG + wg) * move_scratch_doubles_per_wg<D>() + (size_t)tid * 4;
@@ -182,10 +214,23 @@ __global__ void __launch_bounds__(kFlowThreads* kMoveWG, 1) flow_move_kernel(con
     auto propose = [&](double xc, double xi, const double2& rf) -> double {
         return __dadd_rn(rf.x, __fma_rn(ca, __dsub_rn(xc, rf.x), __dmul_rn(rf.y, xi)));
     };
-    auto noise4 = [&](int t, int64_t row, uint64_t pidx, int q, double (&xi)[4]) {
+    // the normals of chunk q: drawn once per move (Philox + Box-Muller) and parked in TMEM, recalled from there when
+    // the proposal is formed again (further mixture components, accepted move); supplied noise is simply re-read
+    auto noise_draw = [&](int t, int64_t row, uint64_t pidx, int q, double (&xi)[4]) {
         if constexpr (PHILOX) {
             float zn[4];
             philox_normal4(A.keys, stream0 + (uint32_t)t, pidx, (uint32_t)q, zn);
+            tmem_st4(xi_taddr + (uint32_t)(q * 4), zn);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) xi[j] = (double)zn[j];
+        } else {
+            ld_row32(A.prm.d_xi + ((size_t)t * A.n + row) * D + q * 4, xi);
+        }
+    };
+    auto noise_recall = [&](int t, int64_t row, int q, double (&xi)[4]) {  // warp-uniform call sites only
+        if constexpr (PHILOX) {
+            float zn[4];
+            tmem_ld4(xi_taddr + (uint32_t)(q * 4), zn);
 #pragma unroll
             for (int j = 0; j < 4; ++j) xi[j] = (double)zn[j];
         } else {
@@ -201,8 +246,8 @@ __global__ void __launch_bounds__(kFlowThreads* kMoveWG, 1) flow_move_kernel(con
         const int64_t src = A.idx ? A.idx[row] : row;
         const uint64_t pidx = (uint64_t)(A.prm.d_slot ? A.prm.d_slot[row] : A.prm.index0 + row);
         double ll = A.ll[src], lp = A.lp[src], lq = A.lq[src];
-        // the ancestor's row -> scratch; r = |(x - mu) / sigma|^2 of the current point is carried along
-        double r_cur = 0.0;
+        // the ancestor's row -> scratch, with the folded quadratic of the current point
+        double q_cur = 0.0;
         {
             const double* xs = A.x + src * D;
 #pragma unroll 4
@@ -212,11 +257,17 @@ __global__ void __launch_bounds__(kFlowThreads* kMoveWG, 1) flow_move_kernel(con
                 st_g32(cur + q * kChunk, v);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const double z0 = (v[j] - lds2(&s_ref[q * 4 + j]).x) * lds2(&s_ip[q * 4 + j]).x;
-                    r_cur = fma(z0, z0, r_cur);
+                    const double y = v[j] - lds2(&s_ref[q * 4 + j]).x;
+                    const double2 e = lds2(&s_q[q * 4 + j]);
+                    q_cur = fma(y, fma(e.x, y, e.y), q_cur);
                 }
             }
         }
+        // current value of the target up to the constants that cancel; NaN -> -inf (smc/base.py:518)
+        double t_cur = fma(1.0 - beta, lq, q_cur);
+        if constexpr (kGmm) t_cur = fma(beta, ll, t_cur);
+        if (t_cur != t_cur) t_cur = ninf;
+        bool moved = false;
         uint4 aw = make_uint4(0, 0, 0, 0);
         for (int t = 0; t < n_moves; ++t) {
             double log_u;
@@ -228,58 +279,52 @@ __global__ void __launch_bounds__(kFlowThreads* kMoveWG, 1) flow_move_kernel(con
             }
             // ---- proposal, prior, likelihood, reference term, chunk by chunk (rolled: small code, few registers);
             //      the standardised point is parked in this thread's TMEM lane (the accumulator columns are idle) ----
-            double r1 = 0.0, sp = 0.0, sl = 0.0;
-            double d2[kMoveComp];
+            double qn = 0.0, vv = 0.0;
+            double d2[kMoveComp];  // mixture: v . m_c
 #pragma unroll
             for (int c = 0; c < kMoveComp; ++c) d2[c] = 0.0;
             double xc[4];
             ld_g32(cur, xc);
-#pragma unroll 1
+#pragma unroll 2
             for (int q = 0; q < NQ; ++q) {
                 double xi[4], nxt[4];
                 ld_g32(cur + (q + 1 < NQ ? q + 1 : q) * kChunk, nxt);  // the next chunk is in flight during this one
-                noise4(t, row, pidx, q, xi);
+                noise_draw(t, row, pidx, q, xi);
                 float zf[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int d = q * 4 + j;
-                    const double2 rf = lds2(&s_ref[d]), ip = lds2(&s_ip[d]), pf = lds2(&s_pf[d]);
+                    const double2 rf = lds2(&s_ref[d]), e = lds2(&s_q[d]);
                     const double v = propose(xc[j], xi[j], rf);
-                    const double z1 = (v - rf.x) * ip.x;
-                    r1 = fma(z1, z1, r1);
-                    const double zp = (v - ip.y) * pf.x;
-                    sp = fma(zp, zp, sp);
+                    const double y = v - rf.x;
+                    qn = fma(y, fma(e.x, y, e.y), qn);
                     if constexpr (kGmm) {
                         const double* mrow = s_gm + (size_t)d * ncp;
+                        vv = fma(v, v, vv);
 #pragma unroll
                         for (int c = 0; c < kMoveComp; c += 2) {
                             const double2 m = lds2(reinterpret_cast<const double2*>(mrow + c));
-                            const double e0 = v - m.x, e1 = v - m.y;
-                            d2[c] = fma(e0, e0, d2[c]);
-                            d2[c + 1] = fma(e1, e1, d2[c + 1]);
+                            d2[c] = fma(v, m.x, d2[c]);
+                            d2[c + 1] = fma(v, m.y, d2[c + 1]);
                         }
-                    } else {
-                        const double2 lk = lds2(&s_lk[d]);
-                        const double zl = (v - lk.x) * lk.y;
-                        sl = fma(zl, zl, sl);
                     }
-                    zf[j] = (float)(v - pf.y) * s_scale[d];
+                    zf[j] = (float)(v - s_fmean[d]) * s_scale[d];
                 }
                 tmem_st4(lane_taddr + (uint32_t)(q * 4), zf);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) xc[j] = nxt[j];
             }
-            const double lp2 = A.prior.s0 - 0.5 * sp;
-            double ll2;
+            double ll2 = 0.0;
             if constexpr (kGmm) {
                 double m = ninf, acc = 0.0;
 #pragma unroll
                 for (int c = 0; c < kMoveComp; ++c) {
                     if (c < n_comp) {
                         const double2 w = lds2(&s_gw[c]);
-                        lse_push(m, acc, fma(-w.x, d2[c], w.y));
+                        lse_push(m, acc, fma(w.x, fma(-0.5, vv, d2[c]), w.y));
                     }
                 }
+                if (n_comp > kMoveComp) tmem_wait_st();
                 for (int c0 = kMoveComp; c0 < n_comp; c0 += kMoveComp) {  // further components: the proposal is re-formed
 #pragma unroll
                     for (int c = 0; c < kMoveComp; ++c) d2[c] = 0.0;
@@ -287,7 +332,7 @@ __global__ void __launch_bounds__(kFlowThreads* kMoveWG, 1) flow_move_kernel(con
                     for (int q = 0; q < NQ; ++q) {
                         double xi[4];
                         ld_g32(cur + q * kChunk, xc);
-                        noise4(t, row, pidx, q, xi);
+                        noise_recall(t, row, q, xi);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const double v = propose(xc[j], xi[j], lds2(&s_ref[q * 4 + j]));
@@ -295,9 +340,8 @@ __global__ void __launch_bounds__(kFlowThreads* kMoveWG, 1) flow_move_kernel(con
 #pragma unroll
                             for (int c = 0; c < kMoveComp; c += 2) {
                                 const double2 mm = lds2(reinterpret_cast<const double2*>(mrow + c));
-                                const double e0 = v - mm.x, e1 = v - mm.y;
-                                d2[c] = fma(e0, e0, d2[c]);
-                                d2[c + 1] = fma(e1, e1, d2[c + 1]);
+                                d2[c] = fma(v, mm.x, d2[c]);
+                                d2[c + 1] = fma(v, mm.y, d2[c + 1]);
                             }
                         }
                     }
@@ -305,13 +349,11 @@ __global__ void __launch_bounds__(kFlowThreads* kMoveWG, 1) flow_move_kernel(con
                     for (int c = 0; c < kMoveComp; ++c) {
                         if (c0 + c < n_comp) {
                             const double2 w = lds2(&s_gw[c0 + c]);
-                            lse_push(m, acc, fma(-w.x, d2[c], w.y));
+                            lse_push(m, acc, fma(w.x, fma(-0.5, vv, d2[c]), w.y));
                         }
                     }
                 }
                 ll2 = m + log(acc);
-            } else {
-                ll2 = A.like.s0 - 0.5 * sl;
             }
             // ---- log q(x') : the coupling layers on the tensor cores (same chain as flow_kernel's log_prob) ----
             float z[D];
@@ -337,22 +379,36 @@ __global__ void __launch_bounds__(kFlowThreads* kMoveWG, 1) flow_move_kernel(con
             for (int j = 0; j < D; ++j) qq = fmaf(z[j], z[j], qq);
             const double lq2 = (double)(-0.5f * qq - 0.5f * D * kLog2Pi + ladj) + A.log_det0;
             // ---- accept / reject (asp_pcn_accept_scalar); an accepted proposal is formed again, in place ----
-            const double t_cur = tempered(ll, lp, lq, beta), t_new = tempered(ll2, lp2, lq2, beta);
-            const double dr = 0.5 * r1 - 0.5 * r_cur;
-            const bool acc = live && (log_u < (t_new - t_cur) + dr);
+            double t_new = fma(1.0 - beta, lq2, qn);
+            if constexpr (kGmm) t_new = fma(beta, ll2, t_new);
+            const bool acc = live && (log_u < t_new - t_cur);  // NaN -> reject, like the reference's NaN -> -inf
             if (acc) {
-                ll = ll2;
-                lp = lp2;
+                if constexpr (kGmm) ll = ll2;
                 lq = lq2;
-                r_cur = r1;
+                t_cur = t_new;
+                moved = true;
+            }
+            if (__any_sync(0xffffffffu, acc)) {  // warp-uniform: the TMEM reads are .sync.aligned
 #pragma unroll 1
-                for (int q = 0; q < NQ; ++q) {
-                    double xi[4], xo[4];
-                    ld_g32(cur + q * kChunk, xo);
-                    noise4(t, row, pidx, q, xi);
+                for (int g = 0; g < D / 16; ++g) {  // 16 dimensions at a time: four scratch chunks in flight
+                    double xo[4][4], xi[4][4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) xo[j] = propose(xo[j], xi[j], lds2(&s_ref[q * 4 + j]));
-                    st_g32(cur + q * kChunk, xo);
+                    for (int c = 0; c < 4; ++c) ld_g32(cur + (g * 4 + c) * kChunk, xo[c]);
+                    if constexpr (PHILOX) {
+                        float zn[16];
+                        tmem_ld16(xi_taddr + (uint32_t)(g * 16), zn);
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) xi[k >> 2][k & 3] = (double)zn[k];
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) ld_row32(A.prm.d_xi + ((size_t)t * A.n + row) * D + g * 16 + c * 4, xi[c]);
+                    }
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) xo[c][j] = propose(xo[c][j], xi[c][j], lds2(&s_ref[g * 16 + c * 4 + j]));
+                        if (acc) st_g32(cur + (g * 4 + c) * kChunk, xo[c]);
+                    }
                 }
             }
             if (per_move) {
@@ -362,17 +418,35 @@ __global__ void __launch_bounds__(kFlowThreads* kMoveWG, 1) flow_move_kernel(con
                 n_acc += acc ? 1u : 0u;
             }
         }
-        if (live) {
+        {  // final point and its logs (a particle that never moved keeps its input logs bit for bit)
             double* dst = A.xo + row * D;
+            double sp = 0.0, sl = 0.0;
 #pragma unroll 4
             for (int q = 0; q < NQ; ++q) {
                 double v[4];
                 ld_g32(cur + q * kChunk, v);
-                st_row32(dst + q * 4, v[0], v[1], v[2], v[3]);
+                if (live) st_row32(dst + q * 4, v[0], v[1], v[2], v[3]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const double2 pf = lds2(&s_pf[q * 4 + j]);
+                    const double zp = (v[j] - pf.x) * pf.y;
+                    sp = fma(zp, zp, sp);
+                    if constexpr (!kGmm) {
+                        const double2 lk = lds2(&s_lk[q * 4 + j]);
+                        const double zl = (v[j] - lk.x) * lk.y;
+                        sl = fma(zl, zl, sl);
+                    }
+                }
             }
-            A.llo[row] = ll;
-            A.lpo[row] = lp;
-            A.lqo[row] = lq;
+            if (moved) {
+                lp = A.prior.s0 - 0.5 * sp;
+                if constexpr (!kGmm) ll = A.like.s0 - 0.5 * sl;
+            }
+            if (live) {
+                A.llo[row] = ll;
+                A.lpo[row] = lp;
+                A.lqo[row] = lq;
+            }
         }
     }
     if (!per_move) {
@@ -392,7 +466,7 @@ template <int D>
 static size_t move_smem_bytes(int n_layers, int like_kind, int n_comp) {
     using S = FlowSizes<D>;
     return (size_t)n_layers * (S::kLayer + S::kBiasLayer) + S::kOnes + (size_t)kMoveWG * kFlowM * kFlowH * 2 +
-           move_const_bytes<D>(like_kind, n_comp) + D * 4 + kMoveMaxMoves * 4 + (1 + kMoveWG) * 8 + 16 + 128;
+           move_const_bytes<D>(like_kind, n_comp) + D * 12 + kMoveMaxMoves * 4 + (1 + kMoveWG) * 8 + 16 + 128;
 }
 
 static int move_grid(int64_t n) {
