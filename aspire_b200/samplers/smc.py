@@ -44,6 +44,7 @@ class BetaScheduleError(RuntimeError):
 
 class SMCSampler(Sampler):
     default_beta_tolerance = DEFAULT_BETA_TOLERANCE
+    default_step_fn = "pcn"  # the base class runs plain pCN (the north-star kernel); MiniPCNSMC: the reference's "tpcn"
 
     def __init__(
         self,
@@ -375,7 +376,7 @@ class SMCSampler(Sampler):
         kw = dict(sampler_kwargs or {})
         kw.setdefault("n_steps", 5 * self.dims)
         kw.setdefault("target_acceptance_rate", 0.234)
-        kw.setdefault("step_fn", "pcn")
+        kw.setdefault("step_fn", self.default_step_fn)
         kw.setdefault("verbose", False)
         kw.setdefault("rho", 0.5)
         kw.setdefault("adapt_rho", True)
@@ -627,3 +628,4 @@ class MiniPCNSMC(SMCSampler):
     ``beta_tolerance`` default is 1e-6 (``smc/minipcn.py:40``), not the base class's 1e-8."""
 
     default_beta_tolerance = 1e-6
+    default_step_fn = "tpcn"  # smc/minipcn.py:48; built-in densities run it in the fused sweep (params->nu > 0)

@@ -132,7 +132,7 @@ def test_c4_tempering_step_with_the_flow_as_proposal(cuda):
     np.testing.assert_allclose(pg["like"].log_prob(x_d).cpu().numpy(), ll, rtol=1e-12, atol=1e-10)
 
     s = MiniPCNSMC(pg["like"], pg["prior"], dims, f, rng=np.random.default_rng(seed))
-    s._configure_kernel(dict(n_steps=moves, rho=rho, adapt_rho=False))
+    s._configure_kernel(dict(n_steps=moves, rho=rho, adapt_rho=False, step_fn="pcn"))
     s.target_efficiency, s.target_efficiency_rate, s.adaptive, s.adaptive_min_beta_step = 0.5, 1.0, True, False
     s.max_beta_step, s.resampling = 1.0, "multinomial"
     from aspire_b200.history import SMCHistory
@@ -422,7 +422,7 @@ def test_flow_sweep_is_the_route_of_the_c4_mutation(cuda):
     res = []
     for flag in (True, False):
         s = MiniPCNSMC(pg["like"], pg["prior"], dims, f, rng=PhiloxRNG(9))
-        s._configure_kernel(dict(n_steps=4, rho=0.3, adapt_rho=False, flow_sweep=flag))
+        s._configure_kernel(dict(n_steps=4, rho=0.3, adapt_rho=False, flow_sweep=flag, step_fn="pcn"))
         from aspire_b200.history import SMCHistory
 
         s.history = SMCHistory()
