@@ -209,6 +209,8 @@ SIGNATURES = {
     "asp_flow_weights_bytes": (C.c_size_t, [_I32, _I32]),
     "asp_flow_logprob_bf16": (C.c_int, [C.POINTER(Flow), _P, _I64, _P, _P, _P]),
     "asp_flow_sample_bf16": (C.c_int, [C.POINTER(Flow), _P, _I64, _P, _P, _P]),
+    "asp_student_t_workspace_bytes": (C.c_size_t, [_I32]),
+    "asp_student_t_fit": (C.c_int, [_P, _I32, _P, _I64, _I64, _I32, _D, _D, _P, _P, _P]),
     "asp_pcn_sweep_flow_supported": (_I32, [_I32, _I32, _I32]),
     "asp_pcn_sweep_flow_workspace_bytes": (C.c_size_t, [_I32]),
     "asp_pcn_sweep_flow": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, C.POINTER(Density), C.POINTER(Density),
@@ -257,7 +259,7 @@ KERNELS_PER_CALL = {"asp_importance_weights": 3, "asp_cdf_exact": 6, "asp_cdf_ti
                     "asp_search_multinomial_guided": 4, "asp_select_uniforms": 3, "asp_search_systematic": 3,
                     "asp_search_systematic_workspace_bytes": 0, "asp_pcn_propose_eval_supported": 0, "asp_beta_search_max_passes3": 0,
                     "asp_sorted_tiles": 0, "asp_search_sorted": 2, "asp_pcn_sweep_tpcn_supported": 0, "asp_pcn_sweep_flow_supported": 0,
-                    "asp_pcn_sweep_flow_workspace_bytes": 0, "asp_flow_fit_params": 0, "asp_flow_fit_workspace_floats": 0,
+                    "asp_pcn_sweep_flow_workspace_bytes": 0, "asp_student_t_workspace_bytes": 0, "asp_student_t_fit": 30, "asp_flow_fit_params": 0, "asp_flow_fit_workspace_floats": 0,
                     "asp_beta_search_root": 6, "asp_beta_search_run": 8, "asp_beta_search_scratch_words": 0}
 launch_count = 0
 

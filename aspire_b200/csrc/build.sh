@@ -7,7 +7,7 @@ mkdir -p "${OUT}"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC
        -Xcompiler -fvisibility=hidden --expt-relaxed-constexpr)
-SRCS=(core.cu reweight.cu scan_exact.cu search_gather.cu sorted_resample.cu pcn.cu pcn_sweep_gaussian.cu pcn_sweep_rosenbrock.cu pcn_sweep_gmm.cu pcn_sweep_uniform.cu pcn_tpp_gaussian.cu pcn_tpp_rosenbrock.cu pcn_tpp_gmm.cu pcn_tpp_uniform.cu pcn_tpp_t_gaussian.cu pcn_tpp_t_rosenbrock.cu pcn_tpp_t_gmm.cu pcn_tpp_t_uniform.cu pcn_eval.cu rng.cu select.cu flow.cu flow_move.cu flow_fit.cu transform.cu)
+SRCS=(core.cu reweight.cu scan_exact.cu search_gather.cu sorted_resample.cu pcn.cu pcn_sweep_gaussian.cu pcn_sweep_rosenbrock.cu pcn_sweep_gmm.cu pcn_sweep_uniform.cu pcn_tpp_gaussian.cu pcn_tpp_rosenbrock.cu pcn_tpp_gmm.cu pcn_tpp_uniform.cu pcn_tpp_t_gaussian.cu pcn_tpp_t_rosenbrock.cu pcn_tpp_t_gmm.cu pcn_tpp_t_uniform.cu pcn_eval.cu student_t.cu rng.cu select.cu flow.cu flow_move.cu flow_fit.cu transform.cu)
 OBJS=()
 pids=()
 for s in "${SRCS[@]}"; do

@@ -513,6 +513,28 @@ def pcn_sweep_tpcn_supported(dims: int) -> bool:
     return bool(_lib.load().asp_pcn_sweep_tpcn_supported(int(dims)))
 
 
+def student_t_fit(x, mu0, sigma0, idx=None, stride: int = 1, m: int | None = None, n_iter: int = 30, nu0: float = 10.0,
+                  nu_min: float = 1.0, nu_max: float = 1e6):
+    """EM fit of t_nu(mu, diag sigma^2) (tpCN reference measure; spec ``oracle/pcn.py::fit_student_t_diag``) to the
+    rows ``x[idx[i * stride]]`` (``idx`` None: ``x[i * stride]``), ``i < m``, on the device.  -> (mu, sigma, nu),
+    ``nu`` read back to the host (the one device -> host read of the fit)."""
+    x = _f64(x, "x")
+    dims = x.shape[1]
+    idx = None if idx is None else _i64(idx, "idx")
+    n_rows = x.shape[0] if idx is None else idx.numel()
+    if m is None:
+        m = (n_rows + stride - 1) // stride
+    if m < 1 or (m - 1) * stride >= n_rows:
+        raise AspireB200Error("student_t_fit: row selection out of range")
+    state = torch.cat([_f64(mu0, "mu0").reshape(-1), _f64(sigma0, "sigma0").reshape(-1),
+                       torch.tensor([float(nu0)], dtype=torch.float64, device=x.device)]).contiguous()
+    lib = _lib.load()
+    ws = _sized_ws("student_t", lib.asp_student_t_workspace_bytes(dims), x.device)
+    check(lib.asp_student_t_fit(x.data_ptr(), dims, _ptr(idx), int(stride), int(m), int(n_iter), float(nu_min),
+                                float(nu_max), state.data_ptr(), ws.data_ptr(), _stream()), "asp_student_t_fit")
+    return state[:dims].contiguous(), state[dims:2 * dims].contiguous(), float(state[2 * dims])
+
+
 def pcn_sweep_flow_supported(dims: int, like, prior) -> bool:
     return bool(_lib.load().asp_pcn_sweep_flow_supported(int(dims), int(like.kind), int(prior.kind)))
 

@@ -446,7 +446,7 @@ class SMCSampler(Sampler):
         tpcn = getattr(self, "step_fn", "pcn") == "tpcn"
         nu = 0.0
         if tpcn:
-            mu, sigma, nu = fit_student_t_diag(z[:min(m_use, 1 << 20)], mu, sigma)
+            mu, sigma, nu = fit_student_t_diag(z[:min(m_use, 1 << 20)].contiguous(), mu, sigma)
             self.history.__dict__.setdefault("tpcn_nu", []).append(nu)
         if mark:
             mark("moments")
@@ -508,8 +508,7 @@ class SMCSampler(Sampler):
         nu = 0.0
         if tpcn:  # Student-t reference measure t_nu(mu, diag sigma^2) fitted to (a sample of) the ensemble
             t_stride = max(n // min(m_use, 1 << 20), 1)
-            rows = particles.x[::t_stride] if idx is None else particles.x[idx[::t_stride]]
-            mu, sigma, nu = fit_student_t_diag(rows, mu, sigma)
+            mu, sigma, nu = fit_student_t_diag(particles.x, mu, sigma, idx=idx, stride=t_stride)
             self.history.__dict__.setdefault("tpcn_nu", []).append(nu)
         if mark:
             mark("moments")
@@ -588,39 +587,14 @@ class SMCSampler(Sampler):
         return out
 
 
-def fit_student_t_diag(x: torch.Tensor, mu0: torch.Tensor, sigma0: torch.Tensor, n_iter: int = 30, nu0: float = 10.0,
-                       nu_min: float = 1.0, nu_max: float = 1e6):
-    """EM fit of t_nu(mu, diag sigma^2) on the device rows ``x`` (spec: ``oracle/pcn.py::fit_student_t_diag``);
-    the reductions run on the GPU, the scalar nu equation is solved on the host.  -> (mu, sigma, nu)"""
-    from scipy.special import digamma
-
-    n, d = x.shape
-    mu, sigma, nu = mu0.clone(), sigma0.clone(), float(nu0)
-    for _ in range(n_iter):
-        z = (x - mu) / sigma
-        r2 = (z * z).sum(dim=1)
-        w = (nu + d) / (nu + r2)
-        mu = (w[:, None] * x).sum(dim=0) / w.sum()
-        sigma = torch.sqrt((w[:, None] * (x - mu) ** 2).sum(dim=0) / n)
-        const = 1.0 + float((torch.log(w) - w).mean()) + float(digamma(0.5 * (nu + d))) - math.log(0.5 * (nu + d))
-
-        def f(v):
-            return -float(digamma(0.5 * v)) + math.log(0.5 * v) + const
-
-        lo, hi = nu_min, nu_max
-        if f(hi) > 0:
-            nu = hi
-        elif f(lo) < 0:
-            nu = lo
-        else:
-            for _ in range(60):
-                mid = math.sqrt(lo * hi)
-                if f(mid) > 0:
-                    lo = mid
-                else:
-                    hi = mid
-            nu = math.sqrt(lo * hi)
-    return mu.contiguous(), torch.clamp_min(sigma, 1e-150).contiguous(), float(nu)
+def fit_student_t_diag(x: torch.Tensor, mu0: torch.Tensor, sigma0: torch.Tensor, idx=None, stride: int = 1,
+                       n_iter: int = 30, nu0: float = 10.0, nu_min: float = 1.0, nu_max: float = 1e6):
+    """EM fit of t_nu(mu, diag sigma^2) to the rows ``x[idx[::stride]]`` (``idx`` None: ``x[::stride]``) on the
+    device (``asp_student_t_fit``, csrc/student_t.cu: one kernel per EM iteration, the nu equation solved in-kernel;
+    spec ``oracle/pcn.py::fit_student_t_diag``).  -> (mu, sigma, nu)"""
+    mu, sigma, nu = ops.student_t_fit(x, mu0, sigma0, idx=idx, stride=stride, n_iter=n_iter, nu0=nu0, nu_min=nu_min,
+                                      nu_max=nu_max)
+    return mu, torch.clamp_min(sigma, 1e-150).contiguous(), nu
 
 
 class MiniPCNSMC(SMCSampler):

@@ -355,6 +355,15 @@ int asp_pcn_accept(double* d_x, double* d_log_l, double* d_log_p, double* d_log_
                    int32_t dims, const asp_pcn_params_t* params, int32_t move, unsigned long long* d_accepts,
                    void* stream);
 
+/* tpCN reference measure: EM fit (Liu & Rubin 1995) of t_nu(mu, diag sigma^2) to m rows of d_x - row i is
+ * d_x[(d_idx ? d_idx[i * stride] : i * stride)] - entirely on the device: n_iter kernels, no host round trip.
+ * d_state: [2 dims + 1] doubles = mu | sigma | nu, holding the starting point on entry (the ensemble's mean / std and
+ * nu0) and the fit on return.  Spec: oracle/pcn.py::fit_student_t_diag (minipcn absent: parity unpinned).
+ * ws: asp_student_t_workspace_bytes(dims) bytes, zero-initialised once. */
+size_t asp_student_t_workspace_bytes(int32_t dims);
+int asp_student_t_fit(const double* d_x, int32_t dims, const int64_t* d_idx, int64_t stride, int64_t m, int32_t n_iter,
+                      double nu_min, double nu_max, double* d_state, void* ws, void* stream);
+
 /* Semi-fused move for a proposal density that is not a built-in (e.g. a flow evaluated by
  * asp_flow_logprob_bf16): asp_pcn_propose_eval proposes x' for move `move` and evaluates the built-in
  * prior / likelihood at x' plus the reference-measure term d_dr = r(x') - r(x) in ONE pass (x read once,

@@ -229,6 +229,42 @@ class Doubles:
         return False
 
     @staticmethod
+    def student_t_fit(x, mu0, sigma0, idx=None, stride=1, m=None, n_iter=30, nu0=10.0, nu_min=1.0, nu_max=1e6):
+        """oracle/pcn.py::fit_student_t_diag on the selected rows, from the given starting point."""
+        from scipy.special import digamma
+
+        rows = x[::stride] if idx is None else x[idx[::stride]]
+        if m is not None:
+            rows = rows[:m]
+        n, d = rows.shape
+        mu, sigma, nu = mu0.clone(), sigma0.clone(), float(nu0)
+        for _ in range(n_iter):
+            z = (rows - mu) / sigma
+            r2 = (z * z).sum(dim=1)
+            w = (nu + d) / (nu + r2)
+            mu = (w[:, None] * rows).sum(dim=0) / w.sum()
+            sigma = torch.sqrt((w[:, None] * (rows - mu) ** 2).sum(dim=0) / n)
+            const = 1.0 + float((torch.log(w) - w).mean()) + float(digamma(0.5 * (nu + d))) - math.log(0.5 * (nu + d))
+
+            def f(v):
+                return -float(digamma(0.5 * v)) + math.log(0.5 * v) + const
+
+            lo, hi = nu_min, nu_max
+            if f(hi) > 0:
+                nu = hi
+            elif f(lo) < 0:
+                nu = lo
+            else:
+                for _ in range(60):
+                    mid = math.sqrt(lo * hi)
+                    if f(mid) > 0:
+                        lo = mid
+                    else:
+                        hi = mid
+                nu = math.sqrt(lo * hi)
+        return mu.contiguous(), sigma.contiguous(), float(nu)
+
+    @staticmethod
     def pcn_sweep_flow_supported(dims, like, prior):
         return False
 
@@ -258,7 +294,7 @@ class Doubles:
 NAMES = ["_f64", "_i64", "_stream", "device_check", "reweight", "ess_sums", "beta_search", "smc_weights",
          "importance_weights", "cdf_exact", "search_multinomial", "search_multinomial_sorted", "search_systematic", "gather_rows",
          "weighted_moments", "moments_to_mu_sigma", "philox_uniform", "philox_normal", "pcg64_uniform", "make_pcn_params",
-         "tpcn_scales", "pcn_propose", "pcn_accept", "pcn_sweep", "pcn_propose_eval_supported", "pcn_sweep_tpcn_supported", "pcn_sweep_flow_supported",
+         "tpcn_scales", "pcn_propose", "pcn_accept", "pcn_sweep", "pcn_propose_eval_supported", "pcn_sweep_tpcn_supported", "pcn_sweep_flow_supported", "student_t_fit",
          "logdensity",
          "transform_apply"]
 

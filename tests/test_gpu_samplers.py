@@ -415,6 +415,16 @@ def test_smc_with_tpcn_step(cuda):
     np.testing.assert_allclose(mu.cpu().numpy(), mu_r, rtol=1e-9, atol=1e-9)
     np.testing.assert_allclose(sg.cpu().numpy(), sg_r, rtol=1e-9)
     assert nu == pytest.approx(nu_r, rel=1e-6) and 3.0 < nu < 5.5
+    # rows selected in place through the ancestor index with a stride (what the mutation hands over)
+    idx = np.sort(rng.integers(0, 60000, 50001))
+    rows = xs[idx[::3]]
+    mu, sg, nu = fit_student_t_diag(xt, torch.as_tensor(rows.mean(axis=0), device=cuda),
+                                    torch.as_tensor(rows.std(axis=0), device=cuda), idx=torch.as_tensor(idx, device=cuda),
+                                    stride=3)
+    mu_r, sg_r, nu_r = opcn.fit_student_t_diag(rows)
+    np.testing.assert_allclose(mu.cpu().numpy(), mu_r, rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(sg.cpu().numpy(), sg_r, rtol=1e-9)
+    assert nu == pytest.approx(nu_r, rel=1e-6)
 
     dims = 4
     prob = tg.quickstart_problem(dims)
