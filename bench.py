@@ -395,13 +395,23 @@ def run_e2e(args, sampler, prob, flow, dev):
     s_h2d, s_d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
     comp_done, d2h_done = [None, None], [None, None]
 
+    # A 19 GB copy occupies its copy engine for 0.4 s; the step's own small device -> host reads (search state, slot
+    # boundaries, step record) queue behind it.  Row chunks of ~256 MB bound that wait to a few milliseconds.
+    n_chunks = int(os.environ.get("ASP_E2E_CHUNKS", "64"))
+
+    def chunked_copy(dst, src):
+        rows = dst.shape[0]
+        step_rows = max((rows + n_chunks - 1) // n_chunks, 1) if dst.ndim == 2 else rows
+        for r0 in range(0, rows, step_rows):
+            dst[r0:r0 + step_rows].copy_(src[r0:r0 + step_rows], non_blocking=True)
+
     def upload(k):
         b = k % 2
         with torch.cuda.stream(s_h2d):
             if comp_done[b] is not None:
                 s_h2d.wait_event(comp_done[b])  # step k-2 has finished reading this input set
             for d, h in zip(dev_in[b], host_in):
-                d.copy_(h, non_blocking=True)
+                chunked_copy(d, h)
             e = torch.cuda.Event()
             e.record(s_h2d)
         return e
@@ -422,13 +432,13 @@ def run_e2e(args, sampler, prob, flow, dev):
             with torch.cuda.stream(s_d2h):
                 s_d2h.wait_event(comp_done[b])
                 for h, d in zip(host_out, (new.x, new.log_likelihood, new.log_prior, new.log_q)):
-                    h.copy_(d, non_blocking=True)
+                    chunked_copy(h, d)
                 d2h_done[b] = torch.cuda.Event()
                 d2h_done[b].record(s_d2h)
             up = nxt
         s_comp.wait_stream(s_d2h)
 
-    steps = max(2, min(args.steps, 5))
+    steps = max(2, min(args.steps, int(os.environ.get("ASP_E2E_STEPS", "20"))))  # fill + drain are inside the timed region
     run(1)
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -113,7 +113,7 @@ def test_integration_doc_stub_matches_the_abi():
         assert list(eval("[" + args + "]", {"__builtins__": {}}, env)) == list(_lib.SIGNATURES[name][1]), name  # noqa: S307
     for name in set(re.findall(r"\b(asp_[a-z0-9_]+)\b", text)):
         if name.rstrip("_") != name or name in ("asp_status", "asp_density_t", "asp_peer_t", "asp_transform_t",
-                                                "asp_beta_state_t", "asp_pcn_params_t", "asp_flow_t"):
+                                                "asp_beta_state_t", "asp_pcn_params_t", "asp_flow_t", "asp_flow_train_t"):
             continue
         candidates = [s for s in _lib.SIGNATURES if s == name or s.startswith(name)]
         assert candidates, f"INTEGRATION.md names {name}, which the header does not declare"
