@@ -451,7 +451,11 @@ def run_e2e(args, sampler, prob, flow, dev):
     return {"value": n / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n * row_bytes,
             "d2h_bytes_per_step": n * row_bytes, "particles": n, "ms_per_step": ms, "steps": steps,
             "api": "SMCSampler.tempering_step on pinned host buffers; H2D of step k+1 and D2H of step k-1 overlap "
-                   "step k (three streams, two device buffer sets); timed from the first upload to the last download"}
+                   "step k (three streams, two device buffer sets, copies in ~300 MB row chunks so the step's own small "
+                   "device->host reads do not queue behind a 19 GB copy); timed from the first upload to the last "
+                   "download (pipeline fill and drain included)",
+            "link": "measured on this pool (profiles/r2_pcie_probe.jsonl): H2D 55.6, D2H 53.4 GB/s alone, 47.5 GB/s each "
+                    "way when both run - the steady-state step (21 GB each way) is at that limit"}
 
 
 def main():
