@@ -16,7 +16,8 @@
 // 17x the algorithmic DRAM traffic - profiles/r2_ncu_flow_move.md).  The proposal is never stored: it is formed chunk
 // by chunk in a rolled loop (densities accumulated on the fly), its standardised image is parked in the thread's own
 // TMEM lane (tcgen05.st into the idle accumulator columns, read back with tcgen05.ld as the flow state), and an
-// accepted proposal is formed again from the same Philox counters and written over the current point.
+// accepted proposal is formed again - from its normals, parked in 64 further TMEM columns - by the NEXT pass over the
+// scratch tile (the following move's proposal loop, or the final store), on the chunk that pass reads anyway.
 // Four warpgroups per SM share one copy of the weights; while one waits on its MMAs the others run their fp64
 // proposal / density phase, so the tensor pipe, the XU (Philox / Box-Muller) and the fp64 pipe overlap.
 #include "density.cuh"
@@ -262,6 +263,7 @@ __global__ void __launch_bounds__(kFlowThreads* kMoveWG, 1) flow_move_kernel(con
         if (t_cur != t_cur) t_cur = ninf;
         bool moved = false;
         uint4 aw = make_uint4(0, 0, 0, 0);
+        bool pend = false;  // the last move was accepted and its proposal is not yet in the scratch tile
         for (int t = 0; t < n_moves; ++t) {
             double log_u;
             if constexpr (PHILOX) {
@@ -278,10 +280,21 @@ __global__ void __launch_bounds__(kFlowThreads* kMoveWG, 1) flow_move_kernel(con
             for (int c = 0; c < kMoveComp; ++c) d2[c] = 0.0;
             double xc[4];
             ld_g32(cur, xc);
+            const bool any_pend = __any_sync(0xffffffffu, pend);  // warp-uniform: the TMEM reads are .sync.aligned
 #pragma unroll 2
             for (int q = 0; q < NQ; ++q) {
                 double xi[4], nxt[4];
                 ld_g32(cur + (q + 1 < NQ ? q + 1 : q) * kChunk, nxt);  // the next chunk is in flight during this one
+                if (any_pend) {  // the previous move was accepted: its proposal is formed again here, on the chunk
+                                 // this move reads anyway, from the normals still parked in TMEM
+                    noise_recall(t - 1, row, q, xi);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const double xa = propose(xc[j], xi[j], lds2(&s_ref[q * 4 + j]));
+                        xc[j] = pend ? xa : xc[j];
+                    }
+                    if (pend) st_g32(cur + q * kChunk, xc);
+                }
                 noise_draw(t, row, pidx, q, xi);
                 float zf[4];
 #pragma unroll
@@ -381,29 +394,7 @@ __global__ void __launch_bounds__(kFlowThreads* kMoveWG, 1) flow_move_kernel(con
                 t_cur = t_new;
                 moved = true;
             }
-            if (__any_sync(0xffffffffu, acc)) {  // warp-uniform: the TMEM reads are .sync.aligned
-#pragma unroll 1
-                for (int g = 0; g < D / 16; ++g) {  // 16 dimensions at a time: four scratch chunks in flight
-                    double xo[4][4], xi[4][4];
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) ld_g32(cur + (g * 4 + c) * kChunk, xo[c]);
-                    if constexpr (PHILOX) {
-                        float zn[16];
-                        tmem_ld16(xi_taddr + (uint32_t)(g * 16), zn);
-#pragma unroll
-                        for (int k = 0; k < 16; ++k) xi[k >> 2][k & 3] = (double)zn[k];
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) ld_row32(A.prm.d_xi + ((size_t)t * A.n + row) * D + g * 16 + c * 4, xi[c]);
-                    }
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) xo[c][j] = propose(xo[c][j], xi[c][j], lds2(&s_ref[g * 16 + c * 4 + j]));
-                        if (acc) st_g32(cur + (g * 4 + c) * kChunk, xo[c]);
-                    }
-                }
-            }
+            pend = acc;  // the accepted point itself is written by the next pass over the scratch tile
             if (per_move) {
                 const unsigned int votes = __ballot_sync(0xffffffffu, acc);
                 if ((tid & 31) == 0 && votes) atomicAdd(&s_acc[t], __popc(votes));
@@ -414,10 +405,20 @@ __global__ void __launch_bounds__(kFlowThreads* kMoveWG, 1) flow_move_kernel(con
         {  // final point and its logs (a particle that never moved keeps its input logs bit for bit)
             double* dst = A.xo + row * D;
             double sp = 0.0, sl = 0.0;
-#pragma unroll 4
+            const bool any_pend = __any_sync(0xffffffffu, pend);
+#pragma unroll 2
             for (int q = 0; q < NQ; ++q) {
                 double v[4];
                 ld_g32(cur + q * kChunk, v);
+                if (any_pend) {  // the last move's accepted proposal
+                    double xi[4];
+                    noise_recall(n_moves - 1, row, q, xi);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const double xa = propose(v[j], xi[j], lds2(&s_ref[q * 4 + j]));
+                        v[j] = pend ? xa : v[j];
+                    }
+                }
                 if (live) st_row32(dst + q * 4, v[0], v[1], v[2], v[3]);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {

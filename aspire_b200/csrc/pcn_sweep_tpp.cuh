@@ -55,7 +55,8 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __device__ __forceinline__ void lse_push(double& m, double& acc, double t) {
     const double ninf = identity(OP_MAX);
     const double d = t - m;  // +inf on the first finite term
-    const double e = exp(-fabs(d));
+    const double ad = fabs(d);
+    const double e = ad < 746.0 ? exp(-ad) : 0.0;  // exp underflows to exactly 0 below -745.14: far components cost no exp
     const double up = fma(acc, e, 1.0), keep = acc + e;
     if (t > ninf) {
         acc = d > 0.0 ? up : keep;

@@ -515,7 +515,8 @@ def parity_check(comm: Comm, dev, n_total: int = 1_000_003, dims: int = 32, move
 
 def _host_buffer_leg(args, comm, engine, shard0, n_total, dev, unit):
     """The sharded step with HOST buffers: every rank uploads its slice from pinned host memory over its own
-    PCIe link, runs ``ShardedSMC.step`` and downloads its offspring; device-timed, max over ranks."""
+    PCIe link, runs ``ShardedSMC.step`` and downloads its offspring, consecutive steps software-pipelined as in
+    ``bench.py::run_e2e``; device-timed, max over ranks."""
     import psutil
 
     dims = shard0.x.shape[1]
@@ -523,7 +524,7 @@ def _host_buffer_leg(args, comm, engine, shard0, n_total, dev, unit):
     n_local = len(shard0)
     budget = int(0.2 * psutil.virtual_memory().available / comm.world / (2 * row_bytes))
     free_dev, _ = torch.cuda.mem_get_info(dev)
-    m = max(1, min(n_local, budget, int(0.6 * free_dev / (3 * row_bytes))))
+    m = max(1, min(n_local, budget, int(0.6 * free_dev / (4.6 * row_bytes))))  # two input sets + two output sets
     neg = torch.tensor([-m / n_local], dtype=torch.float64, device=dev)
     comm.all_reduce_max(neg)  # every rank uses the smallest fraction, so slices stay comparable
     m = max(1, int(n_local * float(-neg[0])))
@@ -534,30 +535,67 @@ def _host_buffer_leg(args, comm, engine, shard0, n_total, dev, unit):
     cap = int(m * 1.2) + 4096
     host_out = [torch.empty((cap, dims), dtype=torch.float64).pin_memory()] + [
         torch.empty(cap, dtype=torch.float64).pin_memory() for _ in range(3)]
-    dev_in = [torch.empty_like(h, device=dev) for h in host_in]
+    dev_in = [[torch.empty_like(h, device=dev) for h in host_in] for _ in range(2)]
     stream = torch.cuda.current_stream()
+    s_h2d, s_d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    comp_done, d2h_done = [None, None], [None, None]
     moved = [0, 0]
+    n_chunks = 16  # row chunks per copy: the step's small device -> host reads do not queue behind a multi-GB copy
 
-    def step():
-        for d, h in zip(dev_in, host_in):
-            d.copy_(h, non_blocking=True)
-        new, _ = engine.step(Shard(*dev_in), 0.0)
-        k = min(len(new), cap)
-        for h, t in zip(host_out, (new.x, new.log_l, new.log_p, new.log_q)):
-            h[:k].copy_(t[:k], non_blocking=True)
+    def chunked_copy(dst, src_):
+        rows = dst.shape[0]
+        step_rows = max((rows + n_chunks - 1) // n_chunks, 1) if dst.ndim == 2 else max(rows, 1)
+        for r0 in range(0, rows, step_rows):
+            dst[r0:r0 + step_rows].copy_(src_[r0:r0 + step_rows], non_blocking=True)
+
+    def upload(k):
+        b_ = k % 2
+        with torch.cuda.stream(s_h2d):
+            if comp_done[b_] is not None:
+                s_h2d.wait_event(comp_done[b_])  # step k-2 has finished reading this input set
+            for d, h in zip(dev_in[b_], host_in):
+                chunked_copy(d, h)
+            e = torch.cuda.Event()
+            e.record(s_h2d)
         moved[0] += m * row_bytes
-        moved[1] += k * row_bytes
+        return e
 
-    steps = max(1, min(args.steps, 3))
+    def run(n_steps):
+        """Software pipeline over three streams: the upload of step k+1 and the download of step k-1 overlap step k
+        (PCIe is full duplex); the engine's two output buffer sets alternate, so step k+2 waits for download k."""
+        up = upload(0)
+        for k in range(n_steps):
+            b_ = k % 2
+            nxt = upload(k + 1) if k + 1 < n_steps else None
+            stream.wait_event(up)
+            if d2h_done[b_] is not None:
+                stream.wait_event(d2h_done[b_])
+            new, _ = engine.step(Shard(*dev_in[b_]), 0.0)
+            comp_done[b_] = torch.cuda.Event()
+            comp_done[b_].record(stream)
+            kk = min(len(new), cap)
+            with torch.cuda.stream(s_d2h):
+                s_d2h.wait_event(comp_done[b_])
+                for h, t in zip(host_out, (new.x, new.log_l, new.log_p, new.log_q)):
+                    chunked_copy(h[:kk], t[:kk])
+                d2h_done[b_] = torch.cuda.Event()
+                d2h_done[b_].record(s_d2h)
+            moved[1] += kk * row_bytes
+            up = nxt
+        stream.wait_stream(s_d2h)
+
+    steps = max(2, min(args.steps, 10))
     engine.reset()  # a different particle count than the device-resident leg
-    step()
+    run(1)
     torch.cuda.synchronize()
     comm.barrier()
     moved[0] = moved[1] = 0
+    comp_done[:] = [None, None]
+    d2h_done[:] = [None, None]
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record(stream)
-    for _ in range(steps):
-        step()
+    s_h2d.wait_event(a)
+    run(steps)
     b.record(stream)
     torch.cuda.synchronize()
     comm.barrier()
@@ -569,7 +607,9 @@ def _host_buffer_leg(args, comm, engine, shard0, n_total, dev, unit):
     engine.reset()
     return {"value": float(tot[0]) / (ms * 1e-3), "unit": unit, "h2d_bytes_per_step": int(tot[1]),
             "d2h_bytes_per_step": int(tot[2]), "particles": int(tot[0]), "ms_per_step": ms, "steps": steps,
-            "api": "ShardedSMC.step on pinned host buffers, one PCIe link per rank (H2D + step + D2H timed, max over ranks)"}
+            "api": "ShardedSMC.step on pinned host buffers, one PCIe link per rank; upload of step k+1 and download of "
+                   "step k-1 overlap step k (three streams, two buffer sets, chunked copies); timed from the first upload "
+                   "to the last download, max over ranks"}
 
 
 # ---------------------------------------------------------------------------------
