@@ -235,3 +235,27 @@ def test_importance_sampler_fields(cpu):
     # Z = prod_j N(0.5; 0, 1 + 0.7^2): normalised Gaussian likelihood in x under a standard normal prior
     log_z = 3 * (-0.5 * math.log(2 * math.pi * 1.49) - 0.25 / (2 * 1.49))
     assert out.log_evidence == pytest.approx(log_z, abs=5 * out.log_evidence_error + 0.02)
+
+
+def test_step_fn_defaults_follow_the_reference(cpu):
+    """``MiniPCNSMC`` defaults to the Student-t step like the reference (smc/minipcn.py:48); the base class - the
+    north-star kernel - to plain pCN; an explicit choice wins; the tpCN mutation hands (mu, sigma, nu) of the fitted
+    Student-t reference to the sweep."""
+    from aspire_b200 import targets as tg
+    from aspire_b200.flows import DiagGaussianFlow
+    from aspire_b200.rng import PhiloxRNG
+    from aspire_b200.samplers import MiniPCNSMC, SMCSampler
+
+    dims = 4
+    prob = tg.quickstart_problem(dims, device=cpu)
+    flow = DiagGaussianFlow(dims, device=cpu, mean=[0.0] * dims, sigma=[1.3] * dims, rng=PhiloxRNG(2))
+    a = MiniPCNSMC(prob["like"], prob["prior"], dims, flow, rng=PhiloxRNG(3))
+    b = SMCSampler(prob["like"], prob["prior"], dims, flow, rng=PhiloxRNG(3))
+    a._configure_kernel({})
+    b._configure_kernel({})
+    assert (a.step_fn, b.step_fn) == ("tpcn", "pcn")
+    a._configure_kernel({"step_fn": "pcn"})
+    assert a.step_fn == "pcn"
+    out = a.sample(400, sampler_kwargs=dict(n_steps=2), store_sample_history=False)  # default kernel again: tpCN
+    assert a.step_fn == "tpcn" and len(a.history.tpcn_nu) == len(a.history.beta) and len(out.x) == 400
+    assert all(1.0 <= v <= 1e6 for v in a.history.tpcn_nu)
