@@ -438,3 +438,44 @@ def test_flow_sweep_is_the_route_of_the_c4_mutation(cuda):
     assert float(same.double().mean()) >= 0.999
     assert acc_a == pytest.approx(acc_b, abs=2e-3)
     f.check_error()
+
+
+def test_flow_sweep_is_deterministic_and_independent_of_the_split(cuda):
+    """Size-independent properties of asp_pcn_sweep_flow at 2e6 x 64-D (C4 shape): two launches give identical bits;
+    sweeping the two halves of the slot range separately (``index0`` = first slot of the half: the noise is keyed by the
+    global output slot) gives the same rows as sweeping them together; a particle that never moved keeps its row
+    and logs bit for bit."""
+    import torch
+
+    from aspire_b200 import ops
+    from aspire_b200 import targets as tg
+
+    dims, n, moves = 64, 2_000_000, 3
+    f, _ = _flow(dims, 3, cuda, seed=6)
+    f.std = torch.full((dims,), 2.5, dtype=torch.float64, device=cuda)
+    f._struct = None
+    pg = tg.gmm_problem(dims, device=cuda)
+    x, lq = f.sample_and_log_prob(n)
+    ll, lp = pg["like"].log_prob(x), pg["prior"].log_prob(x)
+    idx = torch.sort((ops.philox_uniform(6, 0, n, cuda) * n).to(torch.int64).clamp_(0, n - 1)).values
+    mu, sigma = ops.moments_to_mu_sigma(ops.weighted_moments(x[: 1 << 18]), dims)
+
+    def sweep(lo, hi):
+        prm = ops.make_pcn_params(0.02, 0.3, mu, sigma, moves, seed=5, stream0=7, index0=lo)
+        return ops.pcn_sweep_flow(x, ll, lp, lq, idx[lo:hi].contiguous(), pg["like"], pg["prior"], f.struct(), prm)
+
+    a, b = sweep(0, n), sweep(0, n)
+    for u, v in zip(a[:4], b[:4]):
+        assert torch.equal(u, v)
+    h = n // 2 + 77  # an uneven split that is not a multiple of the 128-particle tile
+    c, d = sweep(0, h), sweep(h, n)
+    for k in range(4):
+        assert torch.equal(a[k][:h], c[k]) and torch.equal(a[k][h:], d[k])
+    assert int(a[4].sum()) == int(c[4].sum()) + int(d[4].sum())
+    f.check_error()
+    stay = (a[0] == x[idx]).all(dim=1)
+    assert 0.0 < float(stay.double().mean()) < 0.9          # some never moved (acceptance < 1), most did
+    for k, src in ((1, ll), (2, lp), (3, lq)):
+        assert torch.equal(a[k][stay], src[idx][stay])
+    rate = int(a[4].sum()) / (moves * n)
+    assert 0.3 < rate < 0.99
