@@ -45,81 +45,18 @@ constexpr int flow_wg() { return D >= 64 ? 4 : 6; }
 template <int D>
 constexpr int flow_ctas_per_sm() { return 1; }
 
-// D = 64: the NEXT tile's rows are fetched while the current tile's GEMMs run.  At every stage of the chain (three per
-// layer) a thread cp.async-es two 32-byte chunks of its next row into a private 64-byte staging slot (no registers are
-// held across the wait), and at the following stage converts them and parks the four floats per chunk in its own lane
-// of 64 spare TMEM columns (tcgen05.st); the next tile then starts from one tcgen05.ld sweep instead of sixteen
-// dependent DRAM loads (the top stall of the round-2a kernel: profiles/r2_ncu_flow.md).
-template <int D>
-constexpr bool flow_prefetch() { return D == 64; }
-constexpr int kPfChunksPerStage = 2;
-
-__device__ __forceinline__ void pf_cp_async16(uint32_t smem_addr, const void* gptr) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
-}
-
-template <int D, bool INVERSE>
-struct RowPrefetch {
-    const double* src;        // this thread's next row (nullptr: nothing to fetch - uniform over the warpgroup)
-    unsigned char* slot;      // warpgroup staging: 16-byte piece p of thread t at (p * 128 + t) * 16
-    uint32_t park_taddr;      // TMEM lane address of the parked row
-    const double* s_mean;
-    const float* s_scale;
-    int tid;
-    __device__ __forceinline__ void operator()(int stage) const {
-        if (src == nullptr) return;
-        constexpr int NQ = D / 4;
-        if (stage > 0) {  // consume what the previous stage fetched
-            const int c0 = (stage - 1) * kPfChunksPerStage;
-            if (c0 < NQ) {
-                asm volatile("cp.async.wait_group 0;" ::: "memory");
-#pragma unroll
-                for (int c = 0; c < kPfChunksPerStage; ++c) {
-                    const double2 a = *reinterpret_cast<const double2*>(slot + ((size_t)(2 * c) * kFlowM + tid) * 16);
-                    const double2 b = *reinterpret_cast<const double2*>(slot + ((size_t)(2 * c + 1) * kFlowM + tid) * 16);
-                    const int j = (c0 + c) * 4;
-                    float v[4];
-                    if (INVERSE) {
-                        v[0] = (float)a.x; v[1] = (float)a.y; v[2] = (float)b.x; v[3] = (float)b.y;
-                    } else {
-                        v[0] = (float)(a.x - s_mean[j]) * s_scale[j];
-                        v[1] = (float)(a.y - s_mean[j + 1]) * s_scale[j + 1];
-                        v[2] = (float)(b.x - s_mean[j + 2]) * s_scale[j + 2];
-                        v[3] = (float)(b.y - s_mean[j + 3]) * s_scale[j + 3];
-                    }
-                    tmem_st4(park_taddr + (uint32_t)j, v);
-                }
-            }
-        }
-        const int c1 = stage * kPfChunksPerStage;
-        if (c1 < NQ) {
-#pragma unroll
-            for (int c = 0; c < kPfChunksPerStage; ++c) {
-                const double* g = src + (c1 + c) * 4;
-                pf_cp_async16(smem_u32(slot + ((size_t)(2 * c) * kFlowM + tid) * 16), g);
-                pf_cp_async16(smem_u32(slot + ((size_t)(2 * c + 1) * kFlowM + tid) * 16), g + 2);
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        }
-    }
-};
-
 template <int D, bool INVERSE>
 __global__ void __launch_bounds__(kFlowThreads * flow_wg<D>(), flow_ctas_per_sm<D>()) flow_kernel(const FlowArgs A) {
     using S = FlowSizes<D>;
     constexpr int HALF = S::kHalf;
     constexpr int NWG = flow_wg<D>();
-    constexpr bool kPf = flow_prefetch<D>();
-    constexpr int kTmemAll = kPf ? 512 : (NWG <= 4 ? 256 : 512);  // power of two >= 64 NWG (+ 64 parked columns each)
-    static_assert(!kPf || NWG * 2 * 64 <= 512, "parked rows need 64 more TMEM columns per warpgroup");
-    constexpr int kPfSlot = kPfChunksPerStage * 2 * kFlowM * 16;  // staging bytes per warpgroup
+    constexpr int kTmemAll = NWG == 1 ? 64 : (NWG == 2 ? 128 : (NWG <= 4 ? 256 : 512));  // power of two >= 64 NWG
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* s_w = smem;                                             // weights blob
     unsigned char* s_bb = smem + A.n_layers * S::kLayer;                   // bias blocks (bf16 hi / lo rows)
     unsigned char* s_ones = s_bb + A.n_layers * S::kBiasLayer;             // constant A operand of the bias step
     unsigned char* s_a_all = s_ones + S::kOnes;                            // NWG A tiles (16 KB each)
-    unsigned char* s_pf = s_a_all + NWG * kFlowM * kFlowH * 2;             // prefetch staging (kPf only)
-    double* s_mean = reinterpret_cast<double*>(s_pf + (kPf ? NWG * kPfSlot : 0));
+    double* s_mean = reinterpret_cast<double*>(s_a_all + NWG * kFlowM * kFlowH * 2);
     float* s_scale = reinterpret_cast<float*>(s_mean + D);                 // log_prob: 1 / std;  sample: std
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_scale + D);           // [0]: weights TMA, [1 + wg]: MMA
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 1 + NWG);
@@ -176,25 +113,12 @@ __global__ void __launch_bounds__(kFlowThreads * flow_wg<D>(), flow_ctas_per_sm<
     uint64_t* mma_bar = &s_bar[1 + wg];
     const uint32_t lane_taddr = tmem + ((uint32_t)(warp * 32) << 16);  // warp % 4 selects the 32-lane TMEM slab
 
-    const uint32_t park_taddr = lane_taddr - (uint32_t)(wg * S::kTmemCols) + (uint32_t)(NWG * S::kTmemCols + wg * 64);
-    bool parked = false;
     const int64_t n_tiles = (A.n + kFlowM - 1) / kFlowM;
     for (int64_t tile = (int64_t)blockIdx.x * NWG + wg; tile < n_tiles; tile += (int64_t)gridDim.x * NWG) {
         const int64_t row = tile * kFlowM + tid;
         const bool live = row < A.n;
         float z[D];
-        const int64_t next_tile = tile + (int64_t)gridDim.x * NWG;
-        const bool fetch_next = kPf && 2 * (3 * A.n_layers - 1) >= D / 4 && next_tile < n_tiles;  // enough stages
-        if (parked) {  // this tile's rows were converted and parked in TMEM during the previous tile
-            tmem_wait_st();
-#pragma unroll
-            for (int h = 0; h < D / 16; ++h) {
-                float v16[16];
-                tmem_ld16(park_taddr + h * 16, v16);
-#pragma unroll
-                for (int k = 0; k < 16; ++k) z[h * 16 + k] = v16[k];
-            }
-        } else {
+        {
             // a row is 8 D bytes, read 32 bytes (one sector) per instruction; the centring stays in fp64 (a parameter
             // can sit far from zero compared with its spread), the scaling is fp32
             const double* src = A.x + (live ? row : A.n - 1) * D;
@@ -213,26 +137,15 @@ __global__ void __launch_bounds__(kFlowThreads * flow_wg<D>(), flow_ctas_per_sm<
             for (int j = 0; j < D; ++j) base = fmaf(z[j], z[j], base);
         }
         float ladj = 0.f;
-        RowPrefetch<D, INVERSE> hook;
-        {
-            const int64_t nrow = next_tile * kFlowM + tid;
-            hook.src = fetch_next ? A.x + (nrow < A.n ? nrow : A.n - 1) * D : nullptr;
-            hook.slot = s_pf + (kPf ? wg * kPfSlot : 0);
-            hook.park_taddr = park_taddr;
-            hook.s_mean = s_mean;
-            hook.s_scale = s_scale;
-            hook.tid = tid;
-        }
         for (int li = 0; li < A.n_layers; ++li) {
             const int layer = INVERSE ? A.n_layers - 1 - li : li;
             if (layer & 1)
                 ok &= coupling_layer<D, INVERSE, true>(z, ladj, layer, s_w, s_a, s_ones, s_bb, mma_bar, tmem, lane_taddr,
-                                                       phase, tid, wg, hook, 3 * li);
+                                                       phase, tid, wg);
             else
                 ok &= coupling_layer<D, INVERSE, false>(z, ladj, layer, s_w, s_a, s_ones, s_bb, mma_bar, tmem, lane_taddr,
-                                                        phase, tid, wg, hook, 3 * li);
+                                                        phase, tid, wg);
         }
-        parked = fetch_next;
         // ---- outputs ----
         if (live) {
             if (INVERSE) {
@@ -268,7 +181,6 @@ template <int D>
 static size_t flow_smem_bytes(int n_layers) {
     using S = FlowSizes<D>;
     return (size_t)n_layers * (S::kLayer + S::kBiasLayer) + S::kOnes + (size_t)flow_wg<D>() * kFlowM * kFlowH * 2 +
-           (flow_prefetch<D>() ? (size_t)flow_wg<D>() * kPfChunksPerStage * 2 * kFlowM * 16 : 0) +
            D * 8 + D * 4 + (1 + flow_wg<D>()) * 8 + 16 + 128;
 }
 

@@ -105,14 +105,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// four fp32 values -> columns [taddr, taddr + 4) of this thread's TMEM lane
-__device__ __forceinline__ void tmem_st4(uint32_t taddr, const float (&v)[4]) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(__float_as_uint(v[0])),
-                 "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3]))
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
 // shared-memory matrix descriptor: no swizzle, K-major; LBO = stride between core
 // matrices along K, SBO = stride between 8-row groups; version 1 (sm_100)
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -201,18 +193,11 @@ __device__ __forceinline__ void wg_sync(int wg) { asm volatile("bar.sync %0, 128
 
 // One coupling layer for this thread's particle; ODD selects which half conditions which
 // (compile time, so z[] keeps static indices and stays in registers).
-// `hook(stage)` runs in every thread of the warpgroup after a GEMM has been issued and before its barrier is waited on
-// (stage = 3 * position of the layer in the chain + 0 / 1 / 2): work placed there overlaps the tensor pipe.
-struct NoHook {
-    __device__ __forceinline__ void operator()(int) const {}
-};
-
-template <int D, bool INVERSE, bool ODD, class Hook = NoHook>
+template <int D, bool INVERSE, bool ODD>
 __device__ __forceinline__ bool coupling_layer(float (&z)[D], float& ladj, int layer, const unsigned char* s_w,
                                                unsigned char* s_a, const unsigned char* s_ones,
                                                const unsigned char* s_bb, uint64_t* mma_bar, uint32_t tmem,
-                                               uint32_t lane_taddr, uint32_t& phase, int tid, int wg,
-                                               Hook hook = Hook(), int stage0 = 0) {
+                                               uint32_t lane_taddr, uint32_t& phase, int tid, int wg) {
     using S = FlowSizes<D>;
     constexpr int HALF = S::kHalf;
     constexpr bool odd = ODD;
@@ -242,7 +227,6 @@ __device__ __forceinline__ bool coupling_layer(float (&z)[D], float& ladj, int l
         tc_fence_after();
         issue_gemm<S::kKA, kFlowH>(tmem, s_a, w1, s_ones, bb1, mma_bar);
     }
-    hook(stage0);
     ok &= mbar_wait(mma_bar, phase);
     phase ^= 1;
     tc_fence_after();
@@ -261,7 +245,6 @@ __device__ __forceinline__ bool coupling_layer(float (&z)[D], float& ladj, int l
         tc_fence_after();
         issue_gemm<kFlowH, kFlowH>(tmem, s_a, w2, s_ones, bb2, mma_bar);
     }
-    hook(stage0 + 1);
     ok &= mbar_wait(mma_bar, phase);
     phase ^= 1;
     tc_fence_after();
@@ -280,7 +263,6 @@ __device__ __forceinline__ bool coupling_layer(float (&z)[D], float& ladj, int l
         tc_fence_after();
         issue_gemm<kFlowH, D>(tmem, s_a, w3, s_ones, bb3, mma_bar);
     }
-    hook(stage0 + 2);
     ok &= mbar_wait(mma_bar, phase);
     phase ^= 1;
     tc_fence_after();

@@ -60,6 +60,13 @@ __device__ __forceinline__ void st_g32(double* p, const double (&v)[4]) {
 template <int D>
 __host__ __device__ constexpr size_t move_scratch_doubles_per_wg() { return (size_t)kFlowM * D; }
 
+// four fp32 values -> columns [taddr, taddr + 4) of this thread's TMEM lane
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const float (&v)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(__float_as_uint(v[0])),
+                 "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3]))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
     uint32_t r[4];
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
@@ -440,6 +447,7 @@ __global__ void __launch_bounds__(kFlowThreads* kMoveWG, 1) flow_move_kernel(con
                 A.llo[row] = ll;
                 A.lpo[row] = lp;
                 A.lqo[row] = lq;
+                if (lq != lq) atomicAdd(&A.accepts[per_move ? n_moves : 1], 1ull);  // NaN log q (smc/minipcn.py:133)
             }
         }
     }

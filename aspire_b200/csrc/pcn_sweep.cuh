@@ -257,6 +257,7 @@ __global__ void __launch_bounds__(kBlock, ASP_SWEEP_MIN_BLOCKS) pcn_sweep_kernel
                 A.llo[i] = ll;
                 A.lpo[i] = lp;
                 A.lqo[i] = lq;
+                if (lq != lq) atomicAdd(&A.accepts[per_move ? n_moves : 1], 1ull);  // NaN log q (smc/minipcn.py:133)
             }
         }
     }

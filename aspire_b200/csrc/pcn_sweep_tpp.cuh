@@ -535,6 +535,7 @@ __global__ void __launch_bounds__(kTppBlock, tpp_min_blocks<DL>()) pcn_sweep_tpp
             A.llo[i] = ll;
             A.lpo[i] = lp;
             A.lqo[i] = lq;
+            if (lq != lq) atomicAdd(&A.accepts[per_move ? n_moves : 1], 1ull);  // NaN log q (smc/minipcn.py:133)
         }
         src = src_next;
         src_next = src_next2;

@@ -500,7 +500,8 @@ def pcn_sweep(x, log_l, log_p, log_q, idx, like, prior, q, prm, out=None):
     if out is None:
         out = (torch.empty(n, dims, dtype=torch.float64, device=x.device),
                *(torch.empty(n, dtype=torch.float64, device=x.device) for _ in range(3)))
-    accepts = torch.zeros(max(prm.n_moves, 1), dtype=torch.int64, device=x.device)
+    accepts = torch.zeros(prm.n_moves + 2, dtype=torch.int64, device=x.device)
+    prm._nan = accepts[1:2] if prm.reserved else accepts[prm.n_moves:prm.n_moves + 1]  # final log q that are NaN
     check(_lib.load().asp_pcn_sweep(x.data_ptr(), log_l.data_ptr(), log_p.data_ptr(), log_q.data_ptr(), _ptr(idx), n,
                                     dims, C.byref(like.struct()), C.byref(prior.struct()), C.byref(q.struct()),
                                     C.byref(prm), out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
@@ -551,7 +552,8 @@ def pcn_sweep_flow(x, log_l, log_p, log_q, idx, like, prior, flow_struct, prm, o
                *(torch.empty(n, dtype=torch.float64, device=x.device) for _ in range(3)))
     lib = _lib.load()
     ws = _sized_ws("flow_sweep", lib.asp_pcn_sweep_flow_workspace_bytes(dims), x.device)
-    accepts = torch.zeros(max(prm.n_moves, 1), dtype=torch.int64, device=x.device)
+    accepts = torch.zeros(prm.n_moves + 2, dtype=torch.int64, device=x.device)
+    prm._nan = accepts[1:2] if prm.reserved else accepts[prm.n_moves:prm.n_moves + 1]  # final log q that are NaN
     check(lib.asp_pcn_sweep_flow(x.data_ptr(), log_l.data_ptr(), log_p.data_ptr(), log_q.data_ptr(), _ptr(idx), n, dims,
                                  C.byref(like.struct()), C.byref(prior.struct()), C.byref(flow_struct), C.byref(prm),
                                  out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), out[3].data_ptr(),

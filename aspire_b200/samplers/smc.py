@@ -526,6 +526,7 @@ class SMCSampler(Sampler):
                                              and particles.x.data_ptr() % 16 == 0))
         if not fused and not self.rng.is_host:
             prm.reserved = 0  # the unfused kernels count accepts per move
+        fused_kernel = True  # a sweep kernel ran the whole mutation (and counted the NaN log q itself)
         if fused:
             x, ll, lp, lq, accepts = ops.pcn_sweep(particles.x, particles.log_likelihood, particles.log_prior,
                                                    particles.log_q, idx, self._log_likelihood, self._log_prior,
@@ -544,6 +545,7 @@ class SMCSampler(Sampler):
                 mark("pcn_sweep")
             self.n_likelihood_evaluations += n * n_moves
         else:
+            fused_kernel = False
             if idx is not None:
                 x, ll, lp, lq = ops.gather_rows(particles.x, idx, particles.log_likelihood, particles.log_prior,
                                                 particles.log_q)
@@ -573,7 +575,14 @@ class SMCSampler(Sampler):
                 ll2 = self.log_likelihood(prop)
                 ops.pcn_accept(x, ll, lp, lq, xp, ll2, lp2, lq2, prm, t, accepts)
             accepts = accepts[:n_moves]
-        acc = float(accepts.sum()) / max(n_moves * n, 1)
+        # the sweeps count the final log q that are NaN themselves (asp_pcn_sweep: the entry behind the accept counts):
+        # one device -> host read serves the acceptance and the reference's NaN check (smc/minipcn.py:133-134)
+        nan_count = getattr(prm, "_nan", None) if fused_kernel else None
+        if nan_count is not None:
+            acc_sum, n_nan = torch.cat([accepts.sum().reshape(1), nan_count]).tolist()
+        else:
+            acc_sum, n_nan = float(accepts.sum()), None
+        acc = acc_sum / max(n_moves * n, 1)
         self._check_flow()  # right after the mutation's own device -> host read
         self.history.mcmc_acceptance.append(acc)
         self.history.rho.append(self.rho)
@@ -582,7 +591,7 @@ class SMCSampler(Sampler):
             self.rho = float(min(max(self.rho * math.exp(acc - target), 1e-3), 1.0))
         out = SMCSamples(x, log_likelihood=ll, log_prior=lp, log_q=lq, beta=beta, parameters=self.parameters,
                          device=self.device)
-        if bool(torch.isnan(lq).any()):
+        if (n_nan > 0) if n_nan is not None else bool(torch.isnan(lq).any()):
             raise ValueError("Log proposal contains NaN values")  # smc/minipcn.py:133-134
         return out
 

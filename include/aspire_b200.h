@@ -327,8 +327,10 @@ typedef struct asp_pcn_params {
 
 /* Fused sweep: particle i starts from row d_idx[i] of the inputs (d_idx NULL
  * = identity, i.e. no resampling gather), runs n_moves accept/reject moves
- * with built-in densities and writes the final state.  d_accepts[n_moves]
- * (uint64) is incremented by the per-move accept counts (caller zeroes it).
+ * with built-in densities and writes the final state.  d_accepts[n_moves + 1]
+ * (uint64, caller zeroes it) is incremented by the per-move accept counts; the entry behind them - d_accepts[n_moves],
+ * or d_accepts[1] when params->reserved = 1 keeps only the total in d_accepts[0] - counts the particles whose final
+ * log q is NaN (the reference raises on them, smc/minipcn.py:133-134: no separate pass over the logs is needed).
  * params->nu > 0 runs tpCN moves in the same kernel (gamma variates drawn in-kernel, or params->d_gamma with
  * supplied noise; d_scale is ignored): same trajectory as asp_tpcn_scales + asp_pcn_propose + asp_pcn_accept.
  * Built for the dims asp_pcn_sweep_tpcn_supported reports (4, 8, 16, 32, 64); other dims return ASP_ERR_ARG. */
