@@ -187,7 +187,7 @@ SIGNATURES = {
     "asp_sorted_lower_bound": (C.c_int, [C.c_uint64, C.c_uint32, _P, _I64, _I64, _P, _I32, _P, _P]),
     "asp_gather_rows": (C.c_int, [_P, _I32, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _P]),
     "asp_moments_workspace_bytes": (C.c_size_t, [_I32]),
-    "asp_weighted_moments": (C.c_int, [_P, _I32, _P, _P, _I64, _D, _D, _P, _P, _P]),
+    "asp_weighted_moments": (C.c_int, [_P, _I32, _P, _I64, _P, _I64, _D, _D, _P, _P, _P]),
     "asp_moments_finish": (C.c_int, [_P, _I32, _D, _P, _P, _P]),
     "asp_pcn_sweep": (
         C.c_int,

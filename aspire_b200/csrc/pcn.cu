@@ -205,7 +205,7 @@ struct MomentsWs {
 
 template <int G>
 __global__ void __launch_bounds__(kBlock) moments_kernel(const double* __restrict__ x, int dims,
-                                                         const int64_t* __restrict__ idx,
+                                                         const int64_t* __restrict__ idx, int64_t istride,
                                                          const double* __restrict__ d, int64_t n, double dbeta,
                                                          double c, double* __restrict__ out, MomentsWs* ws) {
     extern __shared__ double sm[];  // [warps][G][9]
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(kBlock) moments_kernel(const double* __restric
     for (int k = 0; k < 9; ++k) acc[k] = 0.0;
     for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G; i < n; i += groups) {
         double v[kDPL];
-        const int64_t src = idx ? idx[i] : i;
+        const int64_t src = idx ? idx[i * istride] : i * istride;
         row_load(x, src, dims, lane, vec, v);
         const double w = d ? exp(dbeta * d[src] - c) : 1.0;
         acc[0] += w;
@@ -470,15 +470,15 @@ size_t asp_moments_workspace_bytes(int32_t dims) {
     return 256 + sizeof(double) * (size_t)kNumSMs * 4 * (1 + 2 * g * kDPL);
 }
 
-int asp_weighted_moments(const double* d_x, int32_t dims, const int64_t* d_idx, const double* d_d, int64_t n,
-                         double dbeta, double c, double* d_moments, void* ws, void* stream) {
+int asp_weighted_moments(const double* d_x, int32_t dims, const int64_t* d_idx, int64_t idx_stride, const double* d_d,
+                         int64_t n, double dbeta, double c, double* d_moments, void* ws, void* stream) {
     ASP_DEVICE_OR_RETURN();
     ASP_REQUIRE(d_x && d_moments && ws, "null pointer");
-    ASP_REQUIRE(n > 0 && dims > 0 && dims <= 32 * kDPL, "bad sizes");
+    ASP_REQUIRE(n > 0 && dims > 0 && dims <= 32 * kDPL && idx_stride >= 1, "bad sizes");
     const int g = group_size_for(dims);
     int grid = grid_for(n * g, 1, kBlock, 4);
     const size_t smem = sizeof(double) * (kBlock / 32) * g * 9;
-    ASP_DISPATCH_G(g, (moments_kernel<G><<<grid, kBlock, smem, (cudaStream_t)stream>>>(d_x, dims, d_idx, d_d, n, dbeta, c,
+    ASP_DISPATCH_G(g, (moments_kernel<G><<<grid, kBlock, smem, (cudaStream_t)stream>>>(d_x, dims, d_idx, idx_stride, d_d, n, dbeta, c,
                                                                                       d_moments, (MomentsWs*)ws)));
     return check_launch("asp_weighted_moments");
 }

@@ -341,7 +341,7 @@ class ShardedSMC:
         stride = max(n_total // max(self.moment_particles, 1), 1)
         first = (-j_lo) % stride
         if first < n_out:
-            mom = ops.weighted_moments(shard.x, idx=idx[first::stride].contiguous())
+            mom = ops.weighted_moments(shard.x, idx=idx, stride=stride, first=first)
         else:
             mom = torch.zeros(1 + 2 * dims, dtype=torch.float64, device=dev)
         comm.all_reduce_sum(mom)

@@ -367,7 +367,8 @@ class CouplingFlow(Flow):
         x, logq = ops.flow_sample(self.struct(), u)
         return self._extract(x), (logq + self._pad_const if self._pad else logq)
 
-    # -- training scaffolding (torch autograd over the same tensors) -------------------
+    # -- torch restatement of the forward pass: the autograd route of fit(native=False) and the reference the device
+    #    fit kernels are tested against ----------------------------------------------------------------------------
     def _torch_forward(self, x32, layers):
         half = self.kdims // 2
         z = (x32 - self.mean.float()) / self.std.float()
@@ -392,10 +393,10 @@ class CouplingFlow(Flow):
         flows/torch/flows.py:170-325): affine data transform from the samples (mean, unbiased std -
         ``transforms.py:618-621``), random permutation, train / validation split, Adam, optional gradient
         clipping, cosine annealing and early stopping, best-validation weights restored at the end.
-        On a CUDA device the optimisation itself - forward, backward, Adam - runs in the library's own kernels over
-        the flow's fp32 master weights (``asp_flow_fit_step``, csrc/flow_fit.cu); ``native=False`` (and
-        the CPU, where only the host logic can be tested) uses torch autograd over the same tensors, which is also
-        the reference the kernels' gradients are tested against."""
+        The optimisation itself - forward, backward, Adam - runs in the library's own kernels over the flow's fp32
+        master weights (``asp_flow_fit_step``, csrc/flow_fit.cu).  ``native=False`` is test
+        infrastructure: torch autograd over the same tensors, the reference the kernels' gradients are checked against
+        and the way the CPU suite exercises this method's host logic."""
         x = samples.x if hasattr(samples, "x") else samples
         x = torch.as_tensor(x, dtype=torch.float64, device=self.device).clone()
         if bool(torch.isnan(x).any()):
@@ -416,7 +417,7 @@ class CouplingFlow(Flow):
         n_val = int(validation_fraction * n)
         x_train, x_val = (x32[:-n_val], x32[-n_val:]) if n_val > 0 else (x32, x32[:0])
         logger.info(f"Training on {x_train.shape[0]} samples, validating on {x_val.shape[0]} samples.")
-        native = bool(kwargs.get("native", self.device.type == "cuda"))
+        native = bool(kwargs.get("native", True))  # no silent CPU route: the default fails loudly without the library
         hist = FlowHistory()
         best_val, best_state, best_epoch = float("inf"), None, 0
         if native:

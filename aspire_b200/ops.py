@@ -445,18 +445,26 @@ def gather_rows(x, idx, log_l=None, log_p=None, log_q=None):
 
 
 # ---- K8 -------------------------------------------------------------------
-def weighted_moments(x, d=None, dbeta: float = 0.0, c: float = 0.0, idx=None) -> torch.Tensor:
+def weighted_moments(x, d=None, dbeta: float = 0.0, c: float = 0.0, idx=None, stride: int = 1, first: int = 0) -> torch.Tensor:
     """-> device tensor [1 + 2 D] = {sum w, sum w x_j, sum w x_j^2} over rows ``idx`` (all rows
-    when None), w = exp(dbeta d - c) (w = 1 when ``d`` is None)."""
+    when None), w = exp(dbeta d - c) (w = 1 when ``d`` is None).  ``stride`` / ``first``: only the rows
+    ``idx[first::stride]`` (``range(first, n, stride)`` without ``idx``), read in place - no strided copy of the index."""
     x = _f64(x, "x")
     dims = x.shape[1]
     idx = None if idx is None else _i64(idx, "idx")
-    n = x.shape[0] if idx is None else idx.numel()
+    n_rows = x.shape[0] if idx is None else idx.numel()
+    stride, first = int(stride), int(first)
+    n = max((n_rows - first + stride - 1) // stride, 0)
     d = None if d is None else _f64(d, "d")
     out = torch.empty(1 + 2 * dims, dtype=torch.float64, device=x.device)
+    if n == 0:
+        return out.zero_()
+    if idx is None and first:
+        raise AspireB200Error("weighted_moments: `first` needs an index array")
     ws = _sized_ws("moments", _lib.load().asp_moments_workspace_bytes(dims), x.device)
-    check(_lib.load().asp_weighted_moments(x.data_ptr(), dims, _ptr(idx), _ptr(d), n, dbeta, c, out.data_ptr(), ws.data_ptr(),
-                                           _stream()), "asp_weighted_moments")
+    idx_ptr = None if idx is None else idx.data_ptr() + 8 * first
+    check(_lib.load().asp_weighted_moments(x.data_ptr(), dims, idx_ptr, stride, _ptr(d), n, dbeta, c, out.data_ptr(),
+                                           ws.data_ptr(), _stream()), "asp_weighted_moments")
     return out
 
 

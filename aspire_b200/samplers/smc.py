@@ -495,14 +495,7 @@ class SMCSampler(Sampler):
         # resampler are ascending, so a strided sample is spread over the whole genealogy (a prefix would not be)
         m_use = min(n, int(self.sampler_kwargs.get("moment_particles", 1 << 22)))
         stride = max(n // max(m_use, 1), 1)
-        if stride > 1:
-            sub = (idx[::stride] if idx is not None
-                   else torch.arange(0, n, stride, dtype=torch.int64, device=self.device)).contiguous()
-            mom = ops.weighted_moments(particles.x, idx=sub)
-        elif idx is not None:
-            mom = ops.weighted_moments(particles.x, idx=idx)
-        else:
-            mom = ops.weighted_moments(particles.x)
+        mom = ops.weighted_moments(particles.x, idx=idx, stride=stride)  # the strided rows are read in place
         mu, sigma = ops.moments_to_mu_sigma(mom, dims, floor=1e-150)
         tpcn = getattr(self, "step_fn", "pcn") == "tpcn"
         nu = 0.0

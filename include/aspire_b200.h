@@ -292,11 +292,12 @@ int asp_gather_rows(const double* d_x, int32_t dims, const int64_t* d_idx, int64
  * src/aspire/samplers/smc/base.py:507-519.  Step spec: oracle/pcn.py (parity
  * with minipcn itself is UNPINNED - the package is absent).
  * Reference measure moments: d_moments[1 + 2*dims] = {sum w, sum w x_j, sum w x_j^2}
- * over rows r_i = d_idx ? d_idx[i] : i, i < n, with w = d_d ? exp(dbeta d_d[r_i] - c) : 1
- * (d_idx given, d_d NULL: plain moments of the resampled ensemble, never materialised). */
+ * over rows r_i = d_idx ? d_idx[i idx_stride] : i idx_stride, i < n, with w = d_d ? exp(dbeta d_d[r_i] - c) : 1
+ * (d_idx given, d_d NULL: plain moments of the resampled ensemble, never materialised; idx_stride > 1: every
+ * idx_stride-th offspring - the strided subsample the sampler fits the reference measure to, read in place). */
 size_t asp_moments_workspace_bytes(int32_t dims);
-int asp_weighted_moments(const double* d_x, int32_t dims, const int64_t* d_idx, const double* d_d, int64_t n,
-                         double dbeta, double c, double* d_moments, void* ws, void* stream);
+int asp_weighted_moments(const double* d_x, int32_t dims, const int64_t* d_idx, int64_t idx_stride, const double* d_d,
+                         int64_t n, double dbeta, double c, double* d_moments, void* ws, void* stream);
 
 /* mu_j = sum w x_j / sum w,  sigma_j = max(sqrt(max(sum w x_j^2 / sum w - mu_j^2, 0)), sigma_floor) */
 int asp_moments_finish(const double* d_moments, int32_t dims, double sigma_floor, double* d_mu, double* d_sigma,

@@ -170,9 +170,9 @@ def search_multinomial(cdf, u, guided=None):
     return _t(_np(cdf).searchsorted(_np(u), side="right").astype(np.int64))
 
 
-def weighted_moments(x, d=None, dbeta=0.0, c=0.0, idx=None):
+def weighted_moments(x, d=None, dbeta=0.0, c=0.0, idx=None, stride=1, first=0):
     xn = _np(x)
-    rows = xn if idx is None else xn[_np(idx)]
+    rows = xn[first::stride] if idx is None else xn[_np(idx)[first::stride]]
     return _t(np.concatenate([[float(len(rows))], rows.sum(0), (rows * rows).sum(0)]))
 
 

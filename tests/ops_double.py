@@ -135,9 +135,8 @@ class Doubles:
         return (x[idx].contiguous(), *(None if t is None else t[idx].contiguous() for t in (a, b, c)))
 
     @staticmethod
-    def weighted_moments(x, d=None, dbeta=0.0, c=0.0, idx=None):
-        if idx is not None:
-            x = x[idx]
+    def weighted_moments(x, d=None, dbeta=0.0, c=0.0, idx=None, stride=1, first=0):
+        x = x[idx[first::stride]] if idx is not None else x[first::stride]
         return torch.cat([torch.tensor([float(len(x))], dtype=F64), x.sum(0), (x * x).sum(0)])
 
     @staticmethod

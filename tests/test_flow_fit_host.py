@@ -1,6 +1,8 @@
 """``CouplingFlow.fit`` follows the reference's training protocol (``ZukoFlow.fit``,
 src/aspire/flows/torch/flows.py:170-325): data transform, split, history, best-validation restore, early stop.
-Runs on the CPU (the optimiser is torch autograd; only log_prob / sample need the B200 kernels)."""
+Runs on the CPU through ``native=False`` - the torch-autograd route that also serves as the reference of the device
+fit kernels (``asp_flow_fit_step``; their test is ``tests/test_gpu_flow.py::test_native_fit_*``); the default route is
+the kernels and has no CPU path."""
 import numpy as np
 import pytest
 import torch
@@ -18,7 +20,7 @@ def test_fit_protocol_and_history():
     z[:, 8:] = 0.9 * z[:, :8] + 0.3 * z[:, 8:]      # second half depends on the first: what a coupling layer learns
     x = z * np.linspace(0.5, 3.0, 16) + 2.0
     f = _flow()
-    h = f.fit(x, n_epochs=12, batch_size=250, validation_fraction=0.2, lr=2e-3)
+    h = f.fit(x, n_epochs=12, batch_size=250, validation_fraction=0.2, lr=2e-3, native=False)
     assert len(h.training_loss) == len(h.validation_loss) == 12
     assert h.training_loss[-1] < h.training_loss[0] and min(h.validation_loss) < h.validation_loss[0]
     np.testing.assert_allclose(f.mean.numpy(), x.mean(axis=0), rtol=1e-12)
@@ -34,7 +36,7 @@ def test_fit_early_stopping_clip_and_annealing():
     rng = np.random.default_rng(1)
     x = rng.normal(size=(600, 16))
     f = _flow()
-    h = f.fit(x, n_epochs=200, batch_size=200, patience=2, clip_grad=1.0, lr_annealing=True, lr=5e-2)
+    h = f.fit(x, n_epochs=200, batch_size=200, patience=2, clip_grad=1.0, lr_annealing=True, lr=5e-2, native=False)
     assert len(h.training_loss) < 200                  # stopped early
     best = int(np.argmin(h.validation_loss))
     assert len(h.validation_loss) - 1 - best >= 2
@@ -44,10 +46,10 @@ def test_fit_rejects_non_finite_data():
     x = np.zeros((100, 16))
     x[3, 5] = np.nan
     with pytest.raises(ValueError, match="NaN"):
-        _flow().fit(x, n_epochs=1)
+        _flow().fit(x, n_epochs=1, native=False)
     x[3, 5] = np.inf
     with pytest.raises(ValueError, match="infinite"):
-        _flow().fit(x, n_epochs=1)
+        _flow().fit(x, n_epochs=1, native=False)
 
 
 @pytest.mark.parametrize("dims", [2, 4, 5, 16, 23, 40])
@@ -66,7 +68,7 @@ def test_padding_coordinates_are_inert(dims):
     k = f.kdims
     assert k in (16, 32, 64) and k >= dims and f._pad == k - dims and f.dims == dims
     assert len(set(f._pos.tolist())) == dims and int((f._pos < k // 2).sum()) == (dims + 1) // 2  # both halves used
-    h = f.fit(x, n_epochs=3, batch_size=200, lr=5e-3)
+    h = f.fit(x, n_epochs=3, batch_size=200, lr=5e-3, native=False)
     assert np.isfinite(h.training_loss).all() and min(h.training_loss) < h.training_loss[0] + 0.1
     for t, layer in enumerate(f.layers):
         dead = ~f._out_mask(t)
@@ -95,3 +97,12 @@ def test_padding_coordinates_are_inert(dims):
     assert float(z[:, ~f._real].abs().max()) == 0.0 if f._pad else True
     assert f._pad_const == pytest.approx(0.5 * (k - dims) * math.log(2 * math.pi))
     assert torch.isfinite(lq_pad).all()
+
+
+def test_default_fit_route_is_the_device_kernels_and_has_no_cpu_path():
+    """Without ``native=False`` the optimisation runs in ``asp_flow_fit_step``; on a CPU tensor it fails loudly."""
+    from aspire_b200 import AspireB200Error
+
+    x = np.random.default_rng(2).normal(size=(300, 16))
+    with pytest.raises((AspireB200Error, RuntimeError, OSError)):
+        _flow().fit(x, n_epochs=1)
