@@ -351,6 +351,9 @@ def run_gpu(args):
     e2e = run_e2e(args, sampler, prob, flow, dev) if not args.no_e2e else None
     cpu = cpu_baseline(args.cpu_particles, dims, moves) if not args.no_cpu else None
 
+    torch.cuda.empty_cache()
+    others = other_configs() if not args.no_extras else None
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
@@ -359,8 +362,44 @@ def run_gpu(args):
         "step_roofline": step_roofline, "cpu_baseline": cpu, "phase_ms": phase_ms,
         "beta_after_step": beta, "acceptance": sampler.history.mcmc_acceptance[-1],
         "n_beta_evals": sampler.history.n_beta_evals[-1],
+        # the other single-GPU configurations of BASELINE.json, measured in the same run (informational: the metric
+        # above is the contract; each entry is a line of benchmarks/micro.py, device-timed after its own warm-up)
+        "other_configs": others,
     }
     print(json.dumps(line))
+
+
+def other_configs():
+    """BASELINE.json configs[1], [3], [4] on this GPU through benchmarks/micro.py: C2 (importance reweighting of 1e6 x 16-D
+    flow-proposed particles), C4 (one tempering step of 1e7 x 64-D mixture particles with the tcgen05 coupling flow as
+    the proposal, flow inside the move) and C5 at 1e8 particles (exact CDF + multinomial / systematic ancestors).  Never
+    fails the bench line: an exception is recorded in place of the numbers."""
+    import contextlib
+    import importlib.util
+    import io
+    import types
+
+    import torch
+
+    spec = importlib.util.spec_from_file_location("asp_micro", os.path.join(ROOT, "benchmarks", "micro.py"))
+    out = {}
+    try:
+        micro = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(micro)
+    except Exception as e:  # noqa: BLE001
+        return {"error": f"benchmarks/micro.py: {e!r}"}
+    base = dict(n=0, iters=5, moves=10, dims=0, sorted_idx=True, nu=0.0, numpy_max=0, gpus=1, only="", dump="")
+    for key, fn, over in (("C2_importance", "importance", {}), ("C4_flow_proposal_step", "c4", {"iters": 6}),
+                          ("C5_resample_1e8", "resample", {"n": 100_000_000, "iters": 3})):
+        buf = io.StringIO()
+        try:
+            with contextlib.redirect_stdout(buf):
+                getattr(micro, fn)(types.SimpleNamespace(**{**base, **over}))
+            out[key] = [json.loads(l) for l in buf.getvalue().splitlines() if l.startswith("{")]
+        except Exception as e:  # noqa: BLE001
+            out[key] = {"error": repr(e)}
+        torch.cuda.empty_cache()
+    return out
 
 
 def run_e2e(args, sampler, prob, flow, dev):
@@ -472,6 +511,7 @@ def main():
     ap.add_argument("--cpu-particles", type=int, default=1_000_000,
                     help="bounded CPU sample: ~8 s per step on 16 threads (torch-CPU), ~20 s on one core (numpy)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the C2 / C4 / C5 lines (other_configs)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
