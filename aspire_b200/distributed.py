@@ -616,7 +616,7 @@ def _host_buffer_leg(args, comm, engine, shard0, n_total, dev, unit):
 # bench.py --gpus N (N > 1): launched by torch.distributed.run, one rank per GPU
 # ---------------------------------------------------------------------------------
 def run_bench(args, rank, world, dev, metric, unit, workload_config, bytes_per_particle, measured_peaks, ClockSampler,
-              cpu_baseline):
+              cpu_baseline, other_configs=None):
     import json
 
     import torch.distributed as dist
@@ -697,6 +697,11 @@ def run_bench(args, rank, world, dev, metric, unit, workload_config, bytes_per_p
     e2e = None
     if not getattr(args, "no_e2e", False):
         e2e = _host_buffer_leg(args, comm, engine, shard0, n_total, dev, unit)
+    others = None
+    if other_configs is not None:  # collective: every rank runs it, rank 0 reports (bench.py: the sharded C5 lines)
+        del shard0
+        torch.cuda.empty_cache()
+        others = other_configs(comm, dev, engine._peer)
     if rank == 0:
         peaks, kind = measured_peaks()
         value = n_total / (ms_per_step * 1e-3)
@@ -724,7 +729,7 @@ def run_bench(args, rank, world, dev, metric, unit, workload_config, bytes_per_p
             "cpu_baseline": None, "phase_ms": phase_ms,
             "phase_ms_per_rank": [[round(v, 3) for v in row] for row in per_rank],
             "step_ms_per_rank": [[round(v, 2) for v in row] for row in step_ms_per_rank], "beta_after_step": rec.beta, "acceptance": rec.acceptance,
-            "n_local_out": rec.n_local_out, "multi_gpu_parity": parity,
+            "n_local_out": rec.n_local_out, "multi_gpu_parity": parity, "other_configs": others,
         }
         print(json.dumps(line))
     dist.destroy_process_group()

@@ -240,7 +240,8 @@ def run_gpu(args):
         from aspire_b200 import distributed as dist_engine
 
         return dist_engine.run_bench(args, rank, world, dev, METRIC, UNIT, workload_config,
-                                     algorithmic_bytes_per_particle, measured_peaks, ClockSampler, cpu_baseline)
+                                     algorithmic_bytes_per_particle, measured_peaks, ClockSampler, cpu_baseline,
+                                     other_configs=None if args.no_extras else other_configs_sharded)
 
     n, dims, moves = args.particles, args.dims, args.moves
     prob = tg.rosenbrock_problem(dims, device=dev)
@@ -400,6 +401,21 @@ def other_configs():
             out[key] = {"error": repr(e)}
         torch.cuda.empty_cache()
     return out
+
+
+def other_configs_sharded(comm, dev, peer):
+    """BASELINE.json configs[4] at this rank count: exact CDF + ancestors of 1e8 and 1e9 particles sharded over the
+    ranks (benchmarks/micro.py::resample_sharded_lines).  Collective; an exception is recorded, never raised - but it is
+    raised on every rank or none (the failure modes are import / allocation errors, identical on all ranks)."""
+    import importlib.util
+
+    try:
+        spec = importlib.util.spec_from_file_location("asp_micro", os.path.join(ROOT, "benchmarks", "micro.py"))
+        micro = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(micro)
+        return {"C5_resample_sharded": micro.resample_sharded_lines(comm, dev, [10**8, 10**9], 5, peer=peer)}
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)}
 
 
 def run_e2e(args, sampler, prob, flow, dev):

@@ -142,17 +142,28 @@ def _resample_sharded(args, world):
 
     import torch.distributed as dist
 
-    from aspire_b200.distributed import Comm, PeerMailboxes, ShardedSMC
+    from aspire_b200.distributed import Comm
 
     local_rank = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist.init_process_group("nccl", device_id=dev)
     comm = Comm()
-    r = comm.rank
-    eng = ShardedSMC(comm, None, None, None, seed=7)
-    eng._peer = PeerMailboxes.create(comm, dev)
     sizes = [args.n] if args.n else [10**5, 10**6, 10**7, 10**8, 10**9]
+    for line in resample_sharded_lines(comm, dev, sizes, args.iters):
+        print(json.dumps(line))
+    dist.destroy_process_group()
+
+
+def resample_sharded_lines(comm, dev, sizes, iters_small, peer=False):
+    """The sharded C5 measurement on an existing communicator (every rank calls it; rank 0 gets the lines).
+    ``peer``: the engine's mailboxes (False: create them here)."""
+    from aspire_b200.distributed import PeerMailboxes, ShardedSMC
+
+    world, r = comm.world, comm.rank
+    eng = ShardedSMC(comm, None, None, None, seed=7)
+    eng._peer = PeerMailboxes.create(comm, dev) if peer is False else peer
+    lines = []
     for n in sizes:
         base, rem = divmod(n, world)
         n_local, start = base + (1 if r < rem else 0), r * base + min(r, rem)
@@ -182,7 +193,7 @@ def _resample_sharded(args, world):
             j0, j1 = max(min(j0, n), 0), max(min(j1, n), 0)
             return ops.search_systematic(cdf, 0.37, max(j1 - j0, 0), j0=j0, m_total=n)
 
-        iters = args.iters if n <= 10**8 else 3
+        iters = iters_small if n <= 10**8 else 3
         res = {}
         for name, fn in (("cdf", cdf_only), ("multinomial_sorted_uniforms", multinomial), ("systematic", systematic)):
             for _ in range(3):
@@ -201,14 +212,14 @@ def _resample_sharded(args, world):
         if r == 0:
             for name in ("multinomial_sorted_uniforms", "systematic"):
                 t = res[name]
-                print(json.dumps({"bench": f"resample_{name}", "config": "C5", "n_gpus": world, "particles": n,
-                                  "ms_cdf": res["cdf"], "ms_total": t, "indices_per_s": n / t * 1e3,
-                                  "algorithmic_gbs_per_gpu": 32 * n / world / t / 1e6,
-                                  "hbm_frac": 32 * n / world / t / 1e6 / PEAKS["hbm_gbs"],
-                                  "note": "sharded: exact CDF carry chain over " + ("NVLink peer memory" if eng._peer else "NCCL")
-                                          + ", owner-computes ancestors, device-timed, max over ranks"}))
+                lines.append({"bench": f"resample_{name}", "config": "C5", "n_gpus": world, "particles": n,
+                              "ms_cdf": res["cdf"], "ms_total": t, "indices_per_s": n / t * 1e3,
+                              "algorithmic_gbs_per_gpu": 32 * n / world / t / 1e6,
+                              "hbm_frac": 32 * n / world / t / 1e6 / PEAKS["hbm_gbs"],
+                              "note": "sharded: exact CDF carry chain over " + ("NVLink peer memory" if eng._peer else "NCCL")
+                                      + ", owner-computes ancestors, device-timed, max over ranks"})
         del p
-    dist.destroy_process_group()
+    return lines
 
 
 def importance(args):
