@@ -15,6 +15,7 @@
 
 #include "common.cuh"
 #include "density.cuh"
+#include "student_t_math.cuh"
 
 namespace asp {
 
@@ -23,18 +24,6 @@ struct TFitWs {
     unsigned int pad[63];
     double partial[1];  // [blocks][2 + 2 * G * kDPL]
 };
-
-// digamma for x > 0: recurrence up to x >= 10, then the asymptotic series (error < 1e-15)
-__device__ __forceinline__ double digamma_pos(double x) {
-    double r = 0.0;
-    while (x < 10.0) {
-        r -= 1.0 / x;
-        x += 1.0;
-    }
-    const double i = 1.0 / x, i2 = i * i;
-    const double series = i2 * (1.0 / 12.0 - i2 * (1.0 / 120.0 - i2 * (1.0 / 252.0 - i2 * (1.0 / 240.0 - i2 * (1.0 / 132.0)))));
-    return r + log(x) - 0.5 * i - series;
-}
 
 template <int G>
 __global__ void __launch_bounds__(kBlock) student_t_em_kernel(const double* __restrict__ x, int dims,
@@ -134,29 +123,13 @@ __global__ void __launch_bounds__(kBlock) student_t_em_kernel(const double* __re
     __syncthreads();
     const double sw = tot[0];
     for (int j = threadIdx.x; j < dims; j += blockDim.x) {
-        const double a = tot[2 + j], b = tot[2 + G * kDPL + j];
-        state[j] = state[j] + a / sw;
-        state[dims + j] = sqrt(fmax(b - a * a / sw, 0.0) / (double)m);
+        double mu_j = state[j], sg_j;
+        student_t_mstep(sw, tot[2 + j], tot[2 + G * kDPL + j], (double)m, mu_j, sg_j);
+        state[j] = mu_j;
+        state[dims + j] = sg_j;
     }
     if (threadIdx.x == 0) {
-        const double hd = 0.5 * (nu + (double)dims);
-        const double konst = 1.0 + tot[1] / (double)m + digamma_pos(hd) - log(hd);
-        auto f = [&](double v) { return -digamma_pos(0.5 * v) + log(0.5 * v) + konst; };
-        double out;
-        if (f(nu_max) > 0.0) {  // Gaussian-like data: the likelihood keeps growing with nu
-            out = nu_max;
-        } else if (f(nu_min) < 0.0) {
-            out = nu_min;
-        } else {
-            double lo = nu_min, hi = nu_max;
-            for (int it = 0; it < 60; ++it) {
-                const double mid = sqrt(lo * hi);
-                if (f(mid) > 0.0) lo = mid;
-                else hi = mid;
-            }
-            out = sqrt(lo * hi);
-        }
-        state[2 * dims] = out;
+        state[2 * dims] = student_t_nu(nu, dims, tot[1] / (double)m, nu_min, nu_max);
         ws->ticket = 0;
     }
 }
