@@ -28,7 +28,11 @@ int require_device();
         if (_rc != ASP_OK) return _rc;          \
     } while (0)
 
-constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+// B200: 2 dies x 74 SMs.  A sizing constant only: grids are capped at a multiple of it and the per-block workspace
+// slots are dimensioned by that cap, no kernel relies on all its blocks being resident at once (the cross-block steps
+// are last-block tickets or single-block chains), so a part with another SM count runs correctly, merely with grids
+// sized for 148 SMs.
+constexpr int kNumSMs = 148;
 constexpr int kBlock = 256;
 constexpr int kMaxPartialBlocks = kNumSMs * 8;  // persistent grids never exceed this
 
