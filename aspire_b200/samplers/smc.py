@@ -420,7 +420,7 @@ class SMCSampler(Sampler):
         f = self.prior_flow
         return (not tpcn and self.sampler_kwargs.get("flow_sweep", True) and type(f) is CouplingFlow and not f._pad
                 and isinstance(self._log_likelihood, Density) and isinstance(self._log_prior, Density)
-                and self.rho < 1.0 and n_moves <= 256 and particles.x.data_ptr() % 32 == 0
+                and n_moves <= 256 and particles.x.data_ptr() % 32 == 0  # (rho = 1, the independence proposal, included)
                 and ops.pcn_sweep_flow_supported(self.dims, self._log_likelihood, self._log_prior))
 
     def _mutate_preconditioned(self, particles: SMCSamples, beta: float, n_moves: int, idx, mark) -> SMCSamples:

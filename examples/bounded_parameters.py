@@ -11,6 +11,10 @@ proposal flow lives on the logit image of the bounded amplitude (no proposal mas
 stays inside the bounds and the phase wraps around.  Callables receive a `Samples` whose `x` is a torch tensor.
 """
 import math
+import os
+import sys
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))  # run from a checkout
 
 import torch
 

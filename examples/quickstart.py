@@ -8,6 +8,10 @@ namespace ``xp``; here ``xp`` is torch).  With Python callables the pCN moves ru
 the callables, one accept kernel per move); pass ``aspire_b200.targets`` densities instead to get the fused sweep.
 """
 import math
+import os
+import sys
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))  # run from a checkout
 
 import torch
 

@@ -479,3 +479,68 @@ def test_flow_sweep_is_deterministic_and_independent_of_the_split(cuda):
         assert torch.equal(a[k][stay], src[idx][stay])
     rate = int(a[4].sum()) / (moves * n)
     assert 0.3 < rate < 0.99
+
+
+def test_flow_proposal_example_runs_through_the_flow_sweep(cuda, capsys):
+    """examples/flow_proposal.py: Aspire.fit on the device, then SMC with the learned flow as proposal on a bimodal
+    16-D target; every mutation goes through asp_pcn_sweep_flow (checked on the call counter), evidence and mode
+    masses come out right."""
+    import importlib.util
+    import os
+
+    from aspire_b200 import _lib
+
+    spec = importlib.util.spec_from_file_location("flow_proposal", os.path.join(os.path.dirname(__file__), "..", "examples",
+                                                                             "flow_proposal.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    calls = []
+    orig = _lib.check
+
+    def counting(rc, what=""):
+        calls.append(what)
+        return orig(rc, what)
+
+    from aspire_b200 import ops
+
+    ops.check, old = counting, ops.check
+    try:
+        posterior, log_z, left = mod.main(60_000)
+    finally:
+        ops.check = old
+    assert "asp_pcn_sweep_flow" in calls and "asp_pcn_propose_eval" not in calls and "asp_pcn_propose" not in calls
+    assert posterior.log_evidence == pytest.approx(log_z, abs=5 * posterior.log_evidence_error + 0.15)
+    assert 0.4 < left < 0.6
+    assert "tempering steps" in capsys.readouterr().out
+
+
+def test_flow_sweep_with_the_independence_proposal(cuda):
+    """rho = 1 (where the step-size adaptation saturates): x' = mu + sigma xi does not depend on the current point;
+    the flow sweep takes it (no division by sqrt(1 - rho^2) anywhere) and still equals the per-move chain."""
+    import torch
+
+    from aspire_b200 import ops
+    from aspire_b200 import targets as tg
+
+    dims, n, moves = 32, 4000, 4
+    rng = np.random.default_rng(3)
+    f, _ = _flow(dims, 3, cuda, seed=8)
+    f.std = torch.full((dims,), 1.8, dtype=torch.float64, device=cuda)
+    f._struct = None
+    L = tg.GaussianDensity(rng.normal(0.3, 0.2, dims), 1.1, dims, device=cuda)
+    P = tg.GaussianDensity(0.0, 4.0, dims, device=cuda)
+    x = _t(rng.normal(0.0, 1.5, (n, dims)), cuda)
+    ll, lp, lq = L.log_prob(x), P.log_prob(x), f.log_prob(x)
+    mu, sigma = _t(np.full(dims, 0.2), cuda), _t(np.full(dims, 1.3), cuda)
+    mk = lambda: ops.make_pcn_params(0.6, 1.0, mu, sigma, moves, seed=2, stream0=9)  # noqa: E731
+    out = ops.pcn_sweep_flow(x, ll, lp, lq, None, L, P, f.struct(), mk())
+    prm = mk()
+    st = [x.clone(), ll.clone(), lp.clone(), lq.clone()]
+    acc = torch.zeros(moves, dtype=torch.int64, device=cuda)
+    for t in range(moves):
+        xp, ll2, lp2, dr = ops.pcn_propose_eval(st[0], L, P, prm, t)
+        ops.pcn_accept_scalar(st[0], st[1], st[2], st[3], xp, ll2, lp2, f.log_prob(xp), dr, prm, t, acc)
+    f.check_error()
+    same = torch.isclose(out[0], st[0], rtol=1e-12, atol=1e-12).all(dim=1)
+    assert float(same.double().mean()) >= 0.998 and abs(int(out[4].sum()) - int(acc.sum())) <= 8
+    assert 0.01 < int(acc.sum()) / (moves * n) < 0.9
