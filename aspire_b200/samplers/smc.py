@@ -42,6 +42,14 @@ class BetaScheduleError(RuntimeError):
     """smc/base.py:26"""
 
 
+# Bounds of the between-sweep step-size adaptation (oracle/pcn.py::adapt_rho).  The upper bound stops just short of
+# the independence proposal rho = 1: with a high acceptance the adaptation saturates after a step or two, and at
+# rho < 1 every mutation keeps its fastest kernel (the particle-per-thread sweep carries sqrt(1 - rho^2) (x - mu) as its
+# state and cannot represent rho = 1; an explicit rho = 1 is still honoured, through the general kernels).  The step
+# x' = mu + 1.4e-3 (x - mu) + 0.999999 sigma xi is a valid pCN step like any other.
+RHO_MIN, RHO_MAX = 1e-3, 1.0 - 1e-6
+
+
 class SMCSampler(Sampler):
     default_beta_tolerance = DEFAULT_BETA_TOLERANCE
     default_step_fn = "pcn"  # the base class runs plain pCN (the north-star kernel); MiniPCNSMC: the reference's "tpcn"
@@ -472,7 +480,7 @@ class SMCSampler(Sampler):
         self.history.rho.append(self.rho)
         if self.sampler_kwargs.get("adapt_rho", True):
             target = self.sampler_kwargs["target_acceptance_rate"]
-            self.rho = float(min(max(self.rho * math.exp(acc - target), 1e-3), 1.0))
+            self.rho = float(min(max(self.rho * math.exp(acc - target), RHO_MIN), RHO_MAX))
         x = T.inverse(z)[0]
         out = SMCSamples(x, beta=beta, parameters=self.parameters, device=self.device)
         out.log_q = torch.as_tensor(self.prior_flow.log_prob(out.x), dtype=torch.float64, device=self.device).contiguous()
@@ -581,7 +589,7 @@ class SMCSampler(Sampler):
         self.history.rho.append(self.rho)
         if self.sampler_kwargs.get("adapt_rho", True):
             target = self.sampler_kwargs["target_acceptance_rate"]
-            self.rho = float(min(max(self.rho * math.exp(acc - target), 1e-3), 1.0))
+            self.rho = float(min(max(self.rho * math.exp(acc - target), RHO_MIN), RHO_MAX))
         out = SMCSamples(x, log_likelihood=ll, log_prior=lp, log_q=lq, beta=beta, parameters=self.parameters,
                          device=self.device)
         if (n_nan > 0) if n_nan is not None else bool(torch.isnan(lq).any()):

@@ -405,11 +405,12 @@ def full(args):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         out, hist = a.sample_posterior(n, sampler="smc", return_history=True, rng=PhiloxRNG(2 + rep),
-                                       sampler_kwargs=dict(n_steps=args.moves), store_sample_history=False)
+                                       sampler_kwargs=dict(n_steps=args.moves, **({"step_fn": args.only} if args.only else {})),
+                                       store_sample_history=False)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
     steps = len(hist.beta)
-    print(json.dumps({"bench": "smc_full_run", "particles": n, "dims": dims, "moves": args.moves, "tempering_steps": steps,
+    print(json.dumps({"bench": "smc_full_run", "step_fn": args.only or "tpcn (MiniPCNSMC default)", "particles": n, "dims": dims, "moves": args.moves, "tempering_steps": steps,
                       "seconds": dt, "ms_per_step": dt / steps * 1e3, "particle_steps_per_s": n * steps / dt,
                       "log_evidence": float(out.log_evidence), "log_evidence_error": float(out.log_evidence_error),
                       "mean_acceptance": float(sum(hist.mcmc_acceptance) / steps),

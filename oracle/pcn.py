@@ -93,7 +93,7 @@ def sweep(x, log_l, log_p, log_q, *, like, prior, q, beta, mu, sigma, rho, n_mov
 
 
 def adapt_rho(rho: float, acceptance: float, target: float = 0.234,
-              rho_min: float = 1e-3, rho_max: float = 1.0) -> float:
+              rho_min: float = 1e-3, rho_max: float = 1.0 - 1e-6) -> float:
     """Between-sweep step-size adaptation (ours): multiplicative
     Robbins-Monro step in log rho towards the target acceptance."""
     return float(min(max(rho * np.exp(acceptance - target), rho_min), rho_max))
