@@ -175,3 +175,53 @@ def test_peer_descriptor_layout_matches_the_header():
     assert _lib.PeerDesc.rank.offset == 8 * max_peers and _lib.PeerDesc.world.offset == 8 * max_peers + 4
     # the chain region (csrc/scan_exact.cu: kChainBase = 2 * 8 * 16 + 8, counter 8 doubles later) fits in the box
     assert (2 * max_peers * 16 + 8 + 8 + 1) * 8 <= _lib.PEER_BOX_BYTES
+
+
+def _long_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import cpu_backend
+
+    from aspire_b200.distributed import Comm, ShardedSMC, Shard
+
+    n, dims, steps = 2000, 2, 200
+    prob = problems.gaussian_problem(dims)
+    x, ll, lp, lq = problems.draw(prob, n, 21)
+    order = np.argsort(-ll)  # rank 0 starts with the high-likelihood half: the first steps are as skewed as it gets
+    x, ll, lp, lq = x[order], ll[order], lp[order], lq[order]
+    a, b = rank * n // world, (rank + 1) * n // world
+    t = lambda v: torch.as_tensor(np.ascontiguousarray(v))  # noqa: E731
+    # a low efficiency target makes every resampling step degenerate (few distinct ancestors): the ranks' shares of
+    # the offspring fluctuate strongly from step to step
+    eng = ShardedSMC(Comm(), prob["like"], prob["prior"], prob["q"], backend=cpu_backend, seed=5, n_moves=1, rho=0.5,
+                     target_efficiency=0.05, headroom=0.0)
+    shard = Shard(t(x[a:b]), t(ll[a:b]), t(lp[a:b]), t(lq[a:b]))
+    sizes, produced, slots = [], [], []
+    for _ in range(steps):
+        shard, rec = eng.step(shard, 0.0)  # re-temper the current ensemble from beta = 0 every time
+        sizes.append(len(shard))
+        produced.append(rec.n_local_out)
+        slots.append(shard.slot0)
+    ret[rank] = dict(sizes=sizes, produced=produced, slots=slots, finite=bool(torch.isfinite(shard.x).all()))
+    dist.destroy_process_group()
+
+
+def test_two_hundred_skewed_steps_keep_the_shards_balanced():
+    """200 consecutive steps on two ranks with strongly fluctuating offspring shares (efficiency target 0.05, the
+    ensemble initially sorted by likelihood): no step raises, every shard holds exactly N / G particles after every
+    step (the surplus is shipped peer to peer, nothing depends on head-room), and the exchange really happens."""
+    import sys
+
+    sys.path.insert(0, os.path.dirname(__file__))
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_long_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
+    r0, r1 = ret[0], ret[1]
+    assert r0["sizes"] == [1000] * 200 and r1["sizes"] == [1000] * 200
+    assert set(r0["slots"]) == {0} and set(r1["slots"]) == {1000}
+    assert all(p0 + p1 == 2000 for p0, p1 in zip(r0["produced"], r1["produced"]))
+    surplus = np.abs(np.array(r0["produced"]) - 1000)
+    assert surplus.max() >= 50 and (surplus > 0).mean() > 0.9  # rows crossed the shard boundary in almost every step
+    assert r0["finite"] and r1["finite"]
