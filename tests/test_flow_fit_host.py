@@ -106,3 +106,37 @@ def test_default_fit_route_is_the_device_kernels_and_has_no_cpu_path():
     x = np.random.default_rng(2).normal(size=(300, 16))
     with pytest.raises((AspireB200Error, RuntimeError, OSError)):
         _flow().fit(x, n_epochs=1)
+
+
+@pytest.mark.parametrize("dims", [16, 5, 64])
+def test_native_trainer_packs_the_master_weights_in_the_header_layout(dims):
+    """``_NativeTrainer`` hands ``asp_flow_fit_step`` one flat fp32 buffer per quantity, laid out per layer as
+    W1[64, K/2] | b1[64] | W2[64, 64] | b2[64] | W3[K, 64] | b3[K] (include/aspire_b200.h): its size is what the
+    library reports, ``unflatten`` inverts the packing, and the padding mask marks the inert rows.  Host functions of
+    the library only - no kernel is launched."""
+    from aspire_b200.flows import CouplingFlow, _NativeTrainer
+
+    f = CouplingFlow(dims, device="cpu", n_layers=3, seed=2)
+    for layer in f.layers:  # distinct values everywhere, so a transposition or an offset error cannot cancel
+        for v in layer.values():
+            v.copy_(torch.arange(v.numel(), dtype=torch.float32).reshape(v.shape) * 1e-3 + float(v.numel()))
+    f._hold_padding()
+    tr = _NativeTrainer(f, 128)
+    k, h = f.kdims, f.hidden
+    per_layer = h * (k // 2) + h + h * h + h + k * h + k
+    assert tr.w.numel() == 3 * per_layer == tr.m.numel() == tr.v.numel() == tr.g.numel()
+    assert tr.t.kdims == k and tr.t.hidden == 64 and tr.t.n_layers == 3 and tr.t.batch_cap == 128
+    back = tr.unflatten(tr.w)
+    for a, b in zip(back, f.layers):
+        for name in ("W1", "b1", "W2", "b2", "W3", "b3"):
+            assert torch.equal(a[name], b[name].float())
+    # first layer's block starts with W1 row-major
+    assert torch.equal(tr.w[: h * (k // 2)].reshape(h, k // 2), f.layers[0]["W1"].float())
+    assert tr.mask.shape == (3, k // 2) and tr.mask.dtype == torch.uint8
+    if f._pad:
+        assert int(tr.mask.sum()) < tr.mask.numel() and tr.t.d_out_mask
+        for t in range(3):
+            assert torch.equal(tr.mask[t].bool(), f._out_mask(t)[: k // 2])
+    else:
+        assert int(tr.mask.sum()) == tr.mask.numel() and not tr.t.d_out_mask
+    assert tr.ws.numel() >= 4 * 128 * k
